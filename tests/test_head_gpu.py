@@ -1,0 +1,76 @@
+"""Contrastive head kernels (pool, latent projection, fused InfoNCE fwd+bwd) vs the oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lat(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1)
+
+
+def test_clip_loss_reference_fixture(cuda_dev):
+    """demo_tests/test_loss_type.py:14-15 fixed vectors; known answers from SURVEY.md 8c."""
+    from vit_exp_b200 import ops
+    x = torch.tensor([[.1, .2], [.3, .4], [.5, .6], [.7, .8]], device=cuda_dev)
+    y = torch.tensor([[.2, .3], [.3, .6], [.4, .9], [.2, .5]], device=cuda_dev)
+    out, _ = ops.clip_loss_fwd_bwd(x, y, torch.zeros(1, device=cuda_dev), b_local=4, row0=0)
+    assert abs(out[0].item() - 0.34436899) < 2e-6
+    out, _ = ops.clip_loss_fwd_bwd(x, y, torch.ones(1, device=cuda_dev), b_local=4, row0=0)
+    assert abs(out[0].item() - 0.35895544) < 2e-6
+
+
+@pytest.mark.parametrize("N,W,rank", [(8, 1, 0), (64, 8, 3), (256, 4, 1), (1000, 8, 7), (4096, 8, 5)])
+def test_clip_loss_vs_oracle(cuda_dev, N, W, rank):
+    from oracle import ctclip_oracle as orc
+    from vit_exp_b200 import ops
+    d = 512
+    B = N // W
+    T, I = _lat(N, d, 0), _lat(N, d, 1)
+    lt = torch.tensor(1.0)
+    ref = orc.clip_loss_and_local_grads(T.double(), I.double(), lt.double(), B, rank)
+    out, dl = ops.clip_loss_fwd_bwd(T.to(cuda_dev), I.to(cuda_dev), lt.reshape(1).to(cuda_dev), b_local=B, row0=rank * B)
+    out, dl = out.cpu().double(), dl.cpu().double()
+    assert abs(out[0] - ref["loss"]) / abs(ref["loss"]) < 1e-5
+    assert abs(out[1] - ref["dlog_temp"]) <= 1e-5 * abs(ref["dlog_temp"]) + 1e-7
+    for got, want in ((dl[0], ref["dT_local"]), (dl[1], ref["dI_local"])):
+        assert (got - want).abs().max() <= 1e-4 * want.abs().max() + 1e-9
+
+
+def test_pool_latent_fwd_bwd(cuda_dev):
+    from oracle import ctclip_oracle as orc
+    from vit_exp_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, n, dim, dl = 3, 1000, 512, 512
+    x = torch.randn(B, n, dim, generator=g)
+    W = torch.randn(dl, dim, generator=g) * dim ** -0.5
+    dlat = torch.randn(B, dl, generator=g)
+    ref = orc.pooled_latent_fwd_bwd(x.double(), W.double(), dlat.double())
+    xc, Wc = x.to(cuda_dev), W.to(cuda_dev)
+    pooled = ops.mean_pool(xc)
+    lat, rn = ops.latent_fwd(pooled, Wc)
+    dW, dpool = ops.latent_bwd(dlat.to(cuda_dev), lat, rn, pooled, Wc)
+    assert (pooled.cpu().double() - ref["pooled"]).abs().max() < 1e-5
+    assert (lat.cpu().double() - ref["latent"]).abs().max() < 1e-5
+    assert (dW.cpu().double() - ref["dW"]).abs().max() <= 1e-4 * ref["dW"].abs().max()
+    assert (dpool.cpu().double() - ref["dpooled"]).abs().max() <= 1e-4 * ref["dpooled"].abs().max()
+
+
+def test_latent_strided_cls_rows(cuda_dev):
+    """text branch: CLS rows enc_text[:, 0, :] (ct_clip.py:1309) are read in place (row stride L*768)."""
+    from vit_exp_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    enc = torch.randn(4, 16, 768, generator=g).to(cuda_dev)
+    W = (torch.randn(512, 768, generator=g) * 768 ** -0.5).to(cuda_dev)
+    lat, _ = ops.latent_fwd(enc[:, 0, :], W)
+    ref = torch.nn.functional.normalize(enc[:, 0, :] @ W.T, dim=-1)
+    assert (lat - ref).abs().max().item() < 1e-5
+
+
+def test_pair_logits(cuda_dev):
+    from vit_exp_b200 import ops
+    t, i = _lat(36, 512, 0).to(cuda_dev), _lat(1, 512, 1).to(cuda_dev)
+    lt = torch.tensor([1.0], device=cuda_dev)
+    out = ops.pair_logits(t, i[0].contiguous(), lt)
+    assert (out - (t @ i[0]) * lt.exp()).abs().max().item() < 1e-5

@@ -1,0 +1,419 @@
+// Contrastive head: token mean-pool, latent projection + l2norm, and the fused symmetric
+// InfoNCE forward/backward (ct_clip.py:1280-1388; closed form in SURVEY.md appendix B).
+//
+// Loss pipeline (every rank evaluates the full N x N matrix redundantly, as the reference does):
+//   pass 1  clip_tile_stats : 64x64 logit tiles in fp32; per-tile online (max, sum e^x, sum x e^x)
+//                             for rows and columns; diagonal. Logits stay in registers/smem.
+//   pass 2  clip_reduce     : merge tile partials -> row/col log-sum-exp, loss, d(log temp).
+//   pass 3  clip_grad_tiles : recompute logits for the rank's rows / columns only and emit
+//                             G = dloss/dS stripes [b_local, N];  pass 4: dT = s G I, dI = s G^T T.
+#include "common.cuh"
+#include "sgemm.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- mean pool
+__global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict__ pooled,
+                                 long long n, int dim, long long tok_per_block) {
+    const int b = blockIdx.y;
+    const long long t0 = (long long)blockIdx.x * tok_per_block;
+    long long t1 = t0 + tok_per_block;
+    if (t1 > n) t1 = n;
+    const float inv = 1.0f / (float)n;
+    for (int c = threadIdx.x * 4; c < dim; c += blockDim.x * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* p = x + ((long long)b * n + t0) * dim + c;
+        for (long long t = t0; t < t1; ++t, p += dim) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float* o = pooled + (long long)b * dim + c;
+        atomicAdd(o + 0, acc.x * inv);
+        atomicAdd(o + 1, acc.y * inv);
+        atomicAdd(o + 2, acc.z * inv);
+        atomicAdd(o + 3, acc.w * inv);
+    }
+}
+
+// ---------------------------------------------------------------- latent projection + l2norm
+// one CTA (256 threads) per sample
+__global__ void latent_fwd_kernel(const float* __restrict__ x, long long x_stride,
+                                  const float* __restrict__ W, float* __restrict__ latent,
+                                  float* __restrict__ rnorm, int din, int dl) {
+    extern __shared__ float sm[];
+    float* xs = sm;            // [din]
+    float* raw = sm + din;     // [dl]
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < din; i += blockDim.x) xs[i] = x[(long long)b * x_stride + i];
+    __syncthreads();
+    for (int j = warp; j < dl; j += nwarp) {
+        const float* w = W + (long long)j * din;
+        float acc = 0.f;
+        for (int i = lane; i < din; i += 32) acc = fmaf(__ldg(w + i), xs[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) raw[j] = acc;
+    }
+    __syncthreads();
+    float ss = 0.f;
+    for (int j = threadIdx.x; j < dl; j += blockDim.x) ss += raw[j] * raw[j];
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < nwarp; ++w) tot += red[w];
+    const float rn = 1.0f / fmaxf(sqrtf(tot), 1e-12f);       // F.normalize eps (ct_clip.py:70-71)
+    for (int j = threadIdx.x; j < dl; j += blockDim.x) latent[(long long)b * dl + j] = raw[j] * rn;
+    if (threadIdx.x == 0) rnorm[b] = rn;
+}
+
+// draw[b] = rnorm_b * (dlat_b - lat_b * <lat_b, dlat_b>) ; dx[b, i] = sum_j draw[b, j] W[j, i]
+__global__ void latent_bwd_dx_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
+                                     const float* __restrict__ rnorm, const float* __restrict__ W,
+                                     float* __restrict__ dx, long long dx_stride, int din, int dl) {
+    extern __shared__ float sm[];
+    float* draw = sm;          // [dl]
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    float dot = 0.f;
+    for (int j = threadIdx.x; j < dl; j += blockDim.x)
+        dot += lat[(long long)b * dl + j] * dlat[(long long)b * dl + j];
+    dot = warp_sum(dot);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    float coef = 0.f;
+    for (int w = 0; w < nwarp; ++w) coef += red[w];
+    const float rn = rnorm[b];
+    for (int j = threadIdx.x; j < dl; j += blockDim.x)
+        draw[j] = rn * (dlat[(long long)b * dl + j] - lat[(long long)b * dl + j] * coef);
+    __syncthreads();
+    for (int i = threadIdx.x; i < din; i += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < dl; ++j) acc = fmaf(draw[j], __ldg(W + (long long)j * din + i), acc);
+        dx[(long long)b * dx_stride + i] = acc;
+    }
+}
+
+// dW[j, i] = sum_b draw[b, j] x[b, i]; one CTA per 8 output rows j
+__global__ void latent_bwd_dw_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
+                                     const float* __restrict__ rnorm, const float* __restrict__ x,
+                                     long long x_stride, float* __restrict__ dW, int B, int din,
+                                     int dl) {
+    extern __shared__ float sm[];
+    float* coef = sm;                 // [B]
+    float* draw = sm + B;             // [8][B]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int b = warp; b < B; b += nwarp) {
+        float dot = 0.f;
+        for (int j = lane; j < dl; j += 32)
+            dot += lat[(long long)b * dl + j] * dlat[(long long)b * dl + j];
+        dot = warp_sum(dot);
+        if (lane == 0) coef[b] = dot;
+    }
+    __syncthreads();
+    const int j0 = blockIdx.x * 8;
+    for (int t = threadIdx.x; t < 8 * B; t += blockDim.x) {
+        const int jj = t / B, b = t % B;
+        const int j = j0 + jj;
+        draw[jj * B + b] = j < dl ? rnorm[b] * (dlat[(long long)b * dl + j] -
+                                               lat[(long long)b * dl + j] * coef[b])
+                                  : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < din; i += blockDim.x) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int b = 0; b < B; ++b) {
+            const float xv = x[(long long)b * x_stride + i];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) acc[jj] = fmaf(draw[jj * B + b], xv, acc[jj]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+            if (j0 + jj < dl) dW[(long long)(j0 + jj) * din + i] = acc[jj];
+    }
+}
+
+// ---------------------------------------------------------------- contrastive loss
+struct Stat { float m, l, w; };     // online max, sum exp(x-m), sum x exp(x-m)
+
+// pass 1: grid (col blocks, row blocks); S = s * T I^T
+__global__ void __launch_bounds__(256)
+clip_tile_stats_kernel(const float* __restrict__ T, const float* __restrict__ I,
+                       const float* __restrict__ log_temp, float* __restrict__ rowpart,
+                       float* __restrict__ colpart, float* __restrict__ diag, int N, int d) {
+    __shared__ float As[16][68];
+    __shared__ float Bs[16][68];
+    __shared__ float St[64][65];
+    const int cb = blockIdx.x, rb = blockIdx.y;
+    const int m0 = rb * 64, n0 = cb * 64;
+    float acc[4][4];
+    sgemm_tile_64x64<true>(T, d, I, d, m0, n0, N, N, d, acc, As, Bs);
+    const float s = expf(*log_temp);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) St[ty * 4 + i][tx * 4 + j] = acc[i][j] * s;
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < 128) {
+        const bool is_row = t < 64;
+        const int idx = t & 63;
+        const int g = (is_row ? m0 : n0) + idx;
+        if (g < N) {
+            const int lim = min(64, N - (is_row ? n0 : m0));
+            float m = -INFINITY;
+            for (int q = 0; q < lim; ++q) m = fmaxf(m, is_row ? St[idx][q] : St[q][idx]);
+            float l = 0.f, w = 0.f;
+            for (int q = 0; q < lim; ++q) {
+                const float v = is_row ? St[idx][q] : St[q][idx];
+                const float e = expf(v - m);
+                l += e;
+                w = fmaf(e, v, w);
+            }
+            float* dst = is_row ? rowpart + ((long long)cb * N + g) * 3
+                                : colpart + ((long long)rb * N + g) * 3;
+            dst[0] = m; dst[1] = l; dst[2] = w;
+            if (is_row && rb == cb) diag[g] = St[idx][idx];
+        }
+    }
+}
+
+// pass 2: thread per index; merges partials; accumulates loss and dlog_temp into out[0..1]
+__global__ void clip_reduce_kernel(const float* __restrict__ rowpart,
+                                   const float* __restrict__ colpart,
+                                   const float* __restrict__ diag, float* __restrict__ row_lse,
+                                   float* __restrict__ col_lse, float* __restrict__ out, int N,
+                                   int nblk, float inv_2nb) {
+    __shared__ float red[2][8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float loss = 0.f, dtemp = 0.f;
+    if (i < N) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const float* part = side == 0 ? rowpart : colpart;
+            float m = -INFINITY;
+            for (int b = 0; b < nblk; ++b) m = fmaxf(m, part[((long long)b * N + i) * 3]);
+            float l = 0.f, w = 0.f;
+            for (int b = 0; b < nblk; ++b) {
+                const float* p = part + ((long long)b * N + i) * 3;
+                const float sc = expf(p[0] - m);
+                l = fmaf(p[1], sc, l);
+                w = fmaf(p[2], sc, w);
+            }
+            const float lse = m + logf(l);
+            (side == 0 ? row_lse : col_lse)[i] = lse;
+            loss += lse - diag[i];
+            dtemp += w / l - diag[i];
+        }
+    }
+    loss = warp_sum(loss);
+    dtemp = warp_sum(dtemp);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = loss; red[1][warp] = dtemp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+        atomicAdd(out + 0, a * inv_2nb);
+        atomicAdd(out + 1, b * inv_2nb);
+    }
+}
+
+// pass 3: grid (N/64, b_local/64, 2). z = 0: rows = local text rows, cols = all images,
+// Gout[(r-row0), c] = G[r, c].  z = 1: rows = local image cols, cols = all texts,
+// Gout[(c-row0), i] = G[i, c]  (second stripe lives at Gout + b_local*N).
+__global__ void __launch_bounds__(256)
+clip_grad_tiles_kernel(const float* __restrict__ T, const float* __restrict__ I,
+                       const float* __restrict__ log_temp, const float* __restrict__ row_lse,
+                       const float* __restrict__ col_lse, float* __restrict__ Gout, int N, int d,
+                       int b_local, int row0, float inv_2nb) {
+    __shared__ float As[16][68];
+    __shared__ float Bs[16][68];
+    const int z = blockIdx.z;
+    const float* A = (z == 0 ? T : I) + (long long)row0 * d;
+    const float* B = z == 0 ? I : T;
+    const float* lse_a = (z == 0 ? row_lse : col_lse) + row0;   // lse of the stripe's own index
+    const float* lse_b = z == 0 ? col_lse : row_lse;            // lse along the other index
+    float* G = Gout + (long long)z * b_local * N;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4];
+    sgemm_tile_64x64<true>(A, d, B, d, m0, n0, b_local, N, d, acc, As, Bs);
+    const float s = expf(*log_temp);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + ty * 4 + i;
+        if (r >= b_local) continue;
+        const float la = lse_a[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + tx * 4 + j;
+            if (c >= N) continue;
+            const float v = acc[i][j] * s;
+            float g = expf(v - la) + expf(v - lse_b[c]);
+            if (c == row0 + r) g -= 2.f;
+            G[(long long)r * N + c] = g * inv_2nb;
+        }
+    }
+}
+
+// pass 4: C[M, Nc] = alpha * A[M, K] * B[K, Nc]   (fp32, NN)
+__global__ void __launch_bounds__(256)
+sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                const float* __restrict__ log_alpha, int M, int Nc, int K) {
+    __shared__ float As[16][68];
+    __shared__ float Bs[16][68];
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4];
+    sgemm_tile_64x64<false>(A, K, B, Nc, m0, n0, M, Nc, K, acc, As, Bs);
+    const float alpha = log_alpha ? expf(*log_alpha) : 1.f;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + ty * 4 + i;
+        if (r >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + tx * 4 + j;
+            if (c < Nc) C[(long long)r * Nc + c] = acc[i][j] * alpha;
+        }
+    }
+}
+
+__global__ void pair_logits_kernel(const float* __restrict__ tl, const float* __restrict__ il,
+                                   const float* __restrict__ log_temp, float* __restrict__ out,
+                                   int P, int d) {
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    float acc = 0.f;
+    for (int i = lane; i < d; i += 32) acc = fmaf(tl[(long long)p * d + i], il[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[p] = acc * expf(*log_temp);
+}
+
+inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace
+
+extern "C" int ctk_mean_pool_fwd(const float* x, float* pooled, int B, long long n, int dim,
+                                 void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(x && pooled && B > 0 && n > 0 && dim > 0 && dim % 4 == 0, CTK_ERR_SHAPE,
+                "mean_pool: bad args");
+    CTK_REQUIRE(CTK_ALIGNED(x, 16), CTK_ERR_ALIGN, "mean_pool: x must be 16-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    CTK_CUDA(cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)B * dim, s));
+    const long long tpb = 128;
+    dim3 grid((unsigned)((n + tpb - 1) / tpb), B);
+    mean_pool_kernel<<<grid, 128, 0, s>>>(x, pooled, n, dim, tpb);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_latent_fwd(const float* x, long long x_stride, const float* W, float* latent,
+                              float* rnorm, int B, int din, int dl, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(x && W && latent && rnorm && B > 0 && din > 0 && dl > 0, CTK_ERR_SHAPE,
+                "latent_fwd: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    const size_t sm = sizeof(float) * (size_t)(din + dl);
+    CTK_REQUIRE(sm <= 48 * 1024, CTK_ERR_SHAPE, "latent_fwd: din + dl too large");
+    latent_fwd_kernel<<<B, 256, sm, s>>>(x, x_stride, W, latent, rnorm, din, dl);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_latent_bwd(const float* dlatent, const float* latent, const float* rnorm,
+                              const float* x, long long x_stride, const float* W, float* dW,
+                              float* dx, long long dx_stride, int B, int din, int dl,
+                              void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(dlatent && latent && rnorm && x && W && B > 0 && din > 0 && dl > 0, CTK_ERR_SHAPE,
+                "latent_bwd: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (dx) {
+        latent_bwd_dx_kernel<<<B, 256, sizeof(float) * dl, s>>>(dlatent, latent, rnorm, W, dx,
+                                                                dx_stride, din, dl);
+        CTK_LAUNCH_CHECK();
+    }
+    if (dW) {
+        const size_t sm = sizeof(float) * (size_t)(9 * B);
+        CTK_REQUIRE(sm <= 48 * 1024, CTK_ERR_SHAPE, "latent_bwd: batch too large");
+        latent_bwd_dw_kernel<<<(dl + 7) / 8, 256, sm, s>>>(dlatent, latent, rnorm, x, x_stride, dW,
+                                                           B, din, dl);
+        CTK_LAUNCH_CHECK();
+    }
+    return CTK_OK;
+}
+
+extern "C" size_t ctk_clip_loss_ws_bytes(int N, int b_local) {
+    if (N <= 0 || b_local <= 0) return 0;
+    const size_t nblk = (size_t)(N + 63) / 64;
+    size_t bytes = 0;
+    bytes += align256(sizeof(float) * nblk * N * 3) * 2;     // row / col partials
+    bytes += align256(sizeof(float) * N) * 3;                // diag, row_lse, col_lse
+    bytes += align256(sizeof(float) * (size_t)b_local * N * 2);
+    return bytes;
+}
+
+extern "C" int ctk_clip_loss_fwd_bwd(const float* T, const float* I, const float* log_temp,
+                                     float* out, float* d_local, void* ws, size_t ws_bytes, int N,
+                                     int d, int b_local, int row0, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(T && I && log_temp && out && ws, CTK_ERR_SHAPE, "clip_loss: null pointer");
+    CTK_REQUIRE(N > 0 && d > 0 && b_local > 0 && row0 >= 0 && row0 + b_local <= N, CTK_ERR_SHAPE,
+                "clip_loss: bad N=%d d=%d b_local=%d row0=%d", N, d, b_local, row0);
+    CTK_REQUIRE(ws_bytes >= ctk_clip_loss_ws_bytes(N, b_local), CTK_ERR_SHAPE,
+                "clip_loss: workspace too small");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    const int nblk = (N + 63) / 64;
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+    float* rowpart = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)nblk * N * 3);
+    float* colpart = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)nblk * N * 3);
+    float* diag = reinterpret_cast<float*>(p);    p += align256(sizeof(float) * N);
+    float* row_lse = reinterpret_cast<float*>(p); p += align256(sizeof(float) * N);
+    float* col_lse = reinterpret_cast<float*>(p); p += align256(sizeof(float) * N);
+    float* G = reinterpret_cast<float*>(p);
+
+    // reference: / 2 (two directions) / bs_single_gpu (ct_clip.py:1379), means over N rows
+    const float inv_2nb = 1.0f / (2.0f * (float)N * (float)b_local);
+    CTK_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(float), s));
+    clip_tile_stats_kernel<<<dim3(nblk, nblk), 256, 0, s>>>(T, I, log_temp, rowpart, colpart, diag,
+                                                           N, d);
+    CTK_LAUNCH_CHECK();
+    clip_reduce_kernel<<<(N + 127) / 128, 128, 0, s>>>(rowpart, colpart, diag, row_lse, col_lse,
+                                                      out, N, nblk, inv_2nb);
+    CTK_LAUNCH_CHECK();
+    if (d_local) {
+        clip_grad_tiles_kernel<<<dim3(nblk, (b_local + 63) / 64, 2), 256, 0, s>>>(
+            T, I, log_temp, row_lse, col_lse, G, N, d, b_local, row0, inv_2nb);
+        CTK_LAUNCH_CHECK();
+        dim3 g2((d + 63) / 64, (b_local + 63) / 64);
+        sgemm_nn_kernel<<<g2, 256, 0, s>>>(G, I, d_local, log_temp, b_local, d, N);
+        CTK_LAUNCH_CHECK();
+        sgemm_nn_kernel<<<g2, 256, 0, s>>>(G + (long long)b_local * N, T,
+                                           d_local + (long long)b_local * d, log_temp, b_local, d, N);
+        CTK_LAUNCH_CHECK();
+    }
+    return CTK_OK;
+}
+
+extern "C" int ctk_pair_logits(const float* text_lat, const float* image_lat, const float* log_temp,
+                               float* out, int P, int d, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(text_lat && image_lat && log_temp && out && P > 0 && d > 0, CTK_ERR_SHAPE,
+                "pair_logits: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    pair_logits_kernel<<<(P + 3) / 4, 128, 0, s>>>(text_lat, image_lat, log_temp, out, P, d);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
