@@ -1,0 +1,634 @@
+// HBM-bound kernels of the CTViT encoder: tubelet patch gather + LayerNorm statistics,
+// LayerNorm forward/backward (with the spatial<->temporal token transposition folded into the
+// row index), PEG depthwise 3x3x3 conv forward/backward, row l2norm, VQ gather / EMA update.
+#include "common.cuh"
+
+namespace {
+
+// =============================================================================================
+// patch gather + LayerNorm(pt*p1*p2) statistics   (ctvit.py:170-172)
+// One CTA = G consecutive patches along W: (pt*p1) contiguous runs of G*p2 floats.
+// =============================================================================================
+template <int G>
+__global__ void __launch_bounds__(256)
+patch_norm_kernel(const float* __restrict__ video, __nv_bfloat16* __restrict__ xhat, long long ld,
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int D, int H, int W,
+                  int pt, int p1, int p2, float eps) {
+    extern __shared__ float sm[];                 // [G][K]
+    __shared__ float red[G][8];
+    __shared__ float stat[G][2];
+    const int K = pt * p1 * p2;
+    const int T = D / pt, Hp = H / p1, Wp = W / p2;
+    const int wg = Wp / G;
+    long long cta = blockIdx.x;
+    const int wgi = (int)(cta % wg); cta /= wg;
+    const int hp = (int)(cta % Hp);  cta /= Hp;
+    const int tp = (int)(cta % T);   cta /= T;
+    const int b = (int)cta;
+    const int runw = G * p2;                      // floats per contiguous run
+    const int nrun = pt * p1;
+    const float* base = video + (((long long)b * D + (long long)tp * pt) * H + (long long)hp * p1) * W +
+                        (long long)wgi * runw;
+    const bool vec = (p2 % 4 == 0) && (W % 4 == 0);
+    if (vec) {
+        const int q_per_run = runw / 4;
+        for (int i = threadIdx.x; i < nrun * q_per_run; i += blockDim.x) {
+            const int r = i / q_per_run, q = i % q_per_run;
+            const int dt = r / p1, dy = r % p1;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((long long)dt * H + dy) * W) + q);
+            const int x = q * 4;
+            const int g = x / p2, dx = x % p2;
+            float* dst = sm + g * K + r * p2 + dx;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < nrun * runw; i += blockDim.x) {
+            const int r = i / runw, x = i % runw;
+            const int dt = r / p1, dy = r % p1;
+            sm[(x / p2) * K + r * p2 + (x % p2)] = __ldg(base + ((long long)dt * H + dy) * W + x);
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // pass 1: means
+    float s[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float a = 0.f;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) a += sm[g * K + k];
+        s[g] = warp_sum(a);
+    }
+    if (lane == 0)
+#pragma unroll
+        for (int g = 0; g < G; ++g) red[g][warp] = s[g];
+    __syncthreads();
+    if (threadIdx.x < G) {
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += red[threadIdx.x][w];
+        stat[threadIdx.x][0] = a / (float)K;
+    }
+    __syncthreads();
+    // pass 2: centred variance (exact two-pass: padding voxels are -1 while data is in [0,1])
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float mu = stat[g][0];
+        float a = 0.f;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float d = sm[g * K + k] - mu;
+            a = fmaf(d, d, a);
+        }
+        s[g] = warp_sum(a);
+    }
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int g = 0; g < G; ++g) red[g][warp] = s[g];
+    __syncthreads();
+    const long long row0 = (((long long)b * T + tp) * Hp + hp) * Wp + (long long)wgi * G;
+    if (threadIdx.x < G) {
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += red[threadIdx.x][w];
+        const float rs = rsqrtf(a / (float)K + eps);
+        stat[threadIdx.x][1] = rs;
+        mean_out[row0 + threadIdx.x] = stat[threadIdx.x][0];
+        rstd_out[row0 + threadIdx.x] = rs;
+    }
+    __syncthreads();
+    // write xhat (bf16), 8 elements (16 B) per thread-iteration; pad columns [K, ld) zeroed
+    const int k8 = (int)(ld / 8);
+    for (int i = threadIdx.x; i < G * k8; i += blockDim.x) {
+        const int g = i / k8, j = (i % k8) * 8;
+        const float mu = stat[g][0], rs = stat[g][1];
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (j + e < K) ? (sm[g * K + j + e] - mu) * rs : 0.f;
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(xhat + (row0 + g) * ld + j) = u;
+    }
+}
+
+// =============================================================================================
+// LayerNorm forward: one warp per row, NV float2 pairs per lane (dim = 64 * NV)
+// =============================================================================================
+__device__ __forceinline__ long long perm_row(long long row, int outer, int inner) {
+    if (inner <= 0) return row;
+    const long long i = row % inner;
+    const long long t = row / inner;
+    const long long o = t % outer, g = t / outer;
+    return (g * inner + i) * outer + o;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
+                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ xraw_bf16,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
+                     float eps, int perm_outer, int perm_inner) {
+    constexpr int DIM = NV * 64;
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    float2 gm[NV], bt[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        gm[j] = __ldg(reinterpret_cast<const float2*>(gamma) + j * 32 + lane);
+        bt[j] = beta ? __ldg(reinterpret_cast<const float2*>(beta) + j * 32 + lane)
+                     : make_float2(0.f, 0.f);
+    }
+    for (long long row = warp_global; row < rows; row += nwarps) {
+        const float2* xr = reinterpret_cast<const float2*>(x + row * DIM);
+        float2 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            v[j] = xr[j * 32 + lane];
+            s += v[j].x + v[j].y;
+        }
+        const float mu = warp_sum(s) * (1.0f / DIM);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float a = v[j].x - mu, b = v[j].y - mu;
+            q = fmaf(a, a, q);
+            q = fmaf(b, b, q);
+        }
+        const float rs = rsqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mu;
+            if (rstd_out) rstd_out[row] = rs;
+        }
+        const long long orow = perm_row(row, perm_outer, perm_inner);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float a = (v[j].x - mu) * rs * gm[j].x + bt[j].x;
+            const float b = (v[j].y - mu) * rs * gm[j].y + bt[j].y;
+            if (out_bf16)
+                reinterpret_cast<uint32_t*>(out_bf16 + orow * DIM)[j * 32 + lane] = pack_bf16x2(a, b);
+            if (out_f32)
+                reinterpret_cast<float2*>(out_f32 + orow * DIM)[j * 32 + lane] = make_float2(a, b);
+            if (xraw_bf16)
+                reinterpret_cast<uint32_t*>(xraw_bf16 + row * DIM)[j * 32 + lane] =
+                    pack_bf16x2(v[j].x, v[j].y);
+        }
+    }
+}
+
+// LayerNorm backward. dgamma/dbeta: per-warp register partials -> smem -> one atomic per column
+// per CTA.
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __restrict__ dy_f32,
+                     const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     float* __restrict__ dx, int dx_accum, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, long long rows, int perm_outer, int perm_inner,
+                     long long bcast_rows, float dy_scale) {
+    constexpr int DIM = NV * 64;
+    __shared__ float sg[8][DIM + 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    float2 gm[NV], dg[NV], db[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        gm[j] = __ldg(reinterpret_cast<const float2*>(gamma) + j * 32 + lane);
+        dg[j] = make_float2(0.f, 0.f);
+        db[j] = make_float2(0.f, 0.f);
+    }
+    for (long long row = warp_global; row < rows; row += nwarps) {
+        const long long drow = bcast_rows > 0 ? row / bcast_rows : perm_row(row, perm_outer, perm_inner);
+        const float mu = mean[row], rs = rstd[row];
+        const float2* xr = reinterpret_cast<const float2*>(x + row * DIM);
+        float2 xh[NV], g[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            float2 d;
+            if (dy_bf16) d = unpack_bf16x2(reinterpret_cast<const uint32_t*>(dy_bf16 + drow * DIM)[j * 32 + lane]);
+            else d = reinterpret_cast<const float2*>(dy_f32 + drow * DIM)[j * 32 + lane];
+            d.x *= dy_scale; d.y *= dy_scale;
+            const float2 xv = xr[j * 32 + lane];
+            xh[j] = make_float2((xv.x - mu) * rs, (xv.y - mu) * rs);
+            dg[j].x = fmaf(d.x, xh[j].x, dg[j].x); dg[j].y = fmaf(d.y, xh[j].y, dg[j].y);
+            db[j].x += d.x; db[j].y += d.y;
+            g[j] = make_float2(d.x * gm[j].x, d.y * gm[j].y);
+            s1 += g[j].x + g[j].y;
+            s2 = fmaf(g[j].x, xh[j].x, s2);
+            s2 = fmaf(g[j].y, xh[j].y, s2);
+        }
+        s1 = warp_sum(s1) * (1.0f / DIM);
+        s2 = warp_sum(s2) * (1.0f / DIM);
+        float2* dxr = reinterpret_cast<float2*>(dx + row * DIM);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            float2 o = make_float2(rs * (g[j].x - s1 - xh[j].x * s2), rs * (g[j].y - s1 - xh[j].y * s2));
+            if (dx_accum) {
+                const float2 p = dxr[j * 32 + lane];
+                o.x += p.x; o.y += p.y;
+            }
+            dxr[j * 32 + lane] = o;
+        }
+    }
+    // reduce dgamma / dbeta across the CTA's warps
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && !dbeta) break;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float2 v = pass == 0 ? dg[j] : db[j];
+            sg[warp][(j * 32 + lane) * 2] = v.x;
+            sg[warp][(j * 32 + lane) * 2 + 1] = v.y;
+        }
+        __syncthreads();
+        float* dst = pass == 0 ? dgamma : dbeta;
+        for (int c = threadIdx.x; c < DIM; c += blockDim.x) {
+            float a = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sg[w][c];
+            atomicAdd(dst + c, a);
+        }
+    }
+}
+
+// =============================================================================================
+// PEG: depthwise causal 3x3x3 conv + bias + residual on [B, n0, n1, n2, dim] (attention.py:62-90,443)
+// thread.x <-> 2 channels, thread.y <-> one line along n2; sliding 3-wide register window per
+// neighbour line. REVERSE = transposed conv for the input gradient.
+// =============================================================================================
+template <bool REVERSE>
+__global__ void __launch_bounds__(256)
+peg_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ y, int B, int n0, int n1, int n2, int dim) {
+    const int c2 = threadIdx.x;                                   // channel pair
+    const long long line = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    const long long nlines = (long long)B * n0 * n1;
+    if (line >= nlines || c2 * 2 >= dim) return;
+    const int a1 = (int)(line % n1);
+    const int a0 = (int)((line / n1) % n0);
+    const int bb = (int)(line / ((long long)n1 * n0));
+    // weights (dim,1,3,3,3): w[c][k0][k1][k2]
+    float2 wt[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        const int tt = REVERSE ? (26 - t) : t;    // flipped taps for the transposed conv
+        wt[t] = make_float2(__ldg(w + (long long)(2 * c2) * 27 + tt), __ldg(w + (long long)(2 * c2 + 1) * 27 + tt));
+    }
+    const float2 bias = (!REVERSE && b) ? make_float2(__ldg(b + 2 * c2), __ldg(b + 2 * c2 + 1)) : make_float2(0.f, 0.f);
+    // neighbour line pointers (nullptr = zero padding). forward: a0 offsets -2,-1,0; reverse: 0,+1,+2
+    const float2* lines[9];
+#pragma unroll
+    for (int k0 = 0; k0 < 3; ++k0)
+#pragma unroll
+        for (int k1 = 0; k1 < 3; ++k1) {
+            const int q0 = REVERSE ? a0 + k0 : a0 + k0 - 2;
+            const int q1 = a1 + k1 - 1;
+            const bool ok = q0 >= 0 && q0 < n0 && q1 >= 0 && q1 < n1;
+            lines[k0 * 3 + k1] = ok ? reinterpret_cast<const float2*>(
+                                          x + ((((long long)bb * n0 + q0) * n1 + q1) * n2) * dim) + c2
+                                    : nullptr;
+        }
+    const int stride2 = dim / 2;                                   // float2 stride between a2 positions
+    float2 win[9][3];
+#pragma unroll
+    for (int l = 0; l < 9; ++l) {
+        win[l][0] = make_float2(0.f, 0.f);
+        win[l][1] = lines[l] ? lines[l][0] : make_float2(0.f, 0.f);
+    }
+    const int centre = REVERSE ? 1 : 7;                            // (k0,k1) of the centre line: a0+0, a1+0
+    float2* yo = reinterpret_cast<float2*>(y + ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim) + c2;
+    for (int a2 = 0; a2 < n2; ++a2) {
+#pragma unroll
+        for (int l = 0; l < 9; ++l)
+            win[l][2] = (lines[l] && a2 + 1 < n2) ? lines[l][(long long)(a2 + 1) * stride2]
+                                                  : make_float2(0.f, 0.f);
+        float2 acc = make_float2(bias.x + win[centre][1].x, bias.y + win[centre][1].y);   // + residual
+#pragma unroll
+        for (int l = 0; l < 9; ++l)
+#pragma unroll
+            for (int k2 = 0; k2 < 3; ++k2) {
+                acc.x = fmaf(wt[l * 3 + k2].x, win[l][k2].x, acc.x);
+                acc.y = fmaf(wt[l * 3 + k2].y, win[l][k2].y, acc.y);
+            }
+        yo[(long long)a2 * stride2] = acc;
+#pragma unroll
+        for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
+    }
+}
+
+// dw[c][tap] += sum_pos dy[pos] x[pos + off(tap)], db[c] += sum dy. Each thread.y walks lines with
+// a grid stride so the final atomics are amortised.
+__global__ void __launch_bounds__(256)
+peg_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                 float* __restrict__ db, int B, int n0, int n1, int n2, int dim) {
+    const int c2 = threadIdx.x;
+    if (c2 * 2 >= dim) return;
+    const long long nlines = (long long)B * n0 * n1;
+    const int stride2 = dim / 2;
+    float2 acc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc[t] = make_float2(0.f, 0.f);
+    float2 accb = make_float2(0.f, 0.f);
+    for (long long line = (long long)blockIdx.x * blockDim.y + threadIdx.y; line < nlines;
+         line += (long long)gridDim.x * blockDim.y) {
+        const int a1 = (int)(line % n1);
+        const int a0 = (int)((line / n1) % n0);
+        const int bb = (int)(line / ((long long)n1 * n0));
+        const float2* lines[9];
+#pragma unroll
+        for (int k0 = 0; k0 < 3; ++k0)
+#pragma unroll
+            for (int k1 = 0; k1 < 3; ++k1) {
+                const int q0 = a0 + k0 - 2, q1 = a1 + k1 - 1;
+                const bool ok = q0 >= 0 && q1 >= 0 && q1 < n1;
+                lines[k0 * 3 + k1] = ok ? reinterpret_cast<const float2*>(
+                                              x + ((((long long)bb * n0 + q0) * n1 + q1) * n2) * dim) + c2
+                                        : nullptr;
+            }
+        const float2* dyl = reinterpret_cast<const float2*>(
+                                dy + ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim) + c2;
+        float2 win[9][3];
+#pragma unroll
+        for (int l = 0; l < 9; ++l) {
+            win[l][0] = make_float2(0.f, 0.f);
+            win[l][1] = lines[l] ? lines[l][0] : make_float2(0.f, 0.f);
+        }
+        for (int a2 = 0; a2 < n2; ++a2) {
+#pragma unroll
+            for (int l = 0; l < 9; ++l)
+                win[l][2] = (lines[l] && a2 + 1 < n2) ? lines[l][(long long)(a2 + 1) * stride2]
+                                                      : make_float2(0.f, 0.f);
+            const float2 g = dyl[(long long)a2 * stride2];
+            accb.x += g.x; accb.y += g.y;
+#pragma unroll
+            for (int l = 0; l < 9; ++l)
+#pragma unroll
+                for (int k2 = 0; k2 < 3; ++k2) {
+                    acc[l * 3 + k2].x = fmaf(g.x, win[l][k2].x, acc[l * 3 + k2].x);
+                    acc[l * 3 + k2].y = fmaf(g.y, win[l][k2].y, acc[l * 3 + k2].y);
+                }
+#pragma unroll
+            for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        atomicAdd(dw + (long long)(2 * c2) * 27 + t, acc[t].x);
+        atomicAdd(dw + (long long)(2 * c2 + 1) * 27 + t, acc[t].y);
+    }
+    atomicAdd(db + 2 * c2, accb.x);
+    atomicAdd(db + 2 * c2 + 1, accb.y);
+}
+
+// =============================================================================================
+// VQ helpers
+// =============================================================================================
+__global__ void l2norm_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xn_bf16,
+                                   float* __restrict__ xn_f32, long long rows, int dim) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * dim;
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) { const float v = xr[c]; ss = fmaf(v, v, ss); }
+    const float rn = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+    for (int c = lane; c < dim; c += 32) {
+        const float v = xr[c] * rn;
+        if (xn_bf16) xn_bf16[row * dim + c] = __float2bfloat16(v);
+        if (xn_f32) xn_f32[row * dim + c] = v;
+    }
+}
+
+__global__ void vq_gather_kernel(const unsigned long long* __restrict__ best,
+                                 const float* __restrict__ embed, long long* __restrict__ ind,
+                                 float* __restrict__ quant, long long rows, int dim, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    long long idx = (long long)(0xffffffffu - (uint32_t)(best[row] & 0xffffffffull));
+    if (idx < 0 || idx >= C) idx = 0;
+    if (lane == 0) ind[row] = idx;
+    const float* e = embed + idx * dim;
+    for (int c = lane; c < dim; c += 32) quant[row * dim + c] = __ldg(e + c);
+}
+
+// embed_sum[code] += xn[row]; bins[code] += 1
+__global__ void vq_scatter_kernel(const float* __restrict__ xn, const long long* __restrict__ ind,
+                                  float* __restrict__ esum, float* __restrict__ bins, long long rows,
+                                  int dim) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const long long code = ind[row];
+    if (lane == 0) atomicAdd(bins + code, 1.0f);
+    for (int c = lane; c < dim; c += 32) atomicAdd(esum + code * dim + c, xn[row * dim + c]);
+}
+
+// one warp per code: cluster_size EMA; embed <- decay*embed + (1-decay)*l2norm(esum/bins) (codes
+// without hits are pulled towards their own l2-normalised value, as in the cosine-sim codebook)
+__global__ void vq_ema_kernel(float* __restrict__ cluster_size, float* __restrict__ embed,
+                              const float* __restrict__ esum, const float* __restrict__ bins, int C,
+                              int dim, float decay) {
+    const int lane = threadIdx.x & 31;
+    const int code = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (code >= C) return;
+    const float n = bins[code];
+    if (lane == 0) cluster_size[code] = cluster_size[code] * decay + n * (1.0f - decay);
+    const float* src = n > 0.f ? esum + (long long)code * dim : embed + (long long)code * dim;
+    const float inv = n > 0.f ? 1.0f / n : 1.0f;
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) { const float v = src[c] * inv; ss = fmaf(v, v, ss); }
+    const float rn = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+    for (int c = lane; c < dim; c += 32) {
+        const float v = src[c] * inv * rn;
+        float* e = embed + (long long)code * dim + c;
+        *e = *e * decay + v * (1.0f - decay);
+    }
+}
+
+template <int NV>
+int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                  void* xraw, float* mean, float* rstd, long long rows, float eps, int po, int pi,
+                  cudaStream_t s) {
+    long long blocks = (rows + 7) / 8;
+    const long long cap = (long long)ctk_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    layernorm_fwd_kernel<NV><<<(int)blocks, 256, 0, s>>>(
+        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32,
+        reinterpret_cast<__nv_bfloat16*>(xraw), mean, rstd, rows, eps, po, pi);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+template <int NV>
+int launch_ln_bwd(const void* dyb, const float* dyf, const float* x, const float* gamma, const float* mean,
+                  const float* rstd, float* dx, int accum, float* dgamma, float* dbeta, long long rows,
+                  int po, int pi, long long bc, float sc, cudaStream_t s) {
+    long long blocks = (rows + 7) / 8;
+    const long long cap = (long long)ctk_num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    layernorm_bwd_kernel<NV><<<(int)blocks, 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dyb), dyf, x, gamma, mean, rstd, dx, accum, dgamma, dbeta,
+        rows, po, pi, bc, sc);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+}  // namespace
+
+extern "C" int ctk_patch_norm_fwd(const float* video, void* xhat, long long ld, float* mean,
+                                  float* rstd, int B, int D, int H, int W, int pt, int p1, int p2,
+                                  float eps, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(video && xhat && mean && rstd, CTK_ERR_SHAPE, "patch_norm: null pointer");
+    CTK_REQUIRE(B > 0 && pt > 0 && p1 > 0 && p2 > 0 && D % pt == 0 && H % p1 == 0 && W % p2 == 0,
+                CTK_ERR_SHAPE, "patch_norm: volume %dx%dx%d not divisible by patch %dx%dx%d", D, H, W, pt, p1, p2);
+    const int K = pt * p1 * p2;
+    CTK_REQUIRE(ld >= K && ld % 8 == 0 && CTK_ALIGNED(xhat, 16) && CTK_ALIGNED(video, 16), CTK_ERR_ALIGN,
+                "patch_norm: xhat pitch must be a multiple of 8 and >= %d", K);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    const int Wp = W / p2;
+    const int G = (Wp % 4 == 0 && (size_t)4 * K * 4 <= 96 * 1024) ? 4 : (Wp % 2 == 0 && (size_t)2 * K * 4 <= 96 * 1024) ? 2 : 1;
+    const size_t smem = (size_t)G * K * sizeof(float);
+    CTK_REQUIRE(smem <= 200 * 1024, CTK_ERR_SHAPE, "patch_norm: patch of %d voxels too large", K);
+    const long long ctas = (long long)B * (D / pt) * (H / p1) * (Wp / G);
+#define CTK_PN(GV)                                                                                 \
+    {                                                                                              \
+        CTK_CUDA(cudaFuncSetAttribute(patch_norm_kernel<GV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        patch_norm_kernel<GV><<<(unsigned)ctas, 256, smem, s>>>(                                   \
+            video, reinterpret_cast<__nv_bfloat16*>(xhat), ld, mean, rstd, D, H, W, pt, p1, p2, eps); \
+    }
+    if (G == 4) CTK_PN(4) else if (G == 2) CTK_PN(2) else CTK_PN(1)
+#undef CTK_PN
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16,
+                                 float* out_f32, void* xraw_bf16, float* mean, float* rstd,
+                                 long long rows, int dim, float eps, int perm_outer, int perm_inner,
+                                 void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(x && gamma && rows > 0, CTK_ERR_SHAPE, "layernorm_fwd: bad args");
+    CTK_REQUIRE(dim % 64 == 0 && dim >= 64 && dim <= 1024, CTK_ERR_SHAPE,
+                "layernorm: dim %d must be a multiple of 64 in [64, 1024]", dim);
+    CTK_REQUIRE(perm_inner <= 0 || (perm_outer > 0 && rows % ((long long)perm_outer * perm_inner) == 0),
+                CTK_ERR_SHAPE, "layernorm: rows not divisible by the permutation block");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    switch (dim / 64) {
+#define CTK_LN(NV) case NV: return launch_ln_fwd<NV>(x, gamma, beta, out_bf16, out_f32, xraw_bf16, mean, rstd, rows, eps, perm_outer, perm_inner, s);
+        CTK_LN(1) CTK_LN(2) CTK_LN(4) CTK_LN(8) CTK_LN(12) CTK_LN(16)
+#undef CTK_LN
+        default: break;
+    }
+    ctk_set_error("layernorm: dim %d not instantiated (64,128,256,512,768,1024)", dim);
+    return CTK_ERR_SHAPE;
+}
+
+extern "C" int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x,
+                                 const float* gamma, const float* mean, const float* rstd, float* dx,
+                                 int dx_accum, float* dgamma, float* dbeta, long long rows, int dim,
+                                 int perm_outer, int perm_inner, long long dy_bcast_rows, float dy_scale,
+                                 void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE((dy_bf16 || dy_f32) && x && gamma && mean && rstd && dx && dgamma && rows > 0,
+                CTK_ERR_SHAPE, "layernorm_bwd: bad args");
+    CTK_REQUIRE(dim % 64 == 0 && dim >= 64 && dim <= 1024, CTK_ERR_SHAPE, "layernorm_bwd: dim %d", dim);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    switch (dim / 64) {
+#define CTK_LN(NV) case NV: return launch_ln_bwd<NV>(dy_bf16, dy_f32, x, gamma, mean, rstd, dx, dx_accum, dgamma, dbeta, rows, perm_outer, perm_inner, dy_bcast_rows, dy_scale, s);
+        CTK_LN(1) CTK_LN(2) CTK_LN(4) CTK_LN(8) CTK_LN(12) CTK_LN(16)
+#undef CTK_LN
+        default: break;
+    }
+    ctk_set_error("layernorm_bwd: dim %d not instantiated", dim);
+    return CTK_ERR_SHAPE;
+}
+
+static int peg_block(int dim, dim3* block) {
+    const int tx = dim / 2;
+    if (dim % 2 != 0 || tx > 256) return -1;
+    int ty = 256 / tx;
+    if (ty < 1) ty = 1;
+    *block = dim3(tx, ty);
+    return 0;
+}
+
+extern "C" int ctk_peg_fwd(const float* x, const float* w, const float* b, float* y, int B, int n0,
+                           int n1, int n2, int dim, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(x && w && b && y && B > 0 && n0 > 0 && n1 > 0 && n2 > 0, CTK_ERR_SHAPE, "peg_fwd: bad args");
+    dim3 block;
+    CTK_REQUIRE(peg_block(dim, &block) == 0, CTK_ERR_SHAPE, "peg: dim %d must be even and <= 512", dim);
+    CTK_REQUIRE(x != y, CTK_ERR_SHAPE, "peg_fwd: in-place not supported");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    const long long nlines = (long long)B * n0 * n1;
+    peg_conv_kernel<false><<<(unsigned)((nlines + block.y - 1) / block.y), block, 0, s>>>(x, w, b, y, B, n0, n1, n2, dim);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_peg_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw,
+                           float* db, int B, int n0, int n1, int n2, int dim, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(dy && x && w && dx && dw && db && B > 0, CTK_ERR_SHAPE, "peg_bwd: bad args");
+    dim3 block;
+    CTK_REQUIRE(peg_block(dim, &block) == 0, CTK_ERR_SHAPE, "peg: dim %d must be even and <= 512", dim);
+    CTK_REQUIRE(dy != dx, CTK_ERR_SHAPE, "peg_bwd: in-place not supported");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    const long long nlines = (long long)B * n0 * n1;
+    peg_conv_kernel<true><<<(unsigned)((nlines + block.y - 1) / block.y), block, 0, s>>>(dy, w, nullptr, dx, B, n0, n1, n2, dim);
+    CTK_LAUNCH_CHECK();
+    long long blocks = (nlines + block.y - 1) / block.y;
+    const long long cap = (long long)ctk_num_sms() * 2;
+    if (blocks > cap) blocks = cap;
+    peg_wgrad_kernel<<<(unsigned)blocks, block, 0, s>>>(dy, x, dw, db, B, n0, n1, n2, dim);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_l2norm_rows(const float* x, void* xn_bf16, float* xn_f32, long long rows, int dim,
+                               void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(x && (xn_bf16 || xn_f32) && rows > 0 && dim > 0, CTK_ERR_SHAPE, "l2norm_rows: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    l2norm_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(xn_bf16), xn_f32, rows, dim);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_vq_gather(const void* best, const float* embed, long long* ind, float* quant,
+                             long long rows, int dim, int codebook_size, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(best && embed && ind && quant && rows > 0 && dim > 0 && codebook_size > 0, CTK_ERR_SHAPE, "vq_gather: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    vq_gather_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+        reinterpret_cast<const unsigned long long*>(best), embed, ind, quant, rows, dim, codebook_size);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_vq_ema_update(const float* xn_f32, const long long* ind, float* cluster_size,
+                                 float* embed, float* ws, long long rows, int dim, int codebook_size,
+                                 float decay, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(xn_f32 && ind && cluster_size && embed && ws && rows > 0, CTK_ERR_SHAPE, "vq_ema_update: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    float* esum = ws;
+    float* bins = ws + (size_t)codebook_size * dim;
+    CTK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * ((size_t)codebook_size * dim + codebook_size), s));
+    vq_scatter_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(xn_f32, ind, esum, bins, rows, dim);
+    CTK_LAUNCH_CHECK();
+    vq_ema_kernel<<<(codebook_size + 7) / 8, 256, 0, s>>>(cluster_size, embed, esum, bins, codebook_size, dim, decay);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
