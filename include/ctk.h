@@ -110,15 +110,16 @@ int ctk_patch_norm_fwd(const float* video, void* xhat, long long ld, float* mean
                        int B, int D, int H, int W, int pt, int p1, int p2, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * LayerNorm over the last dim (<= 1024, multiple of 128) of an fp32 [rows, dim] matrix.
+ * LayerNorm over the last dim (<= 1024, multiple of 64) of an fp32 [rows, dim] matrix.
  * attention.py:34-41 (gamma + zero beta buffer), :51 nn.LayerNorm, ctvit.py:174.
- * out_bf16 / out_f32 may be NULL. If perm_inner > 0 the output row index is transposed:
+ * out_bf16 / out_f32 may be NULL. xraw_bf16 (may be NULL) receives the un-normalised input cast to
+ * bf16 in the input row order: the k/v projections read the raw stream (attention.py:145-149). If perm_inner > 0 the output row index is transposed:
  * row = (g*perm_outer + o)*perm_inner + i  ->  (g*perm_inner + i)*perm_outer + o, which is the
  * '(b t)(h w) d -> (b h w) t d' rearrangement of ctvit.py:301 (and its inverse :305).
  * ------------------------------------------------------------------------------------------ */
 int ctk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16,
-                      float* out_f32, float* mean, float* rstd, long long rows, int dim, float eps,
-                      int perm_outer, int perm_inner, void* stream);
+                      float* out_f32, void* xraw_bf16, float* mean, float* rstd, long long rows,
+                      int dim, float eps, int perm_outer, int perm_inner, void* stream);
 /* dx (fp32) = LN backward of dy; dy is bf16 (dy_bf16) or fp32 (dy_f32), indexed through the same
  * row permutation as the forward output. dy_bcast_rows > 0: dy has rows/dy_bcast_rows rows and
  * row r reads dy[r / dy_bcast_rows] * dy_scale (gradient of a mean-pool broadcast back).

@@ -40,7 +40,7 @@ SIGNATURES = {
     "ctk_transpose_cast_bf16": (_i, [_vp, _vp, _ll, _ll, _ll, _vp]),
     "ctk_pack_ff_w1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ctk_patch_norm_fwd": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
-    "ctk_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp]),
+    "ctk_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp]),
     "ctk_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _i, _i, _ll, _f, _vp]),
     "ctk_peg_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ctk_peg_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

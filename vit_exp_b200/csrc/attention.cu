@@ -1,0 +1,726 @@
+// Cosine attention core (attention.py:162-184) on the packed qkv buffer produced by the
+// CTK_EPI_QKV GEMM epilogue.  q is already l2-normalised, scaled by q_scale and by the constant 8;
+// k is l2-normalised and scaled by k_scale, so logits = q.k (+ relative position bias).
+//
+// Two regimes (hard parts 2-3):
+//  * "long" sequences (spatial stack, L = 576 tokens per slice): flash-style kernels - the L x L
+//    logits live only in registers, K/V of one (sequence, head) are staged once in shared memory
+//    with a 16-byte XOR swizzle, the products run on the tensor cores (bf16 m16n8k16, fp32
+//    accumulate), softmax is online in fp32 with exp2.  The bias is gathered from the
+//    (2gh-1)x(2gw-1) table in shared memory.  Backward = dq kernel + dk/dv kernel (transposed
+//    formulation, no atomics) + bias-table gradient kernel (tile fixed, loops over sequences).
+//  * "short" sequences (temporal stack, L = 24): one CTA per sequence, one warp per head, one lane
+//    per query/key, fp32 SIMT - a 24x24 problem cannot fill an MMA tile.
+//
+// NOTE: this round the long-sequence path uses the legacy mma.sync tensor-core path; moving it to
+// tcgen05/TMEM is tracked in DESIGN.md (attention is ~5% of the encoder FLOPs).
+#include "common.cuh"
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// [rows][32 bf16] tile, 64-byte rows, 16-byte chunks XOR-swizzled by (row>>1)&3: conflict-free ldmatrix
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+    return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
+// copy `nrows` rows (32 bf16 each, global pitch ld elements) into a swizzled tile; rows >= valid are zero
+__device__ __forceinline__ void load_tile(uint8_t* dst, const __nv_bfloat16* src, long long ld, int nrows,
+                                          int valid, int tid, int nthreads) {
+    for (int i = tid; i < nrows * 4; i += nthreads) {
+        const int row = i >> 2, c = i & 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < valid) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)row * ld) + c);
+        *reinterpret_cast<uint4*>(dst + tile_off(row, c)) = v;
+    }
+}
+
+// A fragments (16 rows x 32 k) of a tile for the warp's rows r0..r0+15 : a[kstep][4]
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[2][4], uint32_t tile, int r0, int lane) {
+    const int m = lane >> 3;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+        ldsm4(a[ks], tile + tile_off(r0 + (m & 1) * 8 + (lane & 7), 2 * ks + (m >> 1)));
+}
+// B fragments for an operand stored [n][k] (k = 32 channels): n-tile n0..n0+7 -> {b0,b1 (k 0-15), b0,b1 (k 16-31)}
+__device__ __forceinline__ void load_b_nk(uint32_t (&b)[4], uint32_t tile, int n0, int lane) {
+    ldsm4(b, tile + tile_off(n0 + (lane & 7), lane >> 3));
+}
+// B fragments for an operand stored [k][n] (n = 32 channels): k-block k0..k0+15, channel n-tiles 2cp, 2cp+1
+__device__ __forceinline__ void load_b_kn(uint32_t (&b)[4], uint32_t tile, int k0, int cp, int lane) {
+    const int m = lane >> 3;
+    ldsm4t(b, tile + tile_off(k0 + (m & 1) * 8 + (lane & 7), 2 * cp + (m >> 1)));
+}
+
+// acc[8][4] (16 x 64) = A(16x32) * B^T where B is a [64][32] block of `tile` starting at row n_base
+__device__ __forceinline__ void mma_16x64(float (&acc)[8][4], const uint32_t (&a)[2][4], uint32_t tile,
+                                          int n_base, int lane) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        uint32_t b[4];
+        load_b_nk(b, tile, n_base + nt * 8, lane);
+        mma16816(acc[nt], a[0], b[0], b[1]);
+        mma16816(acc[nt], a[1], b[2], b[3]);
+    }
+}
+// out[4][4] (16 x 32) += P(16 x 64, bf16 A-fragments from an accumulator) * B where B = [64][32] rows k_base..
+__device__ __forceinline__ void mma_acc_16x32(float (&out)[4][4], const float (&p)[8][4], uint32_t tile,
+                                              int k_base, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
+        a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
+        a[2] = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+        a[3] = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+        for (int cp = 0; cp < 2; ++cp) {
+            uint32_t b[4];
+            load_b_kn(b, tile, k_base + kk * 16, cp, lane);
+            mma16816(out[2 * cp], a, b[0], b[1]);
+            mma16816(out[2 * cp + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+struct BiasIdx {           // relative-position table lookup for query i, key j
+    const float* tab;      // shared memory, [(2gh-1)*(2gw-1)] for this head (nullptr = no bias)
+    int gw, ww, off;
+    __device__ __forceinline__ float operator()(int i, int j) const {
+        if (!tab) return 0.f;
+        const int yi = i / gw, xi = i - yi * gw, yj = j / gw, xj = j - yj * gw;
+        return tab[(yi - yj) * ww + (xi - xj) + off];
+    }
+    __device__ __forceinline__ int index(int i, int j) const {
+        const int yi = i / gw, xi = i - yi * gw, yj = j / gw, xj = j - yj * gw;
+        return (yi - yj) * ww + (xi - xj) + off;
+    }
+};
+
+__device__ __forceinline__ BiasIdx make_bias(const float* tab_smem, int gh, int gw) {
+    BiasIdx b;
+    b.tab = tab_smem; b.gw = gw; b.ww = 2 * gw - 1; b.off = (gh - 1) * (2 * gw - 1) + (gw - 1);
+    return b;
+}
+
+// =============================================================================================
+// forward: grid (q blocks of 64, heads, nseq), 128 threads
+// smem: K [Lp][32] | V [Lp][32] | Q [64][32] | table
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int L, int heads, int gh, int gw) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int Lp = (L + 63) & ~63;
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + Lp * 64;
+    uint8_t* sQ = sV + Lp * 64;
+    float* sT = reinterpret_cast<float*>(sQ + 64 * 64);
+    const int qb = blockIdx.x, h = blockIdx.y, s = blockIdx.z;
+    const int inner = heads * 32;
+    const long long ld = 3LL * inner;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
+    load_tile(sK, base + inner, ld, Lp, L, tid, 128);
+    load_tile(sV, base + 2 * inner, ld, Lp, L, tid, 128);
+    load_tile(sQ, base + (long long)qb * 64 * ld, ld, 64, L - qb * 64, tid, 128);
+    const int n_off = (2 * gh - 1) * (2 * gw - 1);
+    if (table)
+        for (int i = tid; i < n_off; i += 128) sT[i] = table[(long long)h * n_off + i];
+    __syncthreads();
+    const BiasIdx bias = make_bias(table ? sT : nullptr, gh, gw);
+    const uint32_t tK = smem_u32(sK), tV = smem_u32(sV), tQ = smem_u32(sQ);
+    uint32_t qa[2][4];
+    load_a_frags(qa, tQ, warp * 16, lane);
+    const int g = lane >> 2, t = lane & 3;
+    const int i0 = qb * 64 + warp * 16 + g, i1 = i0 + 8;      // this thread's two query rows
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) o[a][0] = o[a][1] = o[a][2] = o[a][3] = 0.f;
+
+    for (int kb = 0; kb < Lp; kb += 64) {
+        float sc[8][4];
+        mma_16x64(sc, qa, tK, kb, lane);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = kb + nt * 8 + 2 * t + (e & 1);
+                const int i = (e < 2) ? i0 : i1;
+                float x = (sc[nt][e] + bias(min(i, L - 1), min(j, L - 1))) * LOG2E;
+                if (j >= L) x = -INFINITY;
+                sc[nt][e] = x;
+                if (e < 2) mx0 = fmaxf(mx0, x); else mx1 = fmaxf(mx1, x);
+            }
+        mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float r0 = exp2f(m0 - mn0), r1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            sc[nt][0] = exp2f(sc[nt][0] - mn0); sc[nt][1] = exp2f(sc[nt][1] - mn0);
+            sc[nt][2] = exp2f(sc[nt][2] - mn1); sc[nt][3] = exp2f(sc[nt][3] - mn1);
+            ps0 += sc[nt][0] + sc[nt][1];
+            ps1 += sc[nt][2] + sc[nt][3];
+        }
+        l0 = l0 * r0 + ps0; l1 = l1 * r1 + ps1;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { o[a][0] *= r0; o[a][1] *= r0; o[a][2] *= r1; o[a][3] *= r1; }
+        mma_acc_16x32(o, sc, tV, kb, lane);
+    }
+    l0 = quad_sum(l0); l1 = quad_sum(l1);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    __nv_bfloat16* ob = out + (long long)s * L * inner + h * 32;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int d = a * 8 + 2 * t;
+        if (i0 < L) *reinterpret_cast<uint32_t*>(ob + (long long)i0 * inner + d) = pack_bf16x2(o[a][0] * inv0, o[a][1] * inv0);
+        if (i1 < L) *reinterpret_cast<uint32_t*>(ob + (long long)i1 * inner + d) = pack_bf16x2(o[a][2] * inv1, o[a][3] * inv1);
+    }
+    if (t == 0) {
+        float* lp = lse + ((long long)s * heads + h) * L;
+        if (i0 < L) lp[i0] = m0 * LN2 + logf(l0);
+        if (i1 < L) lp[i1] = m1 * LN2 + logf(l1);
+    }
+}
+
+// delta[s,h,i] = sum_d dO O     thread per (row, head)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                  float* __restrict__ delta, long long rows, int L, int heads) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * heads) return;
+    const long long row = idx / heads;
+    const int h = (int)(idx % heads);
+    const uint4* a = reinterpret_cast<const uint4*>(out + row * heads * 32 + h * 32);
+    const uint4* b = reinterpret_cast<const uint4*>(dout + row * heads * 32 + h * 32);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint4 x = a[c], y = b[c];
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 u = unpack_bf16x2(xs[e]), v = unpack_bf16x2(ys[e]);
+            acc = fmaf(u.x, v.x, acc);
+            acc = fmaf(u.y, v.y, acc);
+        }
+    }
+    const long long sq = row / L;
+    delta[(sq * heads + h) * L + (row % L)] = acc;
+}
+
+// =============================================================================================
+// backward, dq: grid (q blocks, heads, nseq). smem: K | V | Q tile | dO tile | table
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
+                   const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int heads,
+                   int gh, int gw) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int Lp = (L + 63) & ~63;
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + Lp * 64;
+    uint8_t* sQ = sV + Lp * 64;
+    uint8_t* sdO = sQ + 64 * 64;
+    float* sT = reinterpret_cast<float*>(sdO + 64 * 64);
+    const int qb = blockIdx.x, h = blockIdx.y, s = blockIdx.z;
+    const int inner = heads * 32;
+    const long long ld = 3LL * inner;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
+    load_tile(sK, base + inner, ld, Lp, L, tid, 128);
+    load_tile(sV, base + 2 * inner, ld, Lp, L, tid, 128);
+    load_tile(sQ, base + (long long)qb * 64 * ld, ld, 64, L - qb * 64, tid, 128);
+    load_tile(sdO, dout + ((long long)s * L + qb * 64) * inner + h * 32, inner, 64, L - qb * 64, tid, 128);
+    const int n_off = (2 * gh - 1) * (2 * gw - 1);
+    if (table)
+        for (int i = tid; i < n_off; i += 128) sT[i] = table[(long long)h * n_off + i];
+    __syncthreads();
+    const BiasIdx bias = make_bias(table ? sT : nullptr, gh, gw);
+    const uint32_t tK = smem_u32(sK), tV = smem_u32(sV);
+    uint32_t qa[2][4], da[2][4];
+    load_a_frags(qa, smem_u32(sQ), warp * 16, lane);
+    load_a_frags(da, smem_u32(sdO), warp * 16, lane);
+    const int g = lane >> 2, t = lane & 3;
+    const int i0 = qb * 64 + warp * 16 + g, i1 = i0 + 8;
+    const float* lp = lse + ((long long)s * heads + h) * L;
+    const float* dp = delta + ((long long)s * heads + h) * L;
+    const float lse0 = (i0 < L ? lp[i0] : 0.f) * LOG2E, lse1 = (i1 < L ? lp[i1] : 0.f) * LOG2E;
+    const float dl0 = i0 < L ? dp[i0] : 0.f, dl1 = i1 < L ? dp[i1] : 0.f;
+    float dq[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) dq[a][0] = dq[a][1] = dq[a][2] = dq[a][3] = 0.f;
+    for (int kb = 0; kb < Lp; kb += 64) {
+        float sc[8][4], dpv[8][4];
+        mma_16x64(sc, qa, tK, kb, lane);
+        mma_16x64(dpv, da, tV, kb, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = kb + nt * 8 + 2 * t + (e & 1);
+                const int i = (e < 2) ? i0 : i1;
+                const float x = (sc[nt][e] + bias(min(i, L - 1), min(j, L - 1))) * LOG2E;
+                const float p = (j < L && i < L) ? exp2f(x - (e < 2 ? lse0 : lse1)) : 0.f;
+                sc[nt][e] = p * (dpv[nt][e] - (e < 2 ? dl0 : dl1));      // dS
+            }
+        mma_acc_16x32(dq, sc, tK, kb, lane);
+    }
+    __nv_bfloat16* ob = dqkv + (long long)s * L * ld + h * 32;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int d = a * 8 + 2 * t;
+        if (i0 < L) *reinterpret_cast<uint32_t*>(ob + (long long)i0 * ld + d) = pack_bf16x2(dq[a][0], dq[a][1]);
+        if (i1 < L) *reinterpret_cast<uint32_t*>(ob + (long long)i1 * ld + d) = pack_bf16x2(dq[a][2], dq[a][3]);
+    }
+}
+
+// =============================================================================================
+// backward, dk & dv (transposed tiles: rows = keys): grid (kv blocks, heads, nseq).
+// smem: Q [Lp][32] | dO [Lp][32] | K tile | V tile | lse [Lp] | delta [Lp] | table
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
+                    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int heads,
+                    int gh, int gw) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int Lp = (L + 63) & ~63;
+    uint8_t* sQ = smem;
+    uint8_t* sdO = sQ + Lp * 64;
+    uint8_t* sK = sdO + Lp * 64;
+    uint8_t* sV = sK + 64 * 64;
+    float* sL = reinterpret_cast<float*>(sV + 64 * 64);
+    float* sD = sL + Lp;
+    float* sT = sD + Lp;
+    const int jb = blockIdx.x, h = blockIdx.y, s = blockIdx.z;
+    const int inner = heads * 32;
+    const long long ld = 3LL * inner;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
+    load_tile(sQ, base, ld, Lp, L, tid, 128);
+    load_tile(sdO, dout + (long long)s * L * inner + h * 32, inner, Lp, L, tid, 128);
+    load_tile(sK, base + inner + (long long)jb * 64 * ld, ld, 64, L - jb * 64, tid, 128);
+    load_tile(sV, base + 2 * inner + (long long)jb * 64 * ld, ld, 64, L - jb * 64, tid, 128);
+    const float* lp = lse + ((long long)s * heads + h) * L;
+    const float* dp = delta + ((long long)s * heads + h) * L;
+    for (int i = tid; i < Lp; i += 128) {
+        sL[i] = i < L ? lp[i] * LOG2E : 0.f;
+        sD[i] = i < L ? dp[i] : 0.f;
+    }
+    const int n_off = (2 * gh - 1) * (2 * gw - 1);
+    if (table)
+        for (int i = tid; i < n_off; i += 128) sT[i] = table[(long long)h * n_off + i];
+    __syncthreads();
+    const BiasIdx bias = make_bias(table ? sT : nullptr, gh, gw);
+    const uint32_t tQ = smem_u32(sQ), tdO = smem_u32(sdO);
+    uint32_t ka[2][4], va[2][4];
+    load_a_frags(ka, smem_u32(sK), warp * 16, lane);
+    load_a_frags(va, smem_u32(sV), warp * 16, lane);
+    const int g = lane >> 2, t = lane & 3;
+    const int j0 = jb * 64 + warp * 16 + g, j1 = j0 + 8;       // this thread's two key rows
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        dk[a][0] = dk[a][1] = dk[a][2] = dk[a][3] = 0.f;
+        dv[a][0] = dv[a][1] = dv[a][2] = dv[a][3] = 0.f;
+    }
+    for (int ib = 0; ib < Lp; ib += 64) {
+        float st[8][4], dpt[8][4];
+        mma_16x64(st, ka, tQ, ib, lane);          // S^T[key, query] = K Q^T
+        mma_16x64(dpt, va, tdO, ib, lane);        // dP^T[key, query] = V dO^T
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = ib + nt * 8 + 2 * t + (e & 1);   // query (column)
+                const int j = (e < 2) ? j0 : j1;               // key (row)
+                const float x = (st[nt][e] + bias(min(i, L - 1), min(j, L - 1))) * LOG2E;
+                const float p = (i < L && j < L) ? exp2f(x - sL[i]) : 0.f;
+                st[nt][e] = p;
+                dpt[nt][e] = p * (dpt[nt][e] - sD[i]);         // dS^T
+            }
+        mma_acc_16x32(dv, st, tdO, ib, lane);     // dV += P^T dO
+        mma_acc_16x32(dk, dpt, tQ, ib, lane);     // dK += dS^T Q
+    }
+    __nv_bfloat16* ob = dqkv + (long long)s * L * ld + h * 32;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int d = a * 8 + 2 * t;
+        if (j0 < L) {
+            *reinterpret_cast<uint32_t*>(ob + (long long)j0 * ld + inner + d) = pack_bf16x2(dk[a][0], dk[a][1]);
+            *reinterpret_cast<uint32_t*>(ob + (long long)j0 * ld + 2 * inner + d) = pack_bf16x2(dv[a][0], dv[a][1]);
+        }
+        if (j1 < L) {
+            *reinterpret_cast<uint32_t*>(ob + (long long)j1 * ld + inner + d) = pack_bf16x2(dk[a][2], dk[a][3]);
+            *reinterpret_cast<uint32_t*>(ob + (long long)j1 * ld + 2 * inner + d) = pack_bf16x2(dv[a][2], dv[a][3]);
+        }
+    }
+}
+
+// =============================================================================================
+// backward, bias table: grid (kv blocks, q blocks, heads); loops over sequences accumulating dS of
+// one 64x64 tile in registers, then scatters into the (2gh-1)(2gw-1) table with atomics.
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+attn_bwd_dbias_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
+                      const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                      const float* __restrict__ delta, float* __restrict__ dtable, int nseq, int L,
+                      int heads, int gh, int gw) {
+    __shared__ __align__(128) uint8_t sQ[64 * 64], sdO[64 * 64], sK[64 * 64], sV[64 * 64];
+    extern __shared__ __align__(128) float sT[];
+    const int jb = blockIdx.x, qb = blockIdx.y, h = blockIdx.z;
+    const int inner = heads * 32;
+    const long long ld = 3LL * inner;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_off = (2 * gh - 1) * (2 * gw - 1);
+    for (int i = tid; i < n_off; i += 128) sT[i] = table[(long long)h * n_off + i];
+    const BiasIdx bias = make_bias(sT, gh, gw);
+    const int g = lane >> 2, t = lane & 3;
+    const int i0 = qb * 64 + warp * 16 + g, i1 = i0 + 8;
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    for (int s = 0; s < nseq; ++s) {
+        __syncthreads();
+        const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
+        load_tile(sQ, base + (long long)qb * 64 * ld, ld, 64, L - qb * 64, tid, 128);
+        load_tile(sdO, dout + ((long long)s * L + qb * 64) * inner + h * 32, inner, 64, L - qb * 64, tid, 128);
+        load_tile(sK, base + inner + (long long)jb * 64 * ld, ld, 64, L - jb * 64, tid, 128);
+        load_tile(sV, base + 2 * inner + (long long)jb * 64 * ld, ld, 64, L - jb * 64, tid, 128);
+        __syncthreads();
+        uint32_t qa[2][4], da[2][4];
+        load_a_frags(qa, smem_u32(sQ), warp * 16, lane);
+        load_a_frags(da, smem_u32(sdO), warp * 16, lane);
+        const float* lp = lse + ((long long)s * heads + h) * L;
+        const float* dp = delta + ((long long)s * heads + h) * L;
+        const float lse0 = (i0 < L ? lp[i0] : 0.f) * LOG2E, lse1 = (i1 < L ? lp[i1] : 0.f) * LOG2E;
+        const float dl0 = i0 < L ? dp[i0] : 0.f, dl1 = i1 < L ? dp[i1] : 0.f;
+        float sc[8][4], dpv[8][4];
+        mma_16x64(sc, qa, smem_u32(sK), 0, lane);
+        mma_16x64(dpv, da, smem_u32(sV), 0, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = jb * 64 + nt * 8 + 2 * t + (e & 1);
+                const int i = (e < 2) ? i0 : i1;
+                const float x = (sc[nt][e] + bias(min(i, L - 1), min(j, L - 1))) * LOG2E;
+                const float p = (j < L && i < L) ? exp2f(x - (e < 2 ? lse0 : lse1)) : 0.f;
+                acc[nt][e] += p * (dpv[nt][e] - (e < 2 ? dl0 : dl1));
+            }
+    }
+    float* dt = dtable + (long long)h * n_off;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = jb * 64 + nt * 8 + 2 * t + (e & 1);
+            const int i = (e < 2) ? i0 : i1;
+            if (i < L && j < L) atomicAdd(dt + bias.index(i, j), acc[nt][e]);
+        }
+}
+
+// =============================================================================================
+// short sequences (L <= 32): CTA per sequence, warp per head, lane per query (fwd, dq) / key (dk, dv)
+// smem: the sequence's packed qkv block [L][3*inner] bf16
+// =============================================================================================
+__device__ __forceinline__ void load_row32(const __nv_bfloat16* p, float (&v)[32]) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint4 u = s4[c];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16x2(w[e]);
+            v[c * 8 + e * 2] = f.x;
+            v[c * 8 + e * 2 + 1] = f.y;
+        }
+    }
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16* p, const float (&v)[32]) {
+    uint4* d4 = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        d4[c] = make_uint4(pack_bf16x2(v[c * 8], v[c * 8 + 1]), pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                           pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+}
+__device__ __forceinline__ float dot32(const float (&a)[32], const float (&b)[32]) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) s = fmaf(a[d], b[d], s);
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+attn_short_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                      float* __restrict__ lse, int L, int heads) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem);
+    const int s = blockIdx.x;
+    const int inner = heads * 32, ld = 3 * inner;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + (long long)s * L * ld);
+    for (int i = threadIdx.x; i < L * ld / 8; i += blockDim.x) reinterpret_cast<uint4*>(sq)[i] = __ldg(src + i);
+    __syncthreads();
+    const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
+    if (h >= heads || i >= L) return;
+    float q[32], o[32];
+    load_row32(sq + i * ld + h * 32, q);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < L; ++j) {
+        float kv[32];
+        load_row32(sq + j * ld + inner + h * 32, kv);
+        const float x = dot32(q, kv) * LOG2E;
+        const float mn = fmaxf(m, x);
+        const float r = exp2f(m - mn), p = exp2f(x - mn);
+        m = mn;
+        l = l * r + p;
+        load_row32(sq + j * ld + 2 * inner + h * 32, kv);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[d] = fmaf(p, kv[d], o[d] * r);
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] *= inv;
+    store_row32(out + ((long long)s * L + i) * inner + h * 32, o);
+    lse[((long long)s * heads + h) * L + i] = m * LN2 + logf(l);
+}
+
+// smem: qkv block | dO block [L][inner] | lse [heads][32] | delta [heads][32]
+__global__ void __launch_bounds__(256)
+attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
+                      const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                      __nv_bfloat16* __restrict__ dqkv, int L, int heads) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int inner = heads * 32, ld = 3 * inner;
+    __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem);
+    __nv_bfloat16* sdo = sq + L * ld;
+    float* sL = reinterpret_cast<float*>(sdo + L * inner);
+    float* sD = sL + heads * 32;
+    const int s = blockIdx.x;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(qkv + (long long)s * L * ld);
+        for (int i = threadIdx.x; i < L * ld / 8; i += blockDim.x) reinterpret_cast<uint4*>(sq)[i] = __ldg(src + i);
+        const uint4* src2 = reinterpret_cast<const uint4*>(dout + (long long)s * L * inner);
+        for (int i = threadIdx.x; i < L * inner / 8; i += blockDim.x) reinterpret_cast<uint4*>(sdo)[i] = __ldg(src2 + i);
+    }
+    const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
+    const bool active = h < heads && i < L;
+    __syncthreads();
+    if (active) {
+        float a[32], b[32];
+        load_row32(out + ((long long)s * L + i) * inner + h * 32, a);
+        load_row32(sdo + i * inner + h * 32, b);
+        sD[h * 32 + i] = dot32(a, b);
+        sL[h * 32 + i] = lse[((long long)s * heads + h) * L + i] * LOG2E;
+    }
+    __syncthreads();
+    if (!active) return;
+    // pass A: lane = query i -> dq
+    {
+        float q[32], dO[32], dq[32];
+        load_row32(sq + i * ld + h * 32, q);
+        load_row32(sdo + i * inner + h * 32, dO);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) dq[d] = 0.f;
+        const float li = sL[h * 32 + i], di = sD[h * 32 + i];
+        for (int j = 0; j < L; ++j) {
+            float kk[32], vv[32];
+            load_row32(sq + j * ld + inner + h * 32, kk);
+            load_row32(sq + j * ld + 2 * inner + h * 32, vv);
+            const float p = exp2f(dot32(q, kk) * LOG2E - li);
+            const float ds = p * (dot32(dO, vv) - di);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) dq[d] = fmaf(ds, kk[d], dq[d]);
+        }
+        store_row32(dqkv + ((long long)s * L + i) * ld + h * 32, dq);
+    }
+    // pass B: lane = key j -> dk, dv
+    {
+        const int j = i;
+        float kk[32], vv[32], dk[32], dv[32];
+        load_row32(sq + j * ld + inner + h * 32, kk);
+        load_row32(sq + j * ld + 2 * inner + h * 32, vv);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+        for (int qi = 0; qi < L; ++qi) {
+            float q[32], dO[32];
+            load_row32(sq + qi * ld + h * 32, q);
+            load_row32(sdo + qi * inner + h * 32, dO);
+            const float p = exp2f(dot32(q, kk) * LOG2E - sL[h * 32 + qi]);
+            const float ds = p * (dot32(dO, vv) - sD[h * 32 + qi]);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+                dk[d] = fmaf(ds, q[d], dk[d]);
+                dv[d] = fmaf(p, dO[d], dv[d]);
+            }
+        }
+        store_row32(dqkv + ((long long)s * L + j) * ld + inner + h * 32, dk);
+        store_row32(dqkv + ((long long)s * L + j) * ld + 2 * inner + h * 32, dv);
+    }
+}
+
+// =============================================================================================
+// backward of the qk l2norm + per-channel scale (epilogue CTK_EPI_QKV). Warp per (row, q|k head),
+// lane = channel. In place on dqkv columns [0, 2*inner).
+//   y = xhat * sc, sc = alpha*q_scale (q) or k_scale (k);  g = dy*sc;  dx = rnorm (g - xhat <xhat, g>)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+qknorm_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, const __nv_bfloat16* __restrict__ qkv,
+                  const float* __restrict__ rnorm, const float* __restrict__ q_scale,
+                  const float* __restrict__ k_scale, float alpha, float* __restrict__ dq_scale,
+                  float* __restrict__ dk_scale, long long rows, int heads) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int inner = heads * 32;
+    const long long ld = 3LL * inner;
+    const float qs = q_scale[lane], ks = k_scale[lane];
+    float acc_q = 0.f, acc_k = 0.f;
+    const long long total = rows * 2 * heads;
+    for (long long w = warp_global; w < total; w += nwarps) {
+        const long long row = w / (2 * heads);
+        const int slot = (int)(w % (2 * heads));           // [0,heads): q heads, [heads,2heads): k heads
+        const bool is_q = slot < heads;
+        const long long off = row * ld + (long long)slot * 32 + lane;
+        const float sc = is_q ? qs * alpha : ks;
+        const float y = __bfloat162float(qkv[off]);
+        const float dy = __bfloat162float(dqkv[off]);
+        const float xh = sc != 0.f ? y / sc : 0.f;
+        const float gg = dy * sc;
+        const float dotv = warp_sum(xh * gg);
+        const float rn = rnorm[row * 2 * heads + slot];
+        dqkv[off] = __float2bfloat16(rn * (gg - xh * dotv));
+        if (is_q) acc_q = fmaf(dy * xh, alpha, acc_q); else acc_k = fmaf(dy, xh, acc_k);
+    }
+    atomicAdd(dq_scale + lane, acc_q);
+    atomicAdd(dk_scale + lane, acc_k);
+}
+
+}  // namespace
+
+static size_t fwd_smem(int L, int gh, int gw, bool bias) {
+    const int Lp = (L + 63) & ~63;
+    return (size_t)Lp * 128 + 64 * 64 + (bias ? (size_t)(2 * gh - 1) * (2 * gw - 1) * 4 : 0);
+}
+
+extern "C" int ctk_attn_fwd(const void* qkv, const float* table, void* out, float* lse, int nseq, int L,
+                            int heads, int gh, int gw, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(qkv && out && lse && nseq > 0 && L > 0 && heads > 0 && heads <= 8, CTK_ERR_SHAPE, "attn_fwd: bad args");
+    CTK_REQUIRE(!table || gh * gw == L, CTK_ERR_SHAPE, "attn_fwd: bias table needs L == gh*gw");
+    CTK_REQUIRE(CTK_ALIGNED(qkv, 16) && CTK_ALIGNED(out, 16), CTK_ERR_ALIGN, "attn_fwd: alignment");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    auto o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (!table && L <= 32) {
+        const size_t sm = (size_t)L * 3 * heads * 32 * 2;
+        CTK_CUDA(cudaFuncSetAttribute(attn_short_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        attn_short_fwd_kernel<<<nseq, heads * 32, sm, s>>>(q, o, lse, L, heads);
+        CTK_LAUNCH_CHECK();
+        return CTK_OK;
+    }
+    const size_t sm = fwd_smem(L, gh, gw, table != nullptr);
+    CTK_REQUIRE(sm <= 220 * 1024, CTK_ERR_SHAPE, "attn_fwd: sequence of %d tokens does not fit in shared memory", L);
+    CTK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    attn_fwd_kernel<<<dim3((L + 63) / 64, heads, nseq), 128, sm, s>>>(q, table, o, lse, L, heads, gh, gw);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_attn_bwd(const void* qkv, const float* table, const void* out, const void* dout,
+                            const float* lse, float* delta, void* dqkv, float* dtable, int nseq, int L,
+                            int heads, int gh, int gw, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(qkv && out && dout && lse && delta && dqkv && nseq > 0 && L > 0 && heads > 0 && heads <= 8,
+                CTK_ERR_SHAPE, "attn_bwd: bad args");
+    CTK_REQUIRE(!table || (gh * gw == L && dtable), CTK_ERR_SHAPE, "attn_bwd: bias table needs L == gh*gw and dtable");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    auto o = reinterpret_cast<const __nv_bfloat16*>(out);
+    auto d_o = reinterpret_cast<const __nv_bfloat16*>(dout);
+    auto dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
+    const int inner = heads * 32;
+    if (!table && L <= 32) {
+        const size_t sm = (size_t)L * 3 * inner * 2 + (size_t)L * inner * 2 + (size_t)heads * 32 * 4 * 2;
+        CTK_CUDA(cudaFuncSetAttribute(attn_short_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        attn_short_bwd_kernel<<<nseq, heads * 32, sm, s>>>(q, o, d_o, lse, dq, L, heads);
+        CTK_LAUNCH_CHECK();
+        return CTK_OK;
+    }
+    const long long rows = (long long)nseq * L;
+    attn_delta_kernel<<<(unsigned)((rows * heads + 255) / 256), 256, 0, s>>>(o, d_o, delta, rows, L, heads);
+    CTK_LAUNCH_CHECK();
+    const int Lp = (L + 63) & ~63;
+    const size_t tab = table ? (size_t)(2 * gh - 1) * (2 * gw - 1) * 4 : 0;
+    const size_t sm_dq = (size_t)Lp * 128 + 2 * 64 * 64 + tab;
+    const size_t sm_dkv = (size_t)Lp * 128 + 2 * 64 * 64 + (size_t)Lp * 8 + tab;
+    CTK_REQUIRE(sm_dkv <= 220 * 1024, CTK_ERR_SHAPE, "attn_bwd: sequence of %d tokens does not fit in shared memory", L);
+    CTK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq));
+    CTK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dkv));
+    const dim3 grid((L + 63) / 64, heads, nseq);
+    attn_bwd_dq_kernel<<<grid, 128, sm_dq, s>>>(q, table, d_o, lse, delta, dq, L, heads, gh, gw);
+    CTK_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<<<grid, 128, sm_dkv, s>>>(q, table, d_o, lse, delta, dq, L, heads, gh, gw);
+    CTK_LAUNCH_CHECK();
+    if (table) {
+        const int nb = (L + 63) / 64;
+        attn_bwd_dbias_kernel<<<dim3(nb, nb, heads), 128, tab, s>>>(q, table, d_o, lse, delta, dtable, nseq, L, heads, gh, gw);
+        CTK_LAUNCH_CHECK();
+    }
+    return CTK_OK;
+}
+
+extern "C" int ctk_qknorm_bwd(void* dqkv, const void* qkv, const float* rnorm, const float* q_scale,
+                              const float* k_scale, float alpha, float* dq_scale, float* dk_scale,
+                              long long rows, int heads, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(dqkv && qkv && rnorm && q_scale && k_scale && dq_scale && dk_scale && rows > 0 && heads > 0,
+                CTK_ERR_SHAPE, "qknorm_bwd: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    long long blocks = (rows * 2 * heads + 7) / 8;
+    const long long cap = (long long)ctk_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    qknorm_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(dqkv),
+                                                       reinterpret_cast<const __nv_bfloat16*>(qkv), rnorm,
+                                                       q_scale, k_scale, alpha, dq_scale, dk_scale, rows, heads);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}

@@ -7,7 +7,8 @@
 // 256 threads; thread (ty, tx) = (tid / 16, tid % 16) owns rows m0+ty*4..+3, cols n0+tx*4..+3.
 // A row-major [M, K]; B row-major [N, K] when BT (C = A * B^T) else row-major [K, N] (C = A * B).
 // smem: As, Bs = float[16][68] each.
-template <bool BT>
+// AT: A is stored transposed, row-major [K, M] (C = A^T * B).
+template <bool BT, bool AT = false>
 __device__ __forceinline__ void sgemm_tile_64x64(const float* __restrict__ A, long long lda,
                                                  const float* __restrict__ B, long long ldb,
                                                  int m0, int n0, int M, int N, int K,
@@ -22,7 +23,15 @@ __device__ __forceinline__ void sgemm_tile_64x64(const float* __restrict__ A, lo
 
     for (int k0 = 0; k0 < K; k0 += 16) {
         // A tile: 64 rows x 16 k -> As[k][row]
-        {
+        if (AT) {
+            const int kk = tid >> 4, c = (tid & 15) * 4;
+            const int gk = k0 + kk;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int gm = m0 + c + q;
+                As[kk][c + q] = (gk < K && gm < M) ? A[(long long)gk * lda + gm] : 0.f;
+            }
+        } else {
             const int r = tid >> 2, kk = (tid & 3) * 4;
             const int gr = m0 + r;
 #pragma unroll

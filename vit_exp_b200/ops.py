@@ -153,3 +153,162 @@ def fill_(t: torch.Tensor, v: float):
     _chk(t, torch.float32, "t")
     check(_lib.load().ctk_fill_f32(_p(t), v, t.numel(), _stream()), "ctk_fill_f32")
     return t
+
+
+# --------------------------------------------------------------------------- encoder ops
+def patch_norm_fwd(video: torch.Tensor, pt: int, p1: int, p2: int, eps: float = 1e-5):
+    """video fp32 [B,1,D,H,W] -> (xhat bf16 [B*T*Hp*Wp, ld], mean, rstd); ld = K rounded up to 8."""
+    _chk(video, torch.float32, "video")
+    B, Cc, D, H, W = video.shape
+    assert Cc == 1, "CT volumes are single channel"
+    K = pt * p1 * p2
+    ld = (K + 7) // 8 * 8
+    rows = B * (D // pt) * (H // p1) * (W // p2)
+    xhat = torch.empty(rows, ld, dtype=torch.bfloat16, device=video.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=video.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=video.device)
+    check(_lib.load().ctk_patch_norm_fwd(_p(video), _p(xhat), ld, _p(mean), _p(rstd), B, D, H, W, pt, p1, p2, eps,
+                                         _stream()), "ctk_patch_norm_fwd")
+    return xhat, mean, rstd
+
+
+def layernorm_fwd(x, gamma, beta=None, *, want_bf16=True, want_f32=False, want_raw=False, eps=1e-5,
+                  perm_outer=0, perm_inner=0, save_stats=True):
+    _chk(x, torch.float32, "x")
+    rows, dim = x.shape
+    dev = x.device
+    ob = torch.empty(rows, dim, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    of = torch.empty(rows, dim, dtype=torch.float32, device=dev) if want_f32 else None
+    raw = torch.empty(rows, dim, dtype=torch.bfloat16, device=dev) if want_raw else None
+    mean = torch.empty(rows, dtype=torch.float32, device=dev) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev) if save_stats else None
+    check(_lib.load().ctk_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(ob), _p(of), _p(raw), _p(mean), _p(rstd),
+                                        rows, dim, eps, perm_outer, perm_inner, _stream()), "ctk_layernorm_fwd")
+    return ob, of, raw, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta=None, *, dx=None, accum=False, perm_outer=0,
+                  perm_inner=0, bcast_rows=0, dy_scale=1.0):
+    """dy bf16 or fp32; returns dx (fp32). dgamma/dbeta accumulate (must be zero-initialised)."""
+    rows, dim = x.shape
+    if dx is None:
+        assert not accum
+        dx = torch.empty_like(x)
+    dyb = dy if dy.dtype == torch.bfloat16 else None
+    dyf = dy if dy.dtype == torch.float32 else None
+    assert dy.is_contiguous() and (dyb is not None or dyf is not None)
+    check(_lib.load().ctk_layernorm_bwd(_p(dyb), _p(dyf), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), int(accum),
+                                        _p(dgamma), _p(dbeta), rows, dim, perm_outer, perm_inner, bcast_rows,
+                                        dy_scale, _stream()), "ctk_layernorm_bwd")
+    return dx
+
+
+def peg_fwd(x, w, b, shape):
+    """x fp32 [B*n0*n1*n2, dim] viewed as the grid `shape`=(B,n0,n1,n2); returns conv(x)+b+x."""
+    _chk(x, torch.float32, "x")
+    B, n0, n1, n2 = shape
+    dim = x.shape[-1]
+    y = torch.empty_like(x)
+    check(_lib.load().ctk_peg_fwd(_p(x), _p(w), _p(b), _p(y), B, n0, n1, n2, dim, _stream()), "ctk_peg_fwd")
+    return y
+
+
+def peg_bwd(dy, x, w, shape, dw, db):
+    B, n0, n1, n2 = shape
+    dim = x.shape[-1]
+    dx = torch.empty_like(dy)
+    check(_lib.load().ctk_peg_bwd(_p(dy), _p(x), _p(w), _p(dx), _p(dw), _p(db), B, n0, n1, n2, dim, _stream()), "ctk_peg_bwd")
+    return dx
+
+
+def cpb_fwd(w0, b0, w1, b1, w2, b2, gh: int, gw: int):
+    dim, heads = w1.shape[0], w2.shape[0]
+    n_off = (2 * gh - 1) * (2 * gw - 1)
+    dev = w0.device
+    h0 = torch.empty(n_off, dim, dtype=torch.float32, device=dev)
+    h1 = torch.empty(n_off, dim, dtype=torch.float32, device=dev)
+    table = torch.empty(heads, 2 * gh - 1, 2 * gw - 1, dtype=torch.float32, device=dev)
+    check(_lib.load().ctk_cpb_fwd(_p(w0), _p(b0), _p(w1), _p(b1), _p(w2), _p(b2), _p(h0), _p(h1), _p(table), gh, gw,
+                                  dim, heads, _stream()), "ctk_cpb_fwd")
+    return table, h0, h1
+
+
+def cpb_bwd(dtable, w0, w1, w2, h0, h1, gh: int, gw: int):
+    dim, heads = w1.shape[0], w2.shape[0]
+    dev = w0.device
+    n_off = (2 * gh - 1) * (2 * gw - 1)
+    g = [torch.empty_like(w0), torch.empty(dim, device=dev), torch.empty_like(w1), torch.empty(dim, device=dev),
+         torch.empty_like(w2), torch.empty(heads, device=dev)]
+    ws = torch.empty(2 * n_off * dim, dtype=torch.float32, device=dev)
+    check(_lib.load().ctk_cpb_bwd(_p(dtable), _p(w0), _p(w1), _p(w2), _p(h0), _p(h1), *[_p(t) for t in g], _p(ws), gh,
+                                  gw, dim, heads, _stream()), "ctk_cpb_bwd")
+    return g
+
+
+def attn_fwd(qkv, table, nseq: int, L: int, heads: int, gh: int = 0, gw: int = 0):
+    _chk(qkv, torch.bfloat16, "qkv")
+    dev = qkv.device
+    out = torch.empty(nseq * L, heads * 32, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(nseq, heads, L, dtype=torch.float32, device=dev)
+    check(_lib.load().ctk_attn_fwd(_p(qkv), _p(table), _p(out), _p(lse), nseq, L, heads, gh, gw, _stream()), "ctk_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, table, out, dout, lse, dtable, nseq: int, L: int, heads: int, gh: int = 0, gw: int = 0):
+    _chk(dout, torch.bfloat16, "dout")
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    check(_lib.load().ctk_attn_bwd(_p(qkv), _p(table), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), _p(dtable), nseq,
+                                   L, heads, gh, gw, _stream()), "ctk_attn_bwd")
+    return dqkv
+
+
+def qknorm_bwd_(dqkv, qkv, rnorm, q_scale, k_scale, alpha: float, dq_scale, dk_scale, heads: int):
+    rows = qkv.shape[0]
+    check(_lib.load().ctk_qknorm_bwd(_p(dqkv), _p(qkv), _p(rnorm), _p(q_scale), _p(k_scale), alpha, _p(dq_scale),
+                                     _p(dk_scale), rows, heads, _stream()), "ctk_qknorm_bwd")
+    return dqkv
+
+
+def l2norm_rows(x, want_f32: bool = False):
+    _chk(x, torch.float32, "x")
+    rows, dim = x.shape
+    xb = torch.empty(rows, dim, dtype=torch.bfloat16, device=x.device)
+    xf = torch.empty(rows, dim, dtype=torch.float32, device=x.device) if want_f32 else None
+    check(_lib.load().ctk_l2norm_rows(_p(x), _p(xb), _p(xf), rows, dim, _stream()), "ctk_l2norm_rows")
+    return xb, xf
+
+
+def vq_gather(best, embed):
+    rows = best.shape[0]
+    C, dim = embed.shape
+    ind = torch.empty(rows, dtype=torch.int64, device=embed.device)
+    quant = torch.empty(rows, dim, dtype=torch.float32, device=embed.device)
+    check(_lib.load().ctk_vq_gather(_p(best), _p(embed), _p(ind), _p(quant), rows, dim, C, _stream()), "ctk_vq_gather")
+    return ind, quant
+
+
+def vq_ema_update_(xn_f32, ind, cluster_size, embed, decay: float = 0.8):
+    C, dim = embed.shape
+    ws = torch.empty(C * dim + C, dtype=torch.float32, device=embed.device)
+    check(_lib.load().ctk_vq_ema_update(_p(xn_f32), _p(ind), _p(cluster_size), _p(embed), _p(ws), xn_f32.shape[0], dim, C,
+                                        decay, _stream()), "ctk_vq_ema_update")
+
+
+def patch_affine_bwd(P, W, gamma, beta, db):
+    n, k = W.shape
+    dW = torch.empty_like(W)
+    dgamma = torch.empty_like(gamma)
+    dbeta = torch.empty_like(beta)
+    check(_lib.load().ctk_patch_affine_bwd(_p(P), _p(W), _p(gamma), _p(beta), _p(db), _p(dW), _p(dgamma), _p(dbeta), n, k,
+                                           _stream()), "ctk_patch_affine_bwd")
+    return dW, dgamma, dbeta
+
+
+def colsum_(dy, out):
+    """out[cols] += column sums of dy [rows, cols] (bf16 or fp32)."""
+    rows, cols = dy.shape
+    dyb = dy if dy.dtype == torch.bfloat16 else None
+    dyf = dy if dy.dtype == torch.float32 else None
+    check(_lib.load().ctk_colsum(_p(dyb), _p(dyf), _p(out), rows, cols, _stream()), "ctk_colsum")
+    return out
