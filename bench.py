@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py - CT volumes/s of one CT-CLIP train step (BASELINE.json north star) on N B200s.
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (libctk CUDA path)
+  python bench.py --impl reference [...]                   the reference's CPU path (oracle port) on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...         one rank per GPU over NCCL
+
+One step = forward + backward + all-gather of latents + DDP gradient all-reduce + grad-norm clip 0.5
++ Adam(lr 1.25e-6, betas (0.9, 0.99)) on a batch of synthetic CT-RATE-shaped volumes
+(B, 1, 240, 480, 480) fp32 and (B, 512) token ids, random-init CTViT(dim 512, 4+4) and a random-init
+BERT-base-shaped text encoder.  Per-GPU batch is fixed (weak scaling):
+8 volumes / GPU -> global batch 64 at 8 GPUs, the configuration BASELINE.json quotes.
+
+`value`  : volumes/s with the batch already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same step driven through the public CTCLIP.forward API with HOST (pinned) inputs: the
+           H2D copy of every step's batch and the D2H read of the loss are inside the timed region
+           (the copy of step i+1 is issued on a side stream while step i computes).
+`roofline`: all tcgen05 GEMM launches of a step, timed with CUDA events on the launching stream in an
+           extra instrumented step; algorithmic FLOPs from SURVEY.md 8d.
+`cpu_baseline`: the oracle port of the reference timed on this box's host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOL = (240, 480, 480)
+TEXT_LEN = 512
+PER_GPU_BATCH = 8
+# algorithmic GFLOP per volume executed by ctk_gemm_bf16 launches (SURVEY.md 8d / BASELINE.md 4):
+GF_PATCH = 56.62
+GF_LAYER_GEMM = 3.62 + 7.25 + 3.62 + 38.65 + 19.32        # q, kv, out, FF1, FF2 (attention core excluded)
+GF_VQ = 116.0
+GF_GEMM_FWD = GF_PATCH + 8 * GF_LAYER_GEMM + GF_VQ
+GF_GEMM_BWD = GF_PATCH + 2 * 8 * GF_LAYER_GEMM             # patch: wgrad only; layers: dgrad + wgrad
+GF_GEMM_STEP = GF_GEMM_FWD + GF_GEMM_BWD
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1349.9), d.get("hbm_gbs", 6547.8), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_model(dev, seed=0):
+    import torch
+    from transformers import BertConfig, BertModel
+    from vit_exp_b200.ct_clip import CTCLIP
+    from vit_exp_b200.transformer_maskgit import CTViT
+    torch.manual_seed(seed)
+    vit = CTViT(dim=512, codebook_size=8192, image_size=480, patch_size=20, temporal_patch_size=10,
+                spatial_depth=4, temporal_depth=4, dim_head=32, heads=8)          # run_train.py:56-66
+    bert = BertModel(BertConfig(vocab_size=30522, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=512, dim_latent=512, config={})
+    return clip.to(dev)
+
+
+class AutocastText:
+    """runs the (stock PyTorch) text encoder under bf16 autocast; everything else is libctk."""
+
+    def __init__(self, bert):
+        self.bert = bert
+
+    def __call__(self, input_ids, attention_mask=None):
+        import torch
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return self.bert(input_ids, attention_mask=attention_mask)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vit_exp_b200 import _lib, ops
+    from vit_exp_b200.ct_clip import TorchDistAccelerator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    lib = _lib.load()
+    B = args.batch_per_gpu
+
+    clip = build_model(dev, seed=0)
+    clip.train()
+    bert = clip.text_transformer
+    model = clip
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], find_unused_parameters=True,
+                                                          gradient_as_bucket_view=True)
+    params = [p for p in clip.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1.25e-6, betas=(0.9, 0.99), fused=True)      # optimizer.py:14,23-24
+    acc = TorchDistAccelerator()
+
+    # synthetic CT-RATE-shaped host batch in pinned memory (two buffers -> consecutive steps differ)
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_vid = [torch.rand(B, 1, *VOL, generator=g).pin_memory() for _ in range(2)]
+    host_ids = [torch.randint(0, 30522, (B, TEXT_LEN), generator=g).pin_memory() for _ in range(2)]
+    dev_vid = [torch.empty(B, 1, *VOL, device=dev) for _ in range(2)]
+    dev_ids = [torch.empty(B, TEXT_LEN, dtype=torch.int64, device=dev) for _ in range(2)]
+    mask = torch.ones(B, TEXT_LEN, dtype=torch.int64, device=dev)
+    copy_stream = torch.cuda.Stream()
+
+    def text_forward_patch():
+        # bf16 autocast for the stock-PyTorch text tower only
+        orig = bert.forward
+        def fwd(*a, **k):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return orig(*a, **k)
+        bert.forward = fwd
+    text_forward_patch()
+
+    def h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            dev_vid[slot].copy_(host_vid[slot], non_blocking=True)
+            dev_ids[slot].copy_(host_ids[slot], non_blocking=True)
+
+    def step(slot):
+        batch = {"data_type": ["imagereport"] * B,
+                 "text": SimpleNamespace(input_ids=dev_ids[slot], attention_mask=mask), "image": dev_vid[slot]}
+        loss, ld = model(batch, device=dev, accelerator=acc, return_loss=True, return_loss_dict=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 0.5)                            # CTCLIPTrainer.py:711-712
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return ld["cl_loss"]                                                     # float: D2H read of the loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(k)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), out
+
+    # inputs resident for the device-timed loop
+    for s in range(2):
+        h2d(s)
+    copy_stream.synchronize()
+    log(f"[rank {rank}] warm-up {args.warmup} steps, B={B}/GPU")
+    loss_val = None
+    for i in range(args.warmup):
+        loss_val = step(i % 2)
+
+    # ---- value: K steps, inputs in HBM (each volume batch 1.77 GB >> 126 MB L2) -----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.ctk_launch_count()
+    ms_dev, _ = timed(lambda k: [step(i % 2) for i in range(k)], args.steps)
+    launches = (lib.ctk_launch_count() - n0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host inputs, H2D of step i+1 overlapped with step i, loss read back every step -----
+    def e2e_loop(k):
+        h2d(0)
+        last = None
+        for i in range(k):
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            if i + 1 < k:
+                # the next batch lands in the other slot; it is free once step i-1 finished reading it
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                h2d((i + 1) % 2)
+            last = step(i % 2)
+        return last
+    ms_e2e, loss_val = timed(e2e_loop, args.steps)
+
+    # ---- roofline: instrument every tcgen05 GEMM launch of one more step --------------------------
+    ops.GEMM_PROFILE = []
+    step(0)
+    torch.cuda.synchronize()
+    prof = ops.GEMM_PROFILE
+    ops.GEMM_PROFILE = None
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    by_epi = {}
+    for a, b, tag in prof:
+        by_epi[tag] = by_epi.get(tag, 0.0) + a.elapsed_time(b)
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    achieved_tf = GF_GEMM_STEP * B / gemm_ms                                   # GFLOP / ms == TFLOP/s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    vols = B * world * args.steps
+    line = {
+        "metric": "CT volumes/s, CT-CLIP train step", "value": vols / (ms_dev / 1e3), "unit": "volumes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "impl": "ours",
+        "config": {"workload": "ctclip_train_step: CTViT(dim512, 4 spatial + 4 temporal, heads 8x32, patch 20x20x10 of "
+                               "480x480x240) + random-init BERT-base text tower + all-gathered InfoNCE + clip 0.5 + Adam",
+                   "per_gpu_batch": B, "global_batch": B * world, "text_len": TEXT_LEN, "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2 (1.77 GB of volumes per step); two alternating batches",
+                   "text_tower": "stock PyTorch BertModel under bf16 autocast"},
+        "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s",
+                "h2d_bytes_per_step": int(host_vid[0].numel() * 4 + host_ids[0].numel() * 8), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<EPI, major> (tcgen05 128x256x64, all launches of one step)",
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                     "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": len(prof),
+                     "gemm_share_of_step": gemm_ms / (ms_dev / args.steps),
+                     "algorithmic_gflop_per_volume": GF_GEMM_STEP, "ms_by_epilogue": by_epi},
+        "loss": loss_val,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_train_step_baseline(max_steps=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's train step on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_baseline(max_steps=1, warmup=0, budget_s=240.0):
+    """One CT-CLIP train step (B=2: B=1 makes the contrastive loss identically 0) through the CPU
+    oracle: CTViT fwd+bwd by autograd over oracle.ctclip_oracle, HF BertModel, loss, clip, Adam."""
+    import torch
+    from transformers import BertConfig, BertModel
+    from oracle import ctclip_oracle as orc
+    from vit_exp_b200.transformer_maskgit import CTViT
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    B = 2
+    vit = CTViT(dim=512, codebook_size=8192, image_size=480, patch_size=20, temporal_patch_size=10,
+                spatial_depth=4, temporal_depth=4, dim_head=32, heads=8)          # parameter container only
+    bert = BertModel(BertConfig(vocab_size=30522, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    wt = torch.nn.Parameter(torch.randn(512, 768) * 768 ** -0.5)
+    wv = torch.nn.Parameter(torch.randn(512, 512) * 512 ** -0.5)
+    temp = torch.nn.Parameter(torch.tensor(1.0))
+    p = dict(vit.named_parameters())
+    p.update(dict(vit.named_buffers()))
+    train_params = [q for q in list(vit.parameters()) + list(bert.parameters()) + [wt, wv, temp] if q.numel() > 0]
+    opt = torch.optim.Adam(train_params, lr=1.25e-6, betas=(0.9, 0.99))
+    g = torch.Generator().manual_seed(0)
+    video = torch.rand(B, 1, *VOL, generator=g)
+    ids = torch.randint(0, 30522, (B, TEXT_LEN), generator=g)
+
+    def one():
+        enc_text = bert(ids, attention_mask=torch.ones_like(ids))[0]
+        enc = orc.ctvit_forward(video, p, patch=20, tpatch=10, spatial_depth=4, temporal_depth=4, heads=8, vq=False)
+        q, _, _, _ = orc.vq_cosine(enc.detach(), p["vq._codebook.embed"][0])
+        tokens = enc + (q - enc).detach()                                       # straight-through
+        loss, _, _ = orc.ctclip_loss(enc_text, tokens, {"to_text_latent.weight": wt, "to_visual_latent.weight": wv,
+                                                        "temperature": temp})
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(train_params, 0.5)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.item()
+
+    times = []
+    t_begin = time.time()
+    for i in range(warmup + max_steps):
+        t0 = time.time()
+        loss = one()
+        dt = time.time() - t0
+        if i >= warmup:
+            times.append(dt)
+        log(f"[cpu] step {i} {dt:.1f}s loss {loss:.4f}")
+        if time.time() - t_begin + dt > budget_s:
+            break
+    if not times:
+        times = [dt]
+    sec = sum(times) / len(times)
+    return {"value": B / sec, "unit": "volumes/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} full train step(s) of B=2 volumes (1x240x480x480) + 2x512-token reports, fp32, "
+                      f"torch CPU oracle port (autograd), {sec:.1f} s/step", "steps_timed": len(times),
+            "ms_per_step": sec * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = min(args.warmup, 1)
+    res = cpu_train_step_baseline(max_steps=args.steps, warmup=warm, budget_s=280.0)
+    line = {
+        "metric": "CT volumes/s, CT-CLIP train step", "value": res["value"], "unit": "volumes/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": res["steps_timed"], "warmup": warm, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ctclip_train_step (CPU: bounded sample, B=2 volumes per step; the Python reference "
+                               "cannot travel to the GPU box, so the pinned oracle port runs in its place)",
+                   "per_gpu_batch": 2, "global_batch": 2, "text_len": TEXT_LEN, "parallelism": "cpu"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,8 @@ const char* ctk_last_error(void);
 int ctk_version(void);
 /* CTK_OK when the current CUDA device is sm_100-class, CTK_ERR_ARCH otherwise. */
 int ctk_device_ok(void);
+/* number of kernels this library has launched in the process so far (diagnostic counter only). */
+unsigned long long ctk_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction core (tcgen05 + TMEM + TMA).  D = A[M,K] * B[N,K]^T, bf16 in, fp32 accumulate.
@@ -123,12 +125,12 @@ int ctk_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
 /* dx (fp32) = LN backward of dy; dy is bf16 (dy_bf16) or fp32 (dy_f32), indexed through the same
  * row permutation as the forward output. dy_bcast_rows > 0: dy has rows/dy_bcast_rows rows and
  * row r reads dy[r / dy_bcast_rows] * dy_scale (gradient of a mean-pool broadcast back).
- * dx_accum != 0: dx += result. dgamma/dbeta (fp32 [dim], pre-zeroed) accumulate atomically;
- * dbeta may be NULL. */
+ * dx_accum != 0: dx += result. dx_bf16 (may be NULL) receives a bf16 copy of the final dx (the next
+ * GEMM's A operand). dgamma/dbeta (fp32 [dim], pre-zeroed) accumulate atomically; dbeta may be NULL. */
 int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
-                      const float* mean, const float* rstd, float* dx, int dx_accum, float* dgamma,
-                      float* dbeta, long long rows, int dim, int perm_outer, int perm_inner,
-                      long long dy_bcast_rows, float dy_scale, void* stream);
+                      const float* mean, const float* rstd, float* dx, void* dx_bf16, int dx_accum,
+                      float* dgamma, float* dbeta, long long rows, int dim, int perm_outer,
+                      int perm_inner, long long dy_bcast_rows, float dy_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * PEG (attention.py:62-90) + residual (attention.py:443): depthwise 3x3x3 conv over the token
@@ -137,9 +139,10 @@ int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, 
  * ------------------------------------------------------------------------------------------ */
 int ctk_peg_fwd(const float* x, const float* w, const float* b, float* y, int B, int n0, int n1,
                 int n2, int dim, void* stream);
-/* dx = conv^T(dy) + dy ; dw [dim,27], db [dim] accumulate atomically (pre-zeroed by caller). */
-int ctk_peg_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db,
-                int B, int n0, int n1, int n2, int dim, void* stream);
+/* dx = conv^T(dy) + dy (dx_bf16: optional bf16 copy); dw [dim,27], db [dim] accumulate atomically
+ * (pre-zeroed by caller). */
+int ctk_peg_bwd(const float* dy, const float* x, const float* w, float* dx, void* dx_bf16, float* dw,
+                float* db, int B, int n0, int n1, int n2, int dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * ContinuousPositionBias (attention.py:335-382) on the (2*gh-1)*(2*gw-1) distinct offsets

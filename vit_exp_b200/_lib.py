@@ -35,15 +35,16 @@ SIGNATURES = {
     "ctk_last_error": (C.c_char_p, []),
     "ctk_version": (_i, []),
     "ctk_device_ok": (_i, []),
+    "ctk_launch_count": (C.c_ulonglong, []),
     "ctk_gemm_bf16": (_i, [_vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _vp]),
     "ctk_cast_bf16": (_i, [_vp, _vp, _ll, _ll, _ll, _vp, _vp]),
     "ctk_transpose_cast_bf16": (_i, [_vp, _vp, _ll, _ll, _ll, _vp]),
     "ctk_pack_ff_w1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ctk_patch_norm_fwd": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "ctk_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp]),
-    "ctk_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _i, _i, _ll, _f, _vp]),
+    "ctk_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _i, _i, _ll, _f, _vp]),
     "ctk_peg_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "ctk_peg_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ctk_peg_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ctk_cpb_fwd": (_i, [_vp] * 9 + [_i, _i, _i, _i, _vp]),
     "ctk_cpb_bwd": (_i, [_vp] * 13 + [_i, _i, _i, _i, _vp]),
     "ctk_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

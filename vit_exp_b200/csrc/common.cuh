@@ -13,6 +13,7 @@
 // host-side error plumbing
 // ----------------------------------------------------------------------------------------------
 void ctk_set_error(const char* fmt, ...);
+void ctk_count_launch();  // diagnostic counter behind ctk_launch_count() (bench.py's gpu_launches)
 int ctk_check_device();   // CTK_OK or CTK_ERR_ARCH (no CPU / non-sm_100 fallback)
 
 #define CTK_REQUIRE(cond, code, ...)                                                   \
@@ -35,6 +36,7 @@ int ctk_check_device();   // CTK_OK or CTK_ERR_ARCH (no CPU / non-sm_100 fallbac
 
 #define CTK_LAUNCH_CHECK()                                                             \
     do {                                                                               \
+        ctk_count_launch();                                                            \
         cudaError_t e__ = cudaGetLastError();                                          \
         if (e__ != cudaSuccess) {                                                      \
             ctk_set_error("%s:%d launch -> %s", __FILE__, __LINE__,                    \

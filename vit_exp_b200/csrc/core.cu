@@ -30,6 +30,11 @@ int ctk_check_device() {
     return CTK_OK;
 }
 
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+void ctk_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long ctk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 extern "C" const char* ctk_last_error(void) { return g_err; }
 extern "C" int ctk_version(void) { return 100; }
 extern "C" int ctk_device_ok(void) { return ctk_check_device(); }

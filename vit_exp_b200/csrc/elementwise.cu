@@ -183,9 +183,9 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __restrict__ dy_f32,
                      const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                     float* __restrict__ dx, int dx_accum, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, long long rows, int perm_outer, int perm_inner,
-                     long long bcast_rows, float dy_scale) {
+                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16, int dx_accum,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
+                     int perm_outer, int perm_inner, long long bcast_rows, float dy_scale) {
     constexpr int DIM = NV * 64;
     __shared__ float sg[8][DIM + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -230,6 +230,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
                 o.x += p.x; o.y += p.y;
             }
             dxr[j * 32 + lane] = o;
+            if (dx_bf16)
+                reinterpret_cast<uint32_t*>(dx_bf16 + row * DIM)[j * 32 + lane] = pack_bf16x2(o.x, o.y);
         }
     }
     // reduce dgamma / dbeta across the CTA's warps
@@ -260,7 +262,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
 template <bool REVERSE>
 __global__ void __launch_bounds__(256)
 peg_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                float* __restrict__ y, int B, int n0, int n1, int n2, int dim) {
+                float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, int B, int n0, int n1, int n2,
+                int dim) {
     const int c2 = threadIdx.x;                                   // channel pair
     const long long line = (long long)blockIdx.x * blockDim.y + threadIdx.y;
     const long long nlines = (long long)B * n0 * n1;
@@ -312,6 +315,9 @@ peg_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
                 acc.y = fmaf(wt[l * 3 + k2].y, win[l][k2].y, acc.y);
             }
         yo[(long long)a2 * stride2] = acc;
+        if (y_bf16)
+            reinterpret_cast<uint32_t*>(y_bf16 + ((((long long)bb * n0 + a0) * n1 + a1) * n2 + a2) * dim)[c2] =
+                pack_bf16x2(acc.x, acc.y);
 #pragma unroll
         for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
     }
@@ -463,14 +469,14 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* o
 
 template <int NV>
 int launch_ln_bwd(const void* dyb, const float* dyf, const float* x, const float* gamma, const float* mean,
-                  const float* rstd, float* dx, int accum, float* dgamma, float* dbeta, long long rows,
+                  const float* rstd, float* dx, void* dxb, int accum, float* dgamma, float* dbeta, long long rows,
                   int po, int pi, long long bc, float sc, cudaStream_t s) {
     long long blocks = (rows + 7) / 8;
     const long long cap = (long long)ctk_num_sms() * 4;
     if (blocks > cap) blocks = cap;
     layernorm_bwd_kernel<NV><<<(int)blocks, 256, 0, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dyb), dyf, x, gamma, mean, rstd, dx, accum, dgamma, dbeta,
-        rows, po, pi, bc, sc);
+        reinterpret_cast<const __nv_bfloat16*>(dyb), dyf, x, gamma, mean, rstd, dx,
+        reinterpret_cast<__nv_bfloat16*>(dxb), accum, dgamma, dbeta, rows, po, pi, bc, sc);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
@@ -530,7 +536,7 @@ extern "C" int ctk_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x,
                                  const float* gamma, const float* mean, const float* rstd, float* dx,
-                                 int dx_accum, float* dgamma, float* dbeta, long long rows, int dim,
+                                 void* dx_bf16, int dx_accum, float* dgamma, float* dbeta, long long rows, int dim,
                                  int perm_outer, int perm_inner, long long dy_bcast_rows, float dy_scale,
                                  void* stream_) {
     int rc = ctk_check_device();
@@ -540,7 +546,7 @@ extern "C" int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
     CTK_REQUIRE(dim % 64 == 0 && dim >= 64 && dim <= 1024, CTK_ERR_SHAPE, "layernorm_bwd: dim %d", dim);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     switch (dim / 64) {
-#define CTK_LN(NV) case NV: return launch_ln_bwd<NV>(dy_bf16, dy_f32, x, gamma, mean, rstd, dx, dx_accum, dgamma, dbeta, rows, perm_outer, perm_inner, dy_bcast_rows, dy_scale, s);
+#define CTK_LN(NV) case NV: return launch_ln_bwd<NV>(dy_bf16, dy_f32, x, gamma, mean, rstd, dx, dx_bf16, dx_accum, dgamma, dbeta, rows, perm_outer, perm_inner, dy_bcast_rows, dy_scale, s);
         CTK_LN(1) CTK_LN(2) CTK_LN(4) CTK_LN(8) CTK_LN(12) CTK_LN(16)
 #undef CTK_LN
         default: break;
@@ -568,13 +574,13 @@ extern "C" int ctk_peg_fwd(const float* x, const float* w, const float* b, float
     CTK_REQUIRE(x != y, CTK_ERR_SHAPE, "peg_fwd: in-place not supported");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     const long long nlines = (long long)B * n0 * n1;
-    peg_conv_kernel<false><<<(unsigned)((nlines + block.y - 1) / block.y), block, 0, s>>>(x, w, b, y, B, n0, n1, n2, dim);
+    peg_conv_kernel<false><<<(unsigned)((nlines + block.y - 1) / block.y), block, 0, s>>>(x, w, b, y, nullptr, B, n0, n1, n2, dim);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
 
-extern "C" int ctk_peg_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw,
-                           float* db, int B, int n0, int n1, int n2, int dim, void* stream_) {
+extern "C" int ctk_peg_bwd(const float* dy, const float* x, const float* w, float* dx, void* dx_bf16,
+                           float* dw, float* db, int B, int n0, int n1, int n2, int dim, void* stream_) {
     int rc = ctk_check_device();
     if (rc) return rc;
     CTK_REQUIRE(dy && x && w && dx && dw && db && B > 0, CTK_ERR_SHAPE, "peg_bwd: bad args");
@@ -583,7 +589,8 @@ extern "C" int ctk_peg_bwd(const float* dy, const float* x, const float* w, floa
     CTK_REQUIRE(dy != dx, CTK_ERR_SHAPE, "peg_bwd: in-place not supported");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     const long long nlines = (long long)B * n0 * n1;
-    peg_conv_kernel<true><<<(unsigned)((nlines + block.y - 1) / block.y), block, 0, s>>>(dy, w, nullptr, dx, B, n0, n1, n2, dim);
+    peg_conv_kernel<true><<<(unsigned)((nlines + block.y - 1) / block.y), block, 0, s>>>(
+        dy, w, nullptr, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), B, n0, n1, n2, dim);
     CTK_LAUNCH_CHECK();
     long long blocks = (nlines + block.y - 1) / block.y;
     const long long cap = (long long)ctk_num_sms() * 2;

@@ -1,0 +1,192 @@
+"""Drop-in `CTCLIP` (reference: CT_CLIP/ct_clip/ct_clip.py, CT_CLIP/ct_clip/distributed.py).
+
+Keeps the constructor keywords the launchers use, the attribute names, `forward(batch, device=,
+accelerator=, **kw) -> (loss, {'cl_loss': float})`, `forward_infer`, `load`, and the state-dict
+keys.  The contrastive head (ct_clip.py:1280-1388) - token mean-pool, latent projections,
+l2-normalise, all-gather across ranks, scaled similarity, symmetric log-softmax cross entropy and
+its backward - runs in libctk.so.  The text encoder is whatever module the caller passes
+(HF BertModel in the reference) and runs unmodified in PyTorch.
+"""
+from __future__ import annotations
+
+import copy
+from pathlib import Path
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import ops
+
+
+class TorchDistAccelerator:
+    """Minimal object with the accelerator protocol the reference uses (distributed.py:11-14):
+    gather / num_processes / process_index, backed by torch.distributed (NCCL over NVLink)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.num_processes = dist.get_world_size(group) if self.on else 1
+        self.process_index = dist.get_rank(group) if self.on else 0
+
+    def gather(self, x: torch.Tensor) -> torch.Tensor:
+        if self.num_processes == 1:
+            return x
+        out = torch.empty((x.shape[0] * self.num_processes,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=self.group)
+        return out
+
+
+class AllGather(torch.autograd.Function):
+    """distributed.py:9-20: forward = accelerator.gather (rank-major concat); backward = the local
+    chunk of the incoming gradient, NO reduction over ranks."""
+
+    @staticmethod
+    def forward(ctx, x, accelerator):
+        ctx.num_processes = accelerator.num_processes
+        ctx.process_index = accelerator.process_index
+        return accelerator.gather(x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output.chunk(ctx.num_processes, dim=0)[ctx.process_index], None
+
+
+class _ClipHead(torch.autograd.Function):
+    """Fused contrastive head. Inputs: CLS rows of the text encoder output, encoded image tokens
+    (B, t, h, w, d), the two projection weights and the log-temperature."""
+
+    @staticmethod
+    def forward(ctx, text_cls, tokens, w_text, w_vis, temperature, accelerator):
+        B = text_cls.shape[0]
+        dim = tokens.shape[-1]
+        n_tok = tokens.numel() // (B * dim)
+        text_cls = text_cls.float()
+        if text_cls.stride(-1) != 1:
+            text_cls = text_cls.contiguous()
+        pooled = ops.mean_pool(tokens.reshape(B, n_tok, dim).contiguous())     # ct_clip.py:1297 (pool first)
+        il, rn_i = ops.latent_fwd(pooled, w_vis)                               # ct_clip.py:1290,1316
+        tl, rn_t = ops.latent_fwd(text_cls, w_text)                            # ct_clip.py:1313-1316
+        world, rank = accelerator.num_processes, accelerator.process_index
+        if world > 1:
+            packed = torch.cat([tl, il], dim=1)                                 # one gather instead of two
+            g = accelerator.gather(packed)
+            dl = tl.shape[1]
+            T, I = g[:, :dl].contiguous(), g[:, dl:].contiguous()
+        else:
+            T, I = tl, il
+        lt = temperature.detach().reshape(1).float()
+        out, d_local = ops.clip_loss_fwd_bwd(T, I, lt, b_local=B, row0=rank * B)
+        ctx.save_for_backward(text_cls, pooled, w_text, w_vis, tl, il, rn_t, rn_i, out, d_local)
+        ctx.tok_shape = tuple(tokens.shape)
+        ctx.n_tok = n_tok
+        ctx.mark_non_differentiable(tl, il)
+        return out[0].clone(), tl, il
+
+    @staticmethod
+    def backward(ctx, gloss, _gtl, _gil):
+        text_cls, pooled, w_text, w_vis, tl, il, rn_t, rn_i, out, d_local = ctx.saved_tensors
+        d_local = d_local * gloss
+        dwt, dcls = ops.latent_bwd(d_local[0].contiguous(), tl, rn_t, text_cls, w_text)
+        dwv, dpool = ops.latent_bwd(d_local[1].contiguous(), il, rn_i, pooled, w_vis)
+        B, dim = dpool.shape
+        # mean-pool backward: every token receives dpooled / n; left as a stride-0 expand so the
+        # encoder backward can consume it without materialising B*n*dim floats
+        dtok = (dpool / ctx.n_tok).view(B, *([1] * (len(ctx.tok_shape) - 2)), dim).expand(ctx.tok_shape)
+        dtemp = (out[1] * gloss).reshape(())
+        return dcls, dtok, dwt, dwv, dtemp, None
+
+
+class CTCLIP(nn.Module):
+    """Reference constructor: ct_clip.py:467-660 (only the arguments reachable from the launchers
+    are honoured; the x-clip default encoders, MLM / visual-SSL branches and segmentation heads are
+    outside the contrastive hot path)."""
+
+    def __init__(self, *, image_encoder=None, text_encoder=None, dim_text=512, dim_image=512, dim_latent=512,
+                 use_all_token_embeds=False, downsample_image_embeds=False, decoupled_contrastive_learning=False,
+                 extra_latent_projection=False, use_mlm=False, use_visual_ssl=False, visual_ssl=None,
+                 text_encode_without_mask=False, config=None, tokenizer=None, **kwargs):
+        super().__init__()
+        assert image_encoder is not None and text_encoder is not None, \
+            "pass image_encoder= and text_encoder= (every reference launcher does: run_train.py:143-154)"
+        assert not use_all_token_embeds, "no more support for use_all_token_embeds"       # ct_clip.py:514
+        assert not extra_latent_projection, "no more support for extra_latent_projection"  # ct_clip.py:515
+        assert not (use_mlm or use_visual_ssl or visual_ssl is not None or downsample_image_embeds), \
+            "MLM / visual-SSL / downsampled-latent branches are outside the contrastive hot path"
+        assert not decoupled_contrastive_learning, \
+            "the DCL branch builds a local-batch eye mask and is off in every launcher (ct_clip.py:1366-1368)"
+        config = {} if config is None else config
+        self.dtype = torch.float32
+        self.config = config
+        self.text_transformer = text_encoder
+        self.visual_transformer = image_encoder
+        self.text_encode_without_mask = text_encode_without_mask
+        self.to_text_latent = nn.Linear(dim_text, dim_latent, bias=False)
+        self.to_visual_latent = nn.Linear(dim_image, dim_latent, bias=False)
+        self.temperature = nn.Parameter(torch.tensor(1.0))
+        self.to_text_latent_extra = copy.deepcopy(self.to_text_latent)
+        self.to_visual_latent_extra = copy.deepcopy(self.to_visual_latent)
+        self.tokenizer = tokenizer       # the reference downloads CXR-BERT's tokenizer here (ct_clip.py:650)
+        self.fix_text_encoder = config.get("fix_text_encoder", False)
+        if self.fix_text_encoder:
+            for p in self.text_transformer.parameters():
+                p.requires_grad = False
+        for k in ("use_seg", "use_open_seg"):
+            assert not config.get(k, False), f"{k}: segmentation heads are outside the contrastive hot path"
+
+    # ------------------------------------------------------------------------------------------
+    def load(self, path, check=True):
+        path = Path(path)
+        assert path.exists()
+        pt = torch.load(str(path), map_location="cpu")
+        self.load_state_dict({k[7:]: v for k, v in pt.items()})      # strip 'module.' (ct_clip.py:771)
+        print(f"successfully loaded model from {path}")
+
+    def _encode_text(self, text):
+        if self.fix_text_encoder:
+            self.text_transformer.eval()
+        return self.text_transformer(text.input_ids, attention_mask=text.attention_mask)[0]
+
+    def forward(self, batch, device=None, accelerator=None, **kwargs):
+        if batch["data_type"][0] == "imagereport":
+            return self.forward_batch_image_report(batch, device=device, accelerator=accelerator, **kwargs)
+        raise ValueError(f"Data type {batch['data_type']} is outside the contrastive hot path "
+                         "(imageseg / imageopenseg need the CTViT3D segmentation heads)")
+
+    def forward_batch_image_report(self, batch, device=None, accelerator=None, **kwargs):
+        """ct_clip.py:1252-1388."""
+        assert accelerator is not None, "accelerator is not provided"
+        text, image = batch["text"], batch["image"]
+        enc_text = self._encode_text(text)
+        enc_image = self.visual_transformer(image, return_encoded_tokens=True)       # (B, t, h, w, C)
+        loss, _, _ = _ClipHead.apply(enc_text[:, 0, :], enc_image, self.to_text_latent.weight,
+                                     self.to_visual_latent.weight, self.temperature, accelerator)
+        return loss, {"cl_loss": loss.item()}      # the reference also syncs here (ct_clip.py:1384)
+
+    @torch.no_grad()
+    def latents(self, text=None, image=None, buffer_text_embed=None, buffer_image_embed=None):
+        """l2-normalised (text_latents, image_latents); either side may be None."""
+        tl = il = None
+        if text is not None or buffer_text_embed is not None:
+            emb = buffer_text_embed if buffer_text_embed is not None else \
+                self.text_transformer(text.input_ids, attention_mask=text.attention_mask)
+            enc_text = emb[0]
+            tl, _ = ops.latent_fwd(enc_text[:, 0, :].float(), self.to_text_latent.weight)
+        if image is not None or buffer_image_embed is not None:
+            enc = buffer_image_embed if buffer_image_embed is not None else \
+                self.visual_transformer(image, return_encoded_tokens=True)
+            B, dim = enc.shape[0], enc.shape[-1]
+            pooled = ops.mean_pool(enc.reshape(B, -1, dim).contiguous().float())
+            il, _ = ops.latent_fwd(pooled, self.to_visual_latent.weight)
+        return tl, il
+
+    def forward_infer(self, text, image, buffer_text_embed=None, buffer_image_embed=None):
+        """ct_clip.py:792-855: exp(temperature) * <text latent_p, image latent> for each prompt p
+        (text batch broadcast against a single volume)."""
+        tl, il = self.latents(text, image, buffer_text_embed, buffer_image_embed)
+        assert il.shape[0] == 1 or il.shape[0] == tl.shape[0]
+        lt = self.temperature.detach().reshape(1).float()
+        if il.shape[0] == 1:
+            return ops.pair_logits(tl, il[0].contiguous(), lt)
+        return torch.stack([ops.pair_logits(tl[i:i + 1], il[i].contiguous(), lt)[0] for i in range(tl.shape[0])])

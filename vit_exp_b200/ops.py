@@ -31,6 +31,9 @@ def _chk(t: torch.Tensor, dtype, name: str):
 
 
 # --------------------------------------------------------------------------- GEMM
+GEMM_PROFILE = None     # bench.py sets this to a list: (start_event, end_event, tag) per GEMM launch
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, c: torch.Tensor, *, M: int, N: int, K: int,
          mn_major: bool = False, lda: Optional[int] = None, ldb: Optional[int] = None,
          ldc: Optional[int] = None, bias=None, resid=None, ldr: Optional[int] = None, aux0=None,
@@ -55,8 +58,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, c: torch.Tensor, *, M:
     e.i1 = i1
     lda = lda if lda is not None else a.stride(0)
     ldb = ldb if ldb is not None else b.stride(0)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.ctk_gemm_bf16(_p(a), lda, int(mn_major), _p(b), ldb, int(mn_major), M, N, K, epilogue,
                             C.byref(e), split_k, _stream()), "ctk_gemm_bf16")
+    if prof is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        prof.append((e0, e1, f"epi{epilogue}{'_wgrad' if mn_major else ''}"))
     return c
 
 
@@ -188,7 +199,7 @@ def layernorm_fwd(x, gamma, beta=None, *, want_bf16=True, want_f32=False, want_r
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta=None, *, dx=None, accum=False, perm_outer=0,
-                  perm_inner=0, bcast_rows=0, dy_scale=1.0):
+                  perm_inner=0, bcast_rows=0, dy_scale=1.0, dx_bf16=None):
     """dy bf16 or fp32; returns dx (fp32). dgamma/dbeta accumulate (must be zero-initialised)."""
     rows, dim = x.shape
     if dx is None:
@@ -197,7 +208,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta=None, *, dx=None, accu
     dyb = dy if dy.dtype == torch.bfloat16 else None
     dyf = dy if dy.dtype == torch.float32 else None
     assert dy.is_contiguous() and (dyb is not None or dyf is not None)
-    check(_lib.load().ctk_layernorm_bwd(_p(dyb), _p(dyf), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), int(accum),
+    check(_lib.load().ctk_layernorm_bwd(_p(dyb), _p(dyf), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dx_bf16), int(accum),
                                         _p(dgamma), _p(dbeta), rows, dim, perm_outer, perm_inner, bcast_rows,
                                         dy_scale, _stream()), "ctk_layernorm_bwd")
     return dx
@@ -213,11 +224,12 @@ def peg_fwd(x, w, b, shape):
     return y
 
 
-def peg_bwd(dy, x, w, shape, dw, db):
+def peg_bwd(dy, x, w, shape, dw, db, dx_bf16=None):
     B, n0, n1, n2 = shape
     dim = x.shape[-1]
     dx = torch.empty_like(dy)
-    check(_lib.load().ctk_peg_bwd(_p(dy), _p(x), _p(w), _p(dx), _p(dw), _p(db), B, n0, n1, n2, dim, _stream()), "ctk_peg_bwd")
+    check(_lib.load().ctk_peg_bwd(_p(dy), _p(x), _p(w), _p(dx), _p(dx_bf16), _p(dw), _p(db), B, n0, n1, n2, dim,
+                                  _stream()), "ctk_peg_bwd")
     return dx
 
 

@@ -1,0 +1,482 @@
+"""Drop-in `CTViT` (reference: transformer_maskgit/transformer_maskgit/ctvit.py + attention.py).
+
+Same constructor keywords, attributes, forward signature and state-dict keys as the reference
+module, so a reference checkpoint loads unchanged and callers (`CTCLIP`, the trainer, zero-shot
+inference) keep working.  Only the encoder branch (`return_encoded_tokens=True`, ctvit.py:353-412)
+is implemented; the VQ-GAN decoder / discriminator branches raise NotImplementedError.
+
+The nn.Module tree below only *holds parameters* under the reference's names.  All arithmetic runs
+in libctk.so (sm_100a CUDA) through one autograd.Function that owns the forward and the hand
+written backward of the whole encoder.  There is no CPU or torch fallback.
+"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+ATTN_SCALE = 8.0          # attention.py:105 (scale = 8)
+
+
+def pair(val):
+    ret = (val, val) if not isinstance(val, tuple) else val
+    assert len(ret) == 2
+    return ret
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (names/shapes/init order identical to the reference modules)
+# ------------------------------------------------------------------------------------------------
+class LayerNorm(nn.Module):
+    """attention.py:34-41: learnable gamma, zero `beta` buffer."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+        self.register_buffer("beta", torch.zeros(dim))
+
+
+class PEG(nn.Module):
+    """attention.py:62-90: parameter holder for the depthwise 3x3x3 conv."""
+
+    def __init__(self, dim, causal=False):
+        super().__init__()
+        self.causal = causal
+        self.dsconv = nn.Conv3d(dim, dim, 3, groups=dim)
+
+
+class Attention(nn.Module):
+    """attention.py:94-131 (self-attention, no null kv on this path: attention.py:422)."""
+
+    def __init__(self, dim, dim_head=64, heads=8, num_null_kv=0, scale=8):
+        super().__init__()
+        self.heads, self.scale, self.dim_head = heads, scale, dim_head
+        inner_dim = dim_head * heads
+        self.norm = LayerNorm(dim)
+        self.context_norm = LayerNorm(dim)
+        self.num_null_kv = num_null_kv
+        self.null_kv = nn.Parameter(torch.randn(heads, 2 * num_null_kv, dim_head))
+        self.to_q = nn.Linear(dim, inner_dim, bias=False)
+        self.to_kv = nn.Linear(dim, inner_dim * 2, bias=False)
+        self.q_scale = nn.Parameter(torch.ones(dim_head))
+        self.k_scale = nn.Parameter(torch.ones(dim_head))
+        self.to_out = nn.Linear(inner_dim, dim, bias=False)
+
+
+class _GEGLUSlot(nn.Module):
+    """placeholder so FeedForward keeps the reference's Sequential indices (0,1,2,3,4)."""
+
+
+def FeedForward(dim, mult=4, dropout=0.0):
+    """attention.py:50-58."""
+    inner_dim = int(mult * (2 / 3) * dim)
+    return nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, inner_dim * 2, bias=False), _GEGLUSlot(),
+                         nn.Dropout(dropout), nn.Linear(inner_dim, dim, bias=False))
+
+
+class ContinuousPositionBias(nn.Module):
+    """attention.py:335-361 (num_dims 2, layers 2)."""
+
+    def __init__(self, *, dim, heads, num_dims=2, layers=2):
+        super().__init__()
+        self.net = nn.ModuleList([])
+        self.net.append(nn.Sequential(nn.Linear(num_dims, dim), nn.LeakyReLU(0.1)))
+        for _ in range(layers - 1):
+            self.net.append(nn.Sequential(nn.Linear(dim, dim), nn.LeakyReLU(0.1)))
+        self.net.append(nn.Linear(dim, heads))
+
+
+class Transformer(nn.Module):
+    """attention.py:386-439: layers[i] = [PEG, Attention, None (no cross-attn), FeedForward]."""
+
+    def __init__(self, dim, *, depth, dim_head=64, heads=8, ff_mult=4, peg=False, peg_causal=False,
+                 attn_dropout=0.0, ff_dropout=0.0):
+        super().__init__()
+        assert attn_dropout == 0.0 and ff_dropout == 0.0, "dropout is 0 on the reference path (run_train.py:56-66)"
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                PEG(dim=dim, causal=peg_causal) if peg else None,
+                Attention(dim=dim, dim_head=dim_head, heads=heads),
+                None,
+                FeedForward(dim=dim, mult=ff_mult, dropout=ff_dropout),
+            ]))
+        self.norm_out = LayerNorm(dim)
+
+
+class _CosineSimCodebook(nn.Module):
+    def __init__(self, dim, codebook_size):
+        super().__init__()
+        embed = F.normalize(nn.init.kaiming_uniform_(torch.empty(1, codebook_size, dim)), dim=-1)
+        self.register_buffer("initted", torch.Tensor([True]))
+        self.register_buffer("cluster_size", torch.zeros(1, codebook_size))
+        self.register_buffer("embed", embed)
+
+
+class VectorQuantize(nn.Module):
+    """State holder for VectorQuantize(dim, codebook_size, use_cosine_sim=True) (ctvit.py:188):
+    buffers `_codebook.{initted, cluster_size, embed}` as in vector-quantize-pytorch 1.1.2.
+    The search / gather / EMA kernels live in libctk (parity unpinned: see oracle header)."""
+
+    def __init__(self, dim, codebook_size, use_cosine_sim=True, decay=0.8):
+        super().__init__()
+        assert use_cosine_sim
+        self.decay = decay
+        self.codebook_size = codebook_size
+        self._codebook = _CosineSimCodebook(dim, codebook_size)
+
+    @property
+    def codebook(self):
+        return self._codebook.embed[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# flat parameter view used by the autograd.Function
+# ------------------------------------------------------------------------------------------------
+def _layer_params(tr: Transformer) -> List[torch.Tensor]:
+    out = []
+    for peg, attn, _, ff in tr.layers:
+        out += [peg.dsconv.weight, peg.dsconv.bias, attn.norm.gamma, attn.to_q.weight, attn.to_kv.weight,
+                attn.q_scale, attn.k_scale, attn.to_out.weight, ff[0].weight, ff[0].bias, ff[1].weight, ff[4].weight]
+    out.append(tr.norm_out.gamma)
+    return out
+
+
+N_PER_LAYER = 12
+
+
+class _Cfg:
+    """static shape bundle"""
+
+    def __init__(self, vit: "CTViT", video: torch.Tensor):
+        B, C, D, H, W = video.shape
+        self.B, self.D, self.H, self.W = B, D, H, W
+        self.p1, self.p2 = vit.patch_size
+        self.pt = vit.temporal_patch_size
+        self.t, self.h, self.w = D // self.pt, H // self.p1, W // self.p2
+        self.dim = vit.dim
+        self.heads = vit.heads
+        self.inner = vit.heads * vit.dim_head
+        self.M = B * self.t * self.h * self.w
+        self.ff_inner = vit.ff_inner
+        self.ff_pad = (self.ff_inner + 127) // 128 * 128
+        self.K = self.pt * self.p1 * self.p2
+        self.Kp = (self.K + 7) // 8 * 8
+        self.sd, self.td = vit.spatial_depth, vit.temporal_depth
+
+
+def _prep_layer_weights(lp: List[torch.Tensor], cfg: _Cfg, need_bwd: bool) -> Dict[str, torch.Tensor]:
+    (pw, pb, gamma, wq, wkv, qs, ks, wo, fg, fb, w1, w2) = lp
+    d: Dict[str, torch.Tensor] = {}
+    d["peg_w"] = pw.reshape(cfg.dim, 27)
+    d["wq"] = ops.cast_bf16(wq)
+    d["wkv"] = ops.cast_bf16(wkv)
+    d["wo"] = ops.cast_bf16(wo)
+    d["w1p"], d["w1p_t"], d["w1_map"] = ops.pack_ff_w1(w1, cfg.ff_inner, cfg.ff_pad, want_t=need_bwd)
+    d["w2"] = ops.cast_bf16(w2, ld=cfg.ff_pad)
+    if need_bwd:
+        d["wq_t"] = ops.transpose_cast_bf16(wq)               # [dim, inner]
+        d["wkv_t"] = ops.transpose_cast_bf16(wkv)             # [dim, 2 inner]
+        d["wo_t"] = ops.transpose_cast_bf16(wo)               # [inner, dim]
+        w2t = torch.zeros(cfg.ff_pad, cfg.dim, dtype=torch.bfloat16, device=w2.device)
+        ops.transpose_cast_bf16(w2, out=w2t[: cfg.ff_inner])  # [ff_inner, dim] rows, pad rows stay zero
+        d["w2_t"] = w2t
+    return d
+
+
+def _transformer_fwd(x, lps, norm_gamma, cfg: _Cfg, table, nseq, L, gh, gw, perm, save: bool, need_bwd: bool):
+    """x fp32 [M, dim] -> norm_out(x) written through the row permutation `perm`=(outer, inner)."""
+    dim, heads, inner, M = cfg.dim, cfg.heads, cfg.inner, cfg.M
+    dev = x.device
+    shape = (cfg.B, cfg.t, cfg.h, cfg.w)           # PEG always reshapes with video_shape (ctvit.py:289,303)
+    saved = []
+    for lp in lps:
+        w = _prep_layer_weights(lp, cfg, need_bwd)
+        (pw, pb, gamma, wq, wkv, qs, ks, wo, fg, fb, w1, w2) = lp
+        x1 = ops.peg_fwd(x, w["peg_w"], pb, shape)
+        xn, _, xraw, mu1, rs1 = ops.layernorm_fwd(x1, gamma, None, want_raw=True)
+        qkv = torch.empty(M, 3 * inner, dtype=torch.bfloat16, device=dev)
+        rn = torch.empty(M, 2 * heads, dtype=torch.float32, device=dev)
+        ops.gemm(xn, w["wq"], ops.EPI_QKV, qkv, M=M, N=inner, K=dim, aux0=rn, ld_aux0=2 * heads, vec0=qs,
+                 alpha=ATTN_SCALE, i0=inner, i1=0)
+        ops.gemm(xraw, w["wkv"], ops.EPI_QKV, qkv, M=M, N=2 * inner, K=dim, aux0=rn, ld_aux0=2 * heads, vec0=ks,
+                 alpha=1.0, i0=inner, i1=inner)
+        o, lse = ops.attn_fwd(qkv, table, nseq, L, heads, gh, gw)
+        x2 = torch.empty_like(x1)
+        ops.gemm(o, w["wo"], ops.EPI_RESID_F32, x2, M=M, N=dim, K=inner, resid=x1)
+        hn, _, _, mu2, rs2 = ops.layernorm_fwd(x2, fg, fb)
+        U = torch.empty(M, 2 * cfg.ff_pad, dtype=torch.bfloat16, device=dev)
+        Hh = torch.empty(M, cfg.ff_pad, dtype=torch.bfloat16, device=dev)
+        ops.gemm(hn, w["w1p"], ops.EPI_GEGLU, U, M=M, N=2 * cfg.ff_pad, K=dim, aux0=Hh, ld_aux0=cfg.ff_pad)
+        x3 = torch.empty_like(x2)
+        ops.gemm(Hh, w["w2"], ops.EPI_RESID_F32, x3, M=M, N=dim, K=cfg.ff_pad, resid=x2)
+        if save:
+            saved.append(dict(w=w, x=x, x1=x1, xn=xn, xraw=xraw, mu1=mu1, rs1=rs1, qkv=qkv, rn=rn, o=o, lse=lse,
+                              x2=x2, hn=hn, mu2=mu2, rs2=rs2, U=U, H=Hh))
+        x = x3
+    _, y, _, mu, rs = ops.layernorm_fwd(x, norm_gamma, None, want_bf16=False, want_f32=True,
+                                        perm_outer=perm[0], perm_inner=perm[1])
+    fin = dict(x=x, mu=mu, rs=rs) if save else None
+    return y, saved, fin
+
+
+def _transformer_bwd(dy, dy_bcast, lps, norm_gamma, cfg: _Cfg, table, dtable, nseq, L, gh, gw, perm, saved, fin,
+                     grads_out: List[Optional[torch.Tensor]], want_bf16_out: bool):
+    """dy: gradient wrt the (permuted) norm_out output. Returns (dx fp32, dx bf16 or None); fills
+    grads_out (same order as _layer_params)."""
+    dim, heads, inner, M = cfg.dim, cfg.heads, cfg.inner, cfg.M
+    dev = norm_gamma.device
+    shape = (cfg.B, cfg.t, cfg.h, cfg.w)
+    f32 = dict(dtype=torch.float32, device=dev)
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    dgo = torch.zeros(dim, **f32)
+    g_bf = torch.empty(M, dim, **bf)
+    if dy_bcast is not None:
+        rows_per, scale = dy_bcast
+        g = ops.layernorm_bwd(dy, fin["x"], norm_gamma, fin["mu"], fin["rs"], dgo, None, bcast_rows=rows_per,
+                              dy_scale=scale, dx_bf16=g_bf)
+    else:
+        g = ops.layernorm_bwd(dy, fin["x"], norm_gamma, fin["mu"], fin["rs"], dgo, None, perm_outer=perm[0],
+                              perm_inner=perm[1], dx_bf16=g_bf)
+    grads_out[len(lps) * N_PER_LAYER] = dgo
+    for li in range(len(lps) - 1, -1, -1):
+        (pw, pb, gamma, wq, wkv, qs, ks, wo, fg, fb, w1, w2) = lps[li]
+        s = saved[li]
+        w = s["w"]
+        # ---- feed-forward: x3 = x2 + W2 geglu(W1 LN(x2))
+        dw2 = torch.zeros_like(w2)
+        ops.gemm(g_bf, s["H"], ops.EPI_ATOMIC_F32, dw2, M=dim, N=cfg.ff_inner, K=M, mn_major=True, ldc=cfg.ff_inner)
+        dU = torch.empty_like(s["U"])
+        ops.gemm(g_bf, w["w2_t"], ops.EPI_GEGLU_BWD, dU, M=M, N=cfg.ff_pad, K=dim, aux0=s["U"], ld_aux0=2 * cfg.ff_pad)
+        dw1 = torch.zeros_like(w1)
+        ops.gemm(dU, s["hn"], ops.EPI_ATOMIC_F32, dw1, M=2 * cfg.ff_pad, N=dim, K=M, mn_major=True, ldc=dim,
+                 row_map=w["w1_map"])
+        dhn = torch.empty(M, dim, **bf)
+        ops.gemm(dU, w["w1p_t"], ops.EPI_BF16, dhn, M=M, N=dim, K=2 * cfg.ff_pad)
+        dfg, dfb = torch.zeros(dim, **f32), torch.zeros(dim, **f32)
+        ops.layernorm_bwd(dhn, s["x2"], fg, s["mu2"], s["rs2"], dfg, dfb, dx=g, accum=True, dx_bf16=g_bf)
+        # ---- attention: x2 = x1 + Wo attn(q(LN(x1)), kv(x1))
+        dwo = torch.zeros_like(wo)
+        ops.gemm(g_bf, s["o"], ops.EPI_ATOMIC_F32, dwo, M=dim, N=inner, K=M, mn_major=True, ldc=inner)
+        do = torch.empty(M, inner, **bf)
+        ops.gemm(g_bf, w["wo_t"], ops.EPI_BF16, do, M=M, N=inner, K=dim)
+        dqkv = ops.attn_bwd(s["qkv"], table, s["o"], do, s["lse"], dtable, nseq, L, heads, gh, gw)
+        dqs, dks = torch.zeros(32, **f32), torch.zeros(32, **f32)
+        ops.qknorm_bwd_(dqkv, s["qkv"], s["rn"], qs, ks, ATTN_SCALE, dqs, dks, heads)
+        dwq = torch.zeros_like(wq)
+        ops.gemm(dqkv, s["xn"], ops.EPI_ATOMIC_F32, dwq, M=inner, N=dim, K=M, mn_major=True, lda=3 * inner, ldc=dim)
+        dwkv = torch.zeros_like(wkv)
+        dkv_view = dqkv[:, inner:]
+        ops.gemm(dkv_view, s["xraw"], ops.EPI_ATOMIC_F32, dwkv, M=2 * inner, N=dim, K=M, mn_major=True,
+                 lda=3 * inner, ldc=dim)
+        # k/v read the raw stream: their input gradient joins the residual gradient directly
+        ops.gemm(dkv_view, w["wkv_t"], ops.EPI_RESID_F32, g, M=M, N=dim, K=2 * inner, lda=3 * inner, resid=g)
+        dxn = torch.empty(M, dim, **bf)
+        ops.gemm(dqkv, w["wq_t"], ops.EPI_BF16, dxn, M=M, N=dim, K=inner, lda=3 * inner)
+        dgamma = torch.zeros(dim, **f32)
+        ops.layernorm_bwd(dxn, s["x1"], gamma, s["mu1"], s["rs1"], dgamma, None, dx=g, accum=True)
+        # ---- PEG: x1 = conv(x) + b + x
+        dpw, dpb = torch.zeros(dim, 27, **f32), torch.zeros(dim, **f32)
+        need_bf = li > 0 or want_bf16_out
+        g_new = ops.peg_bwd(g, s["x"], w["peg_w"], shape, dpw, dpb, dx_bf16=g_bf if need_bf else None)
+        g = g_new
+        base = li * N_PER_LAYER
+        grads_out[base:base + N_PER_LAYER] = [dpw.reshape(pw.shape), dpb, dgamma, dwq, dwkv, dqs, dks, dwo, dfg, dfb,
+                                              dw1, dw2]
+        saved[li] = None        # free activations as we go
+    return g, (g_bf if want_bf16_out else None)
+
+
+def _encode_forward(vit: "CTViT", video: torch.Tensor, params: List[torch.Tensor], save: bool, training: bool):
+    cfg = _Cfg(vit, video)
+    dim, M = cfg.dim, cfg.M
+    it = iter(params)
+    cpb = [next(it) for _ in range(6)]
+    g1, b1, wp, bp, g3, b3 = (next(it) for _ in range(6))
+    sp = [[next(it) for _ in range(N_PER_LAYER)] for _ in range(cfg.sd)]
+    sp_norm = next(it)
+    tp = [[next(it) for _ in range(N_PER_LAYER)] for _ in range(cfg.td)]
+    tp_norm = next(it)
+
+    # ---- patch embedding (ctvit.py:170-175); LayerNorm(K) affine folded into the projection
+    xhat, pmean, prstd = ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2)
+    wp_eff = ops.cast_bf16(wp, ld=cfg.Kp, col_scale=g1)
+    bias_eff = torch.addmv(bp, wp, b1)                    # parameter folding: b + W beta (dim x K mat-vec)
+    y0 = torch.empty(M, dim, dtype=torch.float32, device=video.device)
+    ops.gemm(xhat, wp_eff, ops.EPI_F32, y0, M=M, N=dim, K=cfg.Kp, bias=bias_eff)
+    _, x0, _, mu0, rs0 = ops.layernorm_fwd(y0, g3, b3, want_bf16=False, want_f32=True)
+    # ---- continuous position bias table (attention.py:363-382, deduplicated offsets)
+    table, h0, h1 = ops.cpb_fwd(*cpb, cfg.h, cfg.w)
+    # ---- spatial then temporal stacks (ctvit.py:291-305)
+    hw = cfg.h * cfg.w
+    xs, sp_saved, sp_fin = _transformer_fwd(x0, sp, sp_norm, cfg, table, cfg.B * cfg.t, hw, cfg.h, cfg.w,
+                                            (cfg.t, hw), save, save)
+    xt, tp_saved, tp_fin = _transformer_fwd(xs, tp, tp_norm, cfg, None, cfg.B * hw, cfg.t, 0, 0, (hw, cfg.t), save, save)
+    # ---- vector quantisation (ctvit.py:403): cosine-sim code search on the tensor cores
+    embed = vit.vq._codebook.embed[0]
+    xb, xf = ops.l2norm_rows(xt, want_f32=training)
+    eb, _ = ops.l2norm_rows(embed)
+    best = torch.zeros(M, dtype=torch.int64, device=video.device)
+    ops.gemm(xb, eb, ops.EPI_ARGMAX, best, M=M, N=embed.shape[0], K=dim, ldc=0)
+    ind, quant = ops.vq_gather(best, embed)
+    if training:
+        ops.vq_ema_update_(xf, ind, vit.vq._codebook.cluster_size[0], embed, vit.vq.decay)
+    out = quant.view(cfg.B, cfg.t, cfg.h, cfg.w, dim)
+    ctx = None
+    if save:
+        ctx = dict(cfg=cfg, xhat=xhat, y0=y0, mu0=mu0, rs0=rs0, table=table, h0=h0, h1=h1, sp_saved=sp_saved,
+                   sp_fin=sp_fin, tp_saved=tp_saved, tp_fin=tp_fin)
+    return out, ind.view(cfg.B, cfg.t, cfg.h, cfg.w), xt, ctx
+
+
+def _encode_backward(vit: "CTViT", params: List[torch.Tensor], ctx, dtokens: torch.Tensor):
+    cfg: _Cfg = ctx["cfg"]
+    dim, M = cfg.dim, cfg.M
+    dev = dtokens.device
+    it = iter(params)
+    cpb = [next(it) for _ in range(6)]
+    g1, b1, wp, bp, g3, b3 = (next(it) for _ in range(6))
+    sp = [[next(it) for _ in range(N_PER_LAYER)] for _ in range(cfg.sd)]
+    sp_norm = next(it)
+    tp = [[next(it) for _ in range(N_PER_LAYER)] for _ in range(cfg.td)]
+    tp_norm = next(it)
+    hw = cfg.h * cfg.w
+    n_tok = cfg.t * hw
+
+    # straight-through VQ (quantize = x + (quantize - x).detach()): d enc = d tokens.
+    # A mean-pool gradient arrives as a stride-0 expand of [B, dim]: keep it un-materialised.
+    bcast = None
+    if dtokens.dim() == 5 and dtokens.stride()[1:4] == (0, 0, 0) and dtokens.stride(4) == 1:
+        dy = dtokens[:, 0, 0, 0, :].contiguous().float()
+        bcast = (n_tok, 1.0)
+    else:
+        dy = dtokens.reshape(M, dim).contiguous().float()
+
+    sp_g: List[Optional[torch.Tensor]] = [None] * (cfg.sd * N_PER_LAYER + 1)
+    tp_g: List[Optional[torch.Tensor]] = [None] * (cfg.td * N_PER_LAYER + 1)
+    g, _ = _transformer_bwd(dy, bcast, tp, tp_norm, cfg, None, None, cfg.B * hw, cfg.t, 0, 0, (hw, cfg.t),
+                            ctx["tp_saved"], ctx["tp_fin"], tp_g, False)
+    dtable = torch.zeros_like(ctx["table"])
+    g, _ = _transformer_bwd(g, None, sp, sp_norm, cfg, ctx["table"], dtable, cfg.B * cfg.t, hw, cfg.h, cfg.w,
+                            (cfg.t, hw), ctx["sp_saved"], ctx["sp_fin"], sp_g, False)
+    # ---- patch embedding backward (no input gradient: the volume is data)
+    dg3, db3 = torch.zeros(dim, device=dev), torch.zeros(dim, device=dev)
+    dy0_bf = torch.empty(M, dim, dtype=torch.bfloat16, device=dev)
+    dy0 = ops.layernorm_bwd(g, ctx["y0"], g3, ctx["mu0"], ctx["rs0"], dg3, db3, dx_bf16=dy0_bf)
+    dbp = torch.zeros(dim, device=dev)
+    ops.colsum_(dy0, dbp)
+    P = torch.zeros(dim, cfg.K, device=dev)
+    ops.gemm(dy0_bf, ctx["xhat"], ops.EPI_ATOMIC_F32, P, M=dim, N=cfg.K, K=M, mn_major=True, ldc=cfg.K)
+    dwp, dg1, db1 = ops.patch_affine_bwd(P, wp, g1, b1, dbp)
+    cpb_g = ops.cpb_bwd(dtable.reshape(cfg.heads, -1), cpb[0], cpb[2], cpb[4], ctx["h0"], ctx["h1"], cfg.h, cfg.w)
+    return cpb_g + [dg1, db1, dwp, dbp, dg3, db3] + sp_g + tp_g
+
+
+class _CTViTEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vit, video, training, *params):
+        need = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        out, ind, pre_vq, saved = _encode_forward(vit, video, list(params), save=True, training=training)
+        ctx.vit = vit
+        ctx.saved = saved
+        ctx.params = params
+        ctx.mark_non_differentiable(ind)
+        return out, ind, pre_vq.detach()
+
+    @staticmethod
+    def backward(ctx, dtokens, _dind, dpre):
+        assert dtokens is not None
+        grads = _encode_backward(ctx.vit, list(ctx.params), ctx.saved, dtokens)
+        ctx.saved = None
+        return (None, None, None, *grads)
+
+
+class CTViT(nn.Module):
+    """Reference: ctvit.py:118-200 (constructor), :353-412 (forward, encoder branch)."""
+
+    def __init__(self, *, dim, codebook_size, image_size, patch_size, temporal_patch_size, spatial_depth,
+                 temporal_depth, discr_base_dim=16, dim_head=64, heads=8, channels=1, use_vgg_and_gan=True, vgg=None,
+                 discr_attn_res_layers=(16,), use_hinge_loss=True, attn_dropout=0.0, ff_dropout=0.0):
+        super().__init__()
+        assert channels == 1, "CT volumes are single channel (run_train.py:56-66)"
+        self.image_size = pair(image_size)
+        self.patch_size = pair(patch_size)
+        patch_height, patch_width = self.patch_size
+        self.temporal_patch_size = temporal_patch_size
+        self.dim, self.heads, self.dim_head = dim, heads, dim_head
+        assert dim_head == 32, "libctk attention kernels are specialised for dim_head 32 (run_train.py:64)"
+        self.spatial_depth, self.temporal_depth = spatial_depth, temporal_depth
+        self.ff_inner = int(4 * (2 / 3) * dim)
+
+        self.spatial_rel_pos_bias = ContinuousPositionBias(dim=dim, heads=heads)
+        image_height, image_width = self.image_size
+        assert (image_height % patch_height) == 0 and (image_width % patch_width) == 0
+        pdim_ff = channels * patch_width * patch_height
+        pdim = pdim_ff * temporal_patch_size
+        # index 0 of both Sequentials is the einops Rearrange in the reference (no parameters)
+        self.to_patch_emb_first_frame = nn.Sequential(nn.Identity(), nn.LayerNorm(pdim_ff), nn.Linear(pdim_ff, dim),
+                                                      nn.LayerNorm(dim))
+        self.to_patch_emb = nn.Sequential(nn.Identity(), nn.LayerNorm(pdim), nn.Linear(pdim, dim), nn.LayerNorm(dim))
+        kw = dict(dim=dim, dim_head=dim_head, heads=heads, attn_dropout=attn_dropout, ff_dropout=ff_dropout, peg=True,
+                  peg_causal=True)
+        self.enc_spatial_transformer = Transformer(depth=spatial_depth, **kw)
+        self.enc_temporal_transformer = Transformer(depth=temporal_depth, **kw)
+        self.vq = VectorQuantize(dim=dim, codebook_size=codebook_size, use_cosine_sim=True)
+        self.to_pixels_first_frame = nn.Sequential(nn.Linear(dim, pdim_ff), nn.Identity())
+        self.to_pixels = nn.Sequential(nn.Linear(dim, pdim), nn.Identity())
+
+    # -- reference helpers kept for callers --------------------------------------------------------
+    @property
+    def image_num_tokens(self):
+        return int(self.image_size[0] / self.patch_size[0]) * int(self.image_size[1] / self.patch_size[1])
+
+    @property
+    def patch_height_width(self):
+        return self.image_size[0] // self.patch_size[0], self.image_size[1] // self.patch_size[1]
+
+    def load(self, path):
+        path = Path(path)
+        assert path.exists()
+        self.load_state_dict(torch.load(str(path)))
+
+    def _flat_params(self) -> List[torch.Tensor]:
+        cpb = self.spatial_rel_pos_bias.net
+        p = [cpb[0][0].weight, cpb[0][0].bias, cpb[1][0].weight, cpb[1][0].bias, cpb[2].weight, cpb[2].bias]
+        pe = self.to_patch_emb
+        p += [pe[1].weight, pe[1].bias, pe[2].weight, pe[2].bias, pe[3].weight, pe[3].bias]
+        p += _layer_params(self.enc_spatial_transformer)
+        p += _layer_params(self.enc_temporal_transformer)
+        return p
+
+    def encode_with_aux(self, video: torch.Tensor):
+        """returns (tokens after VQ, code indices, tokens before VQ)"""
+        assert video.is_cuda, "CTViT runs on sm_100a only: move the module and its input to a CUDA device"
+        video = video.contiguous().float()
+        params = self._flat_params()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _CTViTEncode.apply(self, video, self.training, *params)
+        out, ind, pre, _ = _encode_forward(self, video, params, save=False, training=self.training)
+        return out, ind, pre
+
+    def forward(self, video, mask=None, return_recons=False, return_recons_only=False, return_discr_loss=False,
+                apply_grad_penalty=True, return_only_codebook_ids=False, return_encoded_tokens=False):
+        assert video.ndim in {4, 5}
+        if video.ndim == 4:
+            video = video[:, :, None]
+            assert mask is None
+        b, c, f, *image_dims = video.shape
+        assert tuple(image_dims) == self.image_size
+        assert mask is None, "frame masks are not used on the CT-CLIP path"
+        tokens, indices, _ = self.encode_with_aux(video)
+        if return_only_codebook_ids:
+            return indices.reshape(b, -1)
+        if return_encoded_tokens:
+            return tokens
+        raise NotImplementedError("only the encoder branch (return_encoded_tokens=True / return_only_codebook_ids=True) "
+                                  "of CTViT is on the CT-CLIP hot path (ctvit.py:411-412)")
