@@ -1,0 +1,44 @@
+"""dev tool: per-kernel time breakdown of one bench train step (torch.profiler / CUPTI)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from types import SimpleNamespace
+import bench
+from vit_exp_b200.ct_clip import TorchDistAccelerator
+
+B = int(os.environ.get("B", "8"))
+dev = torch.device("cuda:0")
+clip = bench.build_model(dev).train()
+bert = clip.text_transformer
+orig = bert.forward
+def fwd(*a, **k):
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        return orig(*a, **k)
+bert.forward = fwd
+params = [p for p in clip.parameters() if p.requires_grad]
+opt = torch.optim.Adam(params, lr=1.25e-6, betas=(0.9, 0.99), fused=True)
+acc = TorchDistAccelerator()
+vid = torch.rand(B, 1, 240, 480, 480, device=dev)
+ids = torch.randint(0, 30522, (B, 512), device=dev)
+mask = torch.ones_like(ids)
+def step():
+    batch = {"data_type": ["imagereport"] * B, "text": SimpleNamespace(input_ids=ids, attention_mask=mask), "image": vid}
+    loss, ld = clip(batch, device=dev, accelerator=acc)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(params, 0.5)
+    opt.step(); opt.zero_grad(set_to_none=True)
+for _ in range(2): step()
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step(); torch.cuda.synchronize()
+rows = []
+for e in prof.key_averages():
+    t = getattr(e, "device_time_total", 0) or getattr(e, "cuda_time_total", 0)
+    if e.device_type == torch.autograd.DeviceType.CUDA and t > 0:
+        rows.append((t, e.count, e.key))
+rows.sort(reverse=True)
+tot = sum(r[0] for r in rows)
+print(f"total device time {tot/1e3:.2f} ms over {sum(r[1] for r in rows)} kernels")
+for t, c, k in rows[:45]:
+    print(f"{t/1e3:9.3f} ms {100*t/tot:5.1f}% x{c:<5d} {k[:110]}")
