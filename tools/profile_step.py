@@ -42,3 +42,21 @@ tot = sum(r[0] for r in rows)
 print(f"total device time {tot/1e3:.2f} ms over {sum(r[1] for r in rows)} kernels")
 for t, c, k in rows[:45]:
     print(f"{t/1e3:9.3f} ms {100*t/tot:5.1f}% x{c:<5d} {k[:110]}")
+
+# ---- host-side cost per phase (no sync inside; CPU launch time only)
+import time
+def phase_times():
+    batch = {"data_type": ["imagereport"] * B, "text": SimpleNamespace(input_ids=ids, attention_mask=mask), "image": vid}
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    loss, ld = clip(batch, device=dev, accelerator=acc)
+    t1 = time.perf_counter()
+    loss.backward()
+    t2 = time.perf_counter()
+    torch.nn.utils.clip_grad_norm_(params, 0.5)
+    t3 = time.perf_counter()
+    opt.step(); opt.zero_grad(set_to_none=True)
+    t4 = time.perf_counter()
+    torch.cuda.synchronize(); t5 = time.perf_counter()
+    return [1e3 * x for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0)]
+for _ in range(2):
+    print("host ms: fwd(+loss.item sync) %.1f  bwd %.1f  clip %.1f  adam %.1f  drain %.1f  total %.1f" % tuple(phase_times()))

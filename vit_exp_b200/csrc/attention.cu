@@ -110,77 +110,93 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-struct BiasIdx {           // relative-position table lookup for query i, key j
+// Relative-position bias lookup.  index(i, j) = (yi-yj)*ww + (xi-xj) + off = pos[i] + off - pos[j]
+// with pos[n] = (n / gw) * ww + n % gw precomputed per CTA in shared memory (no divisions inside
+// the tile loops).
+struct BiasIdx {
     const float* tab;      // shared memory, [(2gh-1)*(2gw-1)] for this head (nullptr = no bias)
-    int gw, ww, off;
-    __device__ __forceinline__ float operator()(int i, int j) const {
-        if (!tab) return 0.f;
-        const int yi = i / gw, xi = i - yi * gw, yj = j / gw, xj = j - yj * gw;
-        return tab[(yi - yj) * ww + (xi - xj) + off];
-    }
-    __device__ __forceinline__ int index(int i, int j) const {
-        const int yi = i / gw, xi = i - yi * gw, yj = j / gw, xj = j - yj * gw;
-        return (yi - yj) * ww + (xi - xj) + off;
-    }
+    const int* pos;        // shared memory, [Lp]
+    int off;
+    __device__ __forceinline__ int index(int i, int j) const { return pos[i] + off - pos[j]; }
+    __device__ __forceinline__ float operator()(int i, int j) const { return tab ? tab[index(i, j)] : 0.f; }
 };
 
-__device__ __forceinline__ BiasIdx make_bias(const float* tab_smem, int gh, int gw) {
+__device__ __forceinline__ void fill_pos(int* pos, int Lp, int L, int gw, int tid, int nthreads) {
+    const int ww = 2 * gw - 1;
+    for (int n = tid; n < Lp; n += nthreads) {
+        const int m = n < L ? n : L - 1;
+        pos[n] = gw > 0 ? (m / gw) * ww + (m % gw) : 0;
+    }
+}
+__device__ __forceinline__ BiasIdx make_bias(const float* tab_smem, const int* pos_smem, int gh, int gw) {
     BiasIdx b;
-    b.tab = tab_smem; b.gw = gw; b.ww = 2 * gw - 1; b.off = (gh - 1) * (2 * gw - 1) + (gw - 1);
+    b.tab = tab_smem; b.pos = pos_smem; b.off = (gh - 1) * (2 * gw - 1) + (gw - 1);
     return b;
 }
 
 // =============================================================================================
-// forward: grid (q blocks of 64, heads, nseq), 128 threads
-// smem: K [Lp][32] | V [Lp][32] | Q [64][32] | table
+// forward: grid (q blocks of 16*NW, heads, nseq), 32*NW threads
+// smem: K [Lp][32] | V [Lp][32] | Q [16 NW][32] | table | pos
 // =============================================================================================
-__global__ void __launch_bounds__(128)
+template <int NW>
+__global__ void __launch_bounds__(32 * NW)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int L, int heads, int gh, int gw) {
+    constexpr int QB = 16 * NW, NT = 32 * NW;
     extern __shared__ __align__(128) uint8_t smem[];
     const int Lp = (L + 63) & ~63;
     uint8_t* sK = smem;
     uint8_t* sV = sK + Lp * 64;
     uint8_t* sQ = sV + Lp * 64;
-    float* sT = reinterpret_cast<float*>(sQ + 64 * 64);
+    int* sP = reinterpret_cast<int*>(sQ + QB * 64);
+    float* sT = reinterpret_cast<float*>(sP + Lp);
     const int qb = blockIdx.x, h = blockIdx.y, s = blockIdx.z;
     const int inner = heads * 32;
     const long long ld = 3LL * inner;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
-    load_tile(sK, base + inner, ld, Lp, L, tid, 128);
-    load_tile(sV, base + 2 * inner, ld, Lp, L, tid, 128);
-    load_tile(sQ, base + (long long)qb * 64 * ld, ld, 64, L - qb * 64, tid, 128);
+    load_tile(sK, base + inner, ld, Lp, L, tid, NT);
+    load_tile(sV, base + 2 * inner, ld, Lp, L, tid, NT);
+    load_tile(sQ, base + (long long)qb * QB * ld, ld, QB, L - qb * QB, tid, NT);
     const int n_off = (2 * gh - 1) * (2 * gw - 1);
     if (table)
-        for (int i = tid; i < n_off; i += 128) sT[i] = table[(long long)h * n_off + i];
+        for (int i = tid; i < n_off; i += NT) sT[i] = table[(long long)h * n_off + i] * LOG2E;
+    fill_pos(sP, Lp, L, gw, tid, NT);
     __syncthreads();
-    const BiasIdx bias = make_bias(table ? sT : nullptr, gh, gw);
+    const BiasIdx bias = make_bias(table ? sT : nullptr, sP, gh, gw);
     const uint32_t tK = smem_u32(sK), tV = smem_u32(sV), tQ = smem_u32(sQ);
     uint32_t qa[2][4];
     load_a_frags(qa, tQ, warp * 16, lane);
     const int g = lane >> 2, t = lane & 3;
-    const int i0 = qb * 64 + warp * 16 + g, i1 = i0 + 8;      // this thread's two query rows
+    const int i0 = qb * QB + warp * 16 + g, i1 = i0 + 8;      // this thread's two query rows
+    const int rb0 = sP[min(i0, Lp - 1)] + bias.off, rb1 = sP[min(i1, Lp - 1)] + bias.off;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float o[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) o[a][0] = o[a][1] = o[a][2] = o[a][3] = 0.f;
+    const bool has_bias = table != nullptr;
 
     for (int kb = 0; kb < Lp; kb += 64) {
         float sc[8][4];
         mma_16x64(sc, qa, tK, kb, lane);
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = kb + nt * 8 + 2 * t + (e & 1);
-                const int i = (e < 2) ? i0 : i1;
-                float x = (sc[nt][e] + bias(min(i, L - 1), min(j, L - 1))) * LOG2E;
-                if (j >= L) x = -INFINITY;
-                sc[nt][e] = x;
-                if (e < 2) mx0 = fmaxf(mx0, x); else mx1 = fmaxf(mx1, x);
+        for (int nt = 0; nt < 8; ++nt) {
+            const int j = kb + nt * 8 + 2 * t;
+            float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+            if (has_bias) {
+                const int2 pj = *reinterpret_cast<const int2*>(sP + j);
+                b00 = sT[rb0 - pj.x]; b01 = sT[rb0 - pj.y]; b10 = sT[rb1 - pj.x]; b11 = sT[rb1 - pj.y];
             }
+            sc[nt][0] = fmaf(sc[nt][0], LOG2E, b00); sc[nt][1] = fmaf(sc[nt][1], LOG2E, b01);
+            sc[nt][2] = fmaf(sc[nt][2], LOG2E, b10); sc[nt][3] = fmaf(sc[nt][3], LOG2E, b11);
+            if (kb + 64 > L) {                   // only the last key block can hold padding
+                if (j >= L) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
+                if (j + 1 >= L) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
+            }
+            mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
         mx0 = quad_max(mx0); mx1 = quad_max(mx1);
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
         const float r0 = exp2f(m0 - mn0), r1 = exp2f(m1 - mn1);
@@ -239,41 +255,85 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
     delta[(sq * heads + h) * L + (row % L)] = acc;
 }
 
+// dS for a 16x64 accumulator pair: sc <- p * (dp - delta), p = exp2(s*log2e + bias - lse)
+// (rows = the thread's fixed index pair, columns = the looped index). ROWS_ARE_QUERIES selects
+// which of (row, column) is the query for the bias / lse / delta lookups.
+template <bool ROWS_ARE_QUERIES>
+__device__ __forceinline__ void ds_from_scores(float (&sc)[8][4], const float (&dpv)[8][4], const BiasIdx& bias,
+                                               bool has_bias, int c0, int t, int r0, int r1, int L,
+                                               float rstat0, float rstat1, float rdel0, float rdel1,
+                                               const float* sL, const float* sD, bool keep_p, float (&pout)[8][4]) {
+    // rows-are-queries: rstat = lse*log2e of the two rows, rdel = delta of the two rows
+    // rows-are-keys   : per-column lse/delta come from sL/sD (shared memory)
+    const int pr0 = bias.pos[min(r0, L - 1)], pr1 = bias.pos[min(r1, L - 1)];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = c0 + nt * 8 + 2 * t;
+        const int2 pc = *reinterpret_cast<const int2*>(bias.pos + c);
+        float b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (has_bias) {
+            if (ROWS_ARE_QUERIES) {
+                b[0] = bias.tab[pr0 + bias.off - pc.x]; b[1] = bias.tab[pr0 + bias.off - pc.y];
+                b[2] = bias.tab[pr1 + bias.off - pc.x]; b[3] = bias.tab[pr1 + bias.off - pc.y];
+            } else {
+                b[0] = bias.tab[pc.x + bias.off - pr0]; b[1] = bias.tab[pc.y + bias.off - pr0];
+                b[2] = bias.tab[pc.x + bias.off - pr1]; b[3] = bias.tab[pc.y + bias.off - pr1];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int cc = c + (e & 1);
+            const int rr = e < 2 ? r0 : r1;
+            float lsev, delv;
+            if (ROWS_ARE_QUERIES) { lsev = e < 2 ? rstat0 : rstat1; delv = e < 2 ? rdel0 : rdel1; }
+            else { lsev = sL[cc]; delv = sD[cc]; }
+            const float x = fmaf(sc[nt][e], LOG2E, b[e]);
+            const float p = (cc < L && rr < L) ? exp2f(x - lsev) : 0.f;
+            if (keep_p) pout[nt][e] = p;
+            sc[nt][e] = p * (dpv[nt][e] - delv);
+        }
+    }
+}
+
 // =============================================================================================
-// backward, dq: grid (q blocks, heads, nseq). smem: K | V | Q tile | dO tile | table
+// backward, dq: grid (q blocks of 16 NW, heads, nseq). smem: K | V | Q tile | dO tile | pos | table
 // =============================================================================================
-__global__ void __launch_bounds__(128)
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 2)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
                    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int heads,
                    int gh, int gw) {
+    constexpr int QB = 16 * NW, NT = 32 * NW;
     extern __shared__ __align__(128) uint8_t smem[];
     const int Lp = (L + 63) & ~63;
     uint8_t* sK = smem;
     uint8_t* sV = sK + Lp * 64;
     uint8_t* sQ = sV + Lp * 64;
-    uint8_t* sdO = sQ + 64 * 64;
-    float* sT = reinterpret_cast<float*>(sdO + 64 * 64);
+    uint8_t* sdO = sQ + QB * 64;
+    int* sP = reinterpret_cast<int*>(sdO + QB * 64);
+    float* sT = reinterpret_cast<float*>(sP + Lp);
     const int qb = blockIdx.x, h = blockIdx.y, s = blockIdx.z;
     const int inner = heads * 32;
     const long long ld = 3LL * inner;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
-    load_tile(sK, base + inner, ld, Lp, L, tid, 128);
-    load_tile(sV, base + 2 * inner, ld, Lp, L, tid, 128);
-    load_tile(sQ, base + (long long)qb * 64 * ld, ld, 64, L - qb * 64, tid, 128);
-    load_tile(sdO, dout + ((long long)s * L + qb * 64) * inner + h * 32, inner, 64, L - qb * 64, tid, 128);
+    load_tile(sK, base + inner, ld, Lp, L, tid, NT);
+    load_tile(sV, base + 2 * inner, ld, Lp, L, tid, NT);
+    load_tile(sQ, base + (long long)qb * QB * ld, ld, QB, L - qb * QB, tid, NT);
+    load_tile(sdO, dout + ((long long)s * L + qb * QB) * inner + h * 32, inner, QB, L - qb * QB, tid, NT);
     const int n_off = (2 * gh - 1) * (2 * gw - 1);
     if (table)
-        for (int i = tid; i < n_off; i += 128) sT[i] = table[(long long)h * n_off + i];
+        for (int i = tid; i < n_off; i += NT) sT[i] = table[(long long)h * n_off + i] * LOG2E;
+    fill_pos(sP, Lp, L, gw, tid, NT);
     __syncthreads();
-    const BiasIdx bias = make_bias(table ? sT : nullptr, gh, gw);
+    const BiasIdx bias = make_bias(table ? sT : nullptr, sP, gh, gw);
     const uint32_t tK = smem_u32(sK), tV = smem_u32(sV);
     uint32_t qa[2][4], da[2][4];
     load_a_frags(qa, smem_u32(sQ), warp * 16, lane);
     load_a_frags(da, smem_u32(sdO), warp * 16, lane);
     const int g = lane >> 2, t = lane & 3;
-    const int i0 = qb * 64 + warp * 16 + g, i1 = i0 + 8;
+    const int i0 = qb * QB + warp * 16 + g, i1 = i0 + 8;
     const float* lp = lse + ((long long)s * heads + h) * L;
     const float* dp = delta + ((long long)s * heads + h) * L;
     const float lse0 = (i0 < L ? lp[i0] : 0.f) * LOG2E, lse1 = (i1 < L ? lp[i1] : 0.f) * LOG2E;
@@ -285,16 +345,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
         float sc[8][4], dpv[8][4];
         mma_16x64(sc, qa, tK, kb, lane);
         mma_16x64(dpv, da, tV, kb, lane);
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = kb + nt * 8 + 2 * t + (e & 1);
-                const int i = (e < 2) ? i0 : i1;
-                const float x = (sc[nt][e] + bias(min(i, L - 1), min(j, L - 1))) * LOG2E;
-                const float p = (j < L && i < L) ? exp2f(x - (e < 2 ? lse0 : lse1)) : 0.f;
-                sc[nt][e] = p * (dpv[nt][e] - (e < 2 ? dl0 : dl1));      // dS
-            }
+        ds_from_scores<true>(sc, dpv, bias, table != nullptr, kb, t, i0, i1, L, lse0, lse1, dl0, dl1, nullptr,
+                             nullptr, false, dpv);
         mma_acc_16x32(dq, sc, tK, kb, lane);
     }
     __nv_bfloat16* ob = dqkv + (long long)s * L * ld + h * 32;
@@ -307,49 +359,53 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
 }
 
 // =============================================================================================
-// backward, dk & dv (transposed tiles: rows = keys): grid (kv blocks, heads, nseq).
-// smem: Q [Lp][32] | dO [Lp][32] | K tile | V tile | lse [Lp] | delta [Lp] | table
+// backward, dk & dv (transposed tiles: rows = keys): grid (kv blocks of 16 NW, heads, nseq).
+// smem: Q [Lp][32] | dO [Lp][32] | K tile | V tile | lse [Lp] | delta [Lp] | pos | table
 // =============================================================================================
-__global__ void __launch_bounds__(128)
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 2)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
                     const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                     const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int heads,
                     int gh, int gw) {
+    constexpr int KB = 16 * NW, NT = 32 * NW;
     extern __shared__ __align__(128) uint8_t smem[];
     const int Lp = (L + 63) & ~63;
     uint8_t* sQ = smem;
     uint8_t* sdO = sQ + Lp * 64;
     uint8_t* sK = sdO + Lp * 64;
-    uint8_t* sV = sK + 64 * 64;
-    float* sL = reinterpret_cast<float*>(sV + 64 * 64);
+    uint8_t* sV = sK + KB * 64;
+    float* sL = reinterpret_cast<float*>(sV + KB * 64);
     float* sD = sL + Lp;
-    float* sT = sD + Lp;
+    int* sP = reinterpret_cast<int*>(sD + Lp);
+    float* sT = reinterpret_cast<float*>(sP + Lp);
     const int jb = blockIdx.x, h = blockIdx.y, s = blockIdx.z;
     const int inner = heads * 32;
     const long long ld = 3LL * inner;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
-    load_tile(sQ, base, ld, Lp, L, tid, 128);
-    load_tile(sdO, dout + (long long)s * L * inner + h * 32, inner, Lp, L, tid, 128);
-    load_tile(sK, base + inner + (long long)jb * 64 * ld, ld, 64, L - jb * 64, tid, 128);
-    load_tile(sV, base + 2 * inner + (long long)jb * 64 * ld, ld, 64, L - jb * 64, tid, 128);
+    load_tile(sQ, base, ld, Lp, L, tid, NT);
+    load_tile(sdO, dout + (long long)s * L * inner + h * 32, inner, Lp, L, tid, NT);
+    load_tile(sK, base + inner + (long long)jb * KB * ld, ld, KB, L - jb * KB, tid, NT);
+    load_tile(sV, base + 2 * inner + (long long)jb * KB * ld, ld, KB, L - jb * KB, tid, NT);
     const float* lp = lse + ((long long)s * heads + h) * L;
     const float* dp = delta + ((long long)s * heads + h) * L;
-    for (int i = tid; i < Lp; i += 128) {
+    for (int i = tid; i < Lp; i += NT) {
         sL[i] = i < L ? lp[i] * LOG2E : 0.f;
         sD[i] = i < L ? dp[i] : 0.f;
     }
     const int n_off = (2 * gh - 1) * (2 * gw - 1);
     if (table)
-        for (int i = tid; i < n_off; i += 128) sT[i] = table[(long long)h * n_off + i];
+        for (int i = tid; i < n_off; i += NT) sT[i] = table[(long long)h * n_off + i] * LOG2E;
+    fill_pos(sP, Lp, L, gw, tid, NT);
     __syncthreads();
-    const BiasIdx bias = make_bias(table ? sT : nullptr, gh, gw);
+    const BiasIdx bias = make_bias(table ? sT : nullptr, sP, gh, gw);
     const uint32_t tQ = smem_u32(sQ), tdO = smem_u32(sdO);
     uint32_t ka[2][4], va[2][4];
     load_a_frags(ka, smem_u32(sK), warp * 16, lane);
     load_a_frags(va, smem_u32(sV), warp * 16, lane);
     const int g = lane >> 2, t = lane & 3;
-    const int j0 = jb * 64 + warp * 16 + g, j1 = j0 + 8;       // this thread's two key rows
+    const int j0 = jb * KB + warp * 16 + g, j1 = j0 + 8;       // this thread's two key rows
     float dk[4][4], dv[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -357,22 +413,13 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
         dv[a][0] = dv[a][1] = dv[a][2] = dv[a][3] = 0.f;
     }
     for (int ib = 0; ib < Lp; ib += 64) {
-        float st[8][4], dpt[8][4];
+        float st[8][4], dpt[8][4], pt[8][4];
         mma_16x64(st, ka, tQ, ib, lane);          // S^T[key, query] = K Q^T
         mma_16x64(dpt, va, tdO, ib, lane);        // dP^T[key, query] = V dO^T
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int i = ib + nt * 8 + 2 * t + (e & 1);   // query (column)
-                const int j = (e < 2) ? j0 : j1;               // key (row)
-                const float x = (st[nt][e] + bias(min(i, L - 1), min(j, L - 1))) * LOG2E;
-                const float p = (i < L && j < L) ? exp2f(x - sL[i]) : 0.f;
-                st[nt][e] = p;
-                dpt[nt][e] = p * (dpt[nt][e] - sD[i]);         // dS^T
-            }
-        mma_acc_16x32(dv, st, tdO, ib, lane);     // dV += P^T dO
-        mma_acc_16x32(dk, dpt, tQ, ib, lane);     // dK += dS^T Q
+        ds_from_scores<false>(st, dpt, bias, table != nullptr, ib, t, j0, j1, L, 0.f, 0.f, 0.f, 0.f, sL, sD,
+                              true, pt);          // st <- dS^T, pt <- P^T
+        mma_acc_16x32(dv, pt, tdO, ib, lane);     // dV += P^T dO
+        mma_acc_16x32(dk, st, tQ, ib, lane);      // dK += dS^T Q
     }
     __nv_bfloat16* ob = dqkv + (long long)s * L * ld + h * 32;
 #pragma unroll
@@ -390,66 +437,118 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
 }
 
 // =============================================================================================
-// backward, bias table: grid (kv blocks, q blocks, heads); loops over sequences accumulating dS of
-// one 64x64 tile in registers, then scatters into the (2gh-1)(2gw-1) table with atomics.
+// backward, bias table: grid (kv blocks, q blocks, heads * nchunk); each CTA owns one 64x64 tile of
+// dS, walks its chunk of the sequences with a 2-stage cp.async ring, accumulates dS in registers,
+// folds it into a shared-memory copy of the (2gh-1)(2gw-1) table and flushes the touched entries.
+// smem: 2 x {Q, dO, K, V tiles, lse[64], delta[64]} | pos | bias table | accumulation table
 // =============================================================================================
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void load_tile_async(uint32_t dst, const __nv_bfloat16* src, long long ld, int valid,
+                                                int tid) {
+    for (int i = tid; i < 64 * 4; i += 128) {
+        const int row = i >> 2, c = i & 3;
+        const bool ok = row < valid;
+        cp_async16(dst + tile_off(row, c), src + (long long)(ok ? row : 0) * ld + c * 8, ok);
+    }
+}
+
+constexpr int DB_STAGE = 4 * 64 * 64 + 2 * 64 * 4;     // bytes per stage
+
+__global__ void __launch_bounds__(128, 3)
 attn_bwd_dbias_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table,
                       const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                       const float* __restrict__ delta, float* __restrict__ dtable, int nseq, int L,
-                      int heads, int gh, int gw) {
-    __shared__ __align__(128) uint8_t sQ[64 * 64], sdO[64 * 64], sK[64 * 64], sV[64 * 64];
-    extern __shared__ __align__(128) float sT[];
-    const int jb = blockIdx.x, qb = blockIdx.y, h = blockIdx.z;
+                      int heads, int gh, int gw, int nchunk) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int Lp = (L + 63) & ~63;
+    const int n_off = (2 * gh - 1) * (2 * gw - 1);
+    uint8_t* stage0 = smem;
+    int* sP = reinterpret_cast<int*>(smem + 2 * DB_STAGE);
+    float* sT = reinterpret_cast<float*>(sP + Lp);
+    float* sA = sT + n_off;
+    const int jb = blockIdx.x, qb = blockIdx.y;
+    const int h = blockIdx.z / nchunk, chunk = blockIdx.z % nchunk;
     const int inner = heads * 32;
     const long long ld = 3LL * inner;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_off = (2 * gh - 1) * (2 * gw - 1);
-    for (int i = tid; i < n_off; i += 128) sT[i] = table[(long long)h * n_off + i];
-    const BiasIdx bias = make_bias(sT, gh, gw);
+    for (int i = tid; i < n_off; i += 128) { sT[i] = table[(long long)h * n_off + i] * LOG2E; sA[i] = 0.f; }
+    fill_pos(sP, Lp, L, gw, tid, 128);
+    const int per = (nseq + nchunk - 1) / nchunk;
+    const int s_begin = chunk * per, s_end = min(nseq, s_begin + per);
+    const int q_valid = L - qb * 64, k_valid = L - jb * 64;
+
+    auto issue = [&](int s, int st) {
+        const uint32_t sb = smem_u32(stage0 + st * DB_STAGE);
+        const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
+        load_tile_async(sb, base + (long long)qb * 64 * ld, ld, q_valid, tid);
+        load_tile_async(sb + 4096, dout + ((long long)s * L + qb * 64) * inner + h * 32, inner, q_valid, tid);
+        load_tile_async(sb + 8192, base + inner + (long long)jb * 64 * ld, ld, k_valid, tid);
+        load_tile_async(sb + 12288, base + 2 * inner + (long long)jb * 64 * ld, ld, k_valid, tid);
+        if (tid < 64) {
+            const int i = min(qb * 64 + tid, L - 1);
+            cp_async4(sb + 16384 + tid * 4, lse + ((long long)s * heads + h) * L + i);
+            cp_async4(sb + 16384 + 256 + tid * 4, delta + ((long long)s * heads + h) * L + i);
+        }
+        cp_async_commit();
+    };
+
     const int g = lane >> 2, t = lane & 3;
-    const int i0 = qb * 64 + warp * 16 + g, i1 = i0 + 8;
+    const int r0 = warp * 16 + g, r1 = r0 + 8;                 // tile-local query rows
+    const int i0 = qb * 64 + r0, i1 = qb * 64 + r1;
     float acc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-    for (int s = 0; s < nseq; ++s) {
-        __syncthreads();
-        const __nv_bfloat16* base = qkv + (long long)s * L * ld + h * 32;
-        load_tile(sQ, base + (long long)qb * 64 * ld, ld, 64, L - qb * 64, tid, 128);
-        load_tile(sdO, dout + ((long long)s * L + qb * 64) * inner + h * 32, inner, 64, L - qb * 64, tid, 128);
-        load_tile(sK, base + inner + (long long)jb * 64 * ld, ld, 64, L - jb * 64, tid, 128);
-        load_tile(sV, base + 2 * inner + (long long)jb * 64 * ld, ld, 64, L - jb * 64, tid, 128);
-        __syncthreads();
+    if (s_begin < s_end) issue(s_begin, 0);
+    for (int s = s_begin; s < s_end; ++s) {
+        const int st = (s - s_begin) & 1;
+        cp_async_wait<0>();
+        __syncthreads();                          // stage `st` landed; everyone is done with the other stage
+        if (s + 1 < s_end) issue(s + 1, st ^ 1);
+        const uint8_t* sb = stage0 + st * DB_STAGE;
+        const uint32_t tb = smem_u32(sb);
+        const float* sLs = reinterpret_cast<const float*>(sb + 16384);
+        const float* sDs = sLs + 64;
         uint32_t qa[2][4], da[2][4];
-        load_a_frags(qa, smem_u32(sQ), warp * 16, lane);
-        load_a_frags(da, smem_u32(sdO), warp * 16, lane);
-        const float* lp = lse + ((long long)s * heads + h) * L;
-        const float* dp = delta + ((long long)s * heads + h) * L;
-        const float lse0 = (i0 < L ? lp[i0] : 0.f) * LOG2E, lse1 = (i1 < L ? lp[i1] : 0.f) * LOG2E;
-        const float dl0 = i0 < L ? dp[i0] : 0.f, dl1 = i1 < L ? dp[i1] : 0.f;
+        load_a_frags(qa, tb, warp * 16, lane);
+        load_a_frags(da, tb + 4096, warp * 16, lane);
         float sc[8][4], dpv[8][4];
-        mma_16x64(sc, qa, smem_u32(sK), 0, lane);
-        mma_16x64(dpv, da, smem_u32(sV), 0, lane);
+        mma_16x64(sc, qa, tb + 8192, 0, lane);
+        mma_16x64(dpv, da, tb + 12288, 0, lane);
+        const BiasIdx bias = make_bias(sT, sP, gh, gw);
+        // columns are addressed globally (jb*64 + ...) for the bias / validity tests
+        const float lse0 = sLs[r0] * LOG2E, lse1 = sLs[r1] * LOG2E;
+        ds_from_scores<true>(sc, dpv, bias, true, jb * 64, t, i0, i1, L, lse0, lse1, sDs[r0], sDs[r1], nullptr,
+                             nullptr, false, dpv);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = jb * 64 + nt * 8 + 2 * t + (e & 1);
-                const int i = (e < 2) ? i0 : i1;
-                const float x = (sc[nt][e] + bias(min(i, L - 1), min(j, L - 1))) * LOG2E;
-                const float p = (j < L && i < L) ? exp2f(x - (e < 2 ? lse0 : lse1)) : 0.f;
-                acc[nt][e] += p * (dpv[nt][e] - (e < 2 ? dl0 : dl1));
-            }
+            for (int e = 0; e < 4; ++e) acc[nt][e] += sc[nt][e];
     }
-    float* dt = dtable + (long long)h * n_off;
+    __syncthreads();
+    const BiasIdx bias = make_bias(sT, sP, gh, gw);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int j = jb * 64 + nt * 8 + 2 * t + (e & 1);
             const int i = (e < 2) ? i0 : i1;
-            if (i < L && j < L) atomicAdd(dt + bias.index(i, j), acc[nt][e]);
+            if (i < L && j < L) atomicAdd(sA + bias.index(i, j), acc[nt][e]);
         }
+    __syncthreads();
+    float* dt = dtable + (long long)h * n_off;
+    for (int i = tid; i < n_off; i += 128) {
+        const float v = sA[i];
+        if (v != 0.f) atomicAdd(dt + i, v);
+    }
 }
 
 // =============================================================================================
@@ -604,38 +703,70 @@ qknorm_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, const __nv_bfloat16* __restr
                   const float* __restrict__ rnorm, const float* __restrict__ q_scale,
                   const float* __restrict__ k_scale, float alpha, float* __restrict__ dq_scale,
                   float* __restrict__ dk_scale, long long rows, int heads) {
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    // thread per (row, q|k head): 32 channels = 64 contiguous bytes. The thread's slot type (q or k)
+    // is fixed across its grid-stride loop (stride is a multiple of 2*heads), so the per-channel
+    // scale gradient accumulates in registers.
     const int inner = heads * 32;
     const long long ld = 3LL * inner;
-    const float qs = q_scale[lane], ks = k_scale[lane];
-    float acc_q = 0.f, acc_k = 0.f;
-    const long long total = rows * 2 * heads;
-    for (long long w = warp_global; w < total; w += nwarps) {
-        const long long row = w / (2 * heads);
-        const int slot = (int)(w % (2 * heads));           // [0,heads): q heads, [heads,2heads): k heads
-        const bool is_q = slot < heads;
-        const long long off = row * ld + (long long)slot * 32 + lane;
-        const float sc = is_q ? qs * alpha : ks;
-        const float y = __bfloat162float(qkv[off]);
-        const float dy = __bfloat162float(dqkv[off]);
-        const float xh = sc != 0.f ? y / sc : 0.f;
-        const float gg = dy * sc;
-        const float dotv = warp_sum(xh * gg);
-        const float rn = rnorm[row * 2 * heads + slot];
-        dqkv[off] = __float2bfloat16(rn * (gg - xh * dotv));
-        if (is_q) acc_q = fmaf(dy * xh, alpha, acc_q); else acc_k = fmaf(dy, xh, acc_k);
+    const int nslot = 2 * heads;
+    const long long total = rows * nslot;
+    const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of 2*heads (host guarantees)
+    const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = (int)(idx0 % nslot);
+    const bool is_q = slot < heads;
+    const float* scp = is_q ? q_scale : k_scale;
+    const float a = is_q ? alpha : 1.f;
+    float sc[32], acc[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) { sc[d] = __ldg(scp + d) * a; acc[d] = 0.f; }
+    for (long long idx = idx0; idx < total; idx += stride) {
+        const long long row = idx / nslot;
+        const long long off = row * ld + (long long)slot * 32;
+        float y[32], dy[32];
+        load_row32(qkv + off, y);
+        load_row32(dqkv + off, dy);
+        float dotv = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+            const float xh = sc[d] != 0.f ? __fdividef(y[d], sc[d]) : 0.f;
+            acc[d] = fmaf(dy[d], xh, acc[d]);
+            y[d] = xh;
+            dy[d] *= sc[d];                                  // g = d loss / d xhat
+            dotv = fmaf(xh, dy[d], dotv);
+        }
+        const float rn = rnorm[row * nslot + slot];
+#pragma unroll
+        for (int d = 0; d < 32; ++d) dy[d] = rn * (dy[d] - y[d] * dotv);
+        store_row32(dqkv + off, dy);
     }
-    atomicAdd(dq_scale + lane, acc_q);
-    atomicAdd(dk_scale + lane, acc_k);
+    // reduce the scale gradients: lanes with the same slot type sit 2*heads apart... reduce over the
+    // whole warp per type with a masked butterfly, then one atomic per channel per warp and type
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+        float vq = is_q ? acc[d] * a : 0.f, vk = is_q ? 0.f : acc[d];
+        vq = warp_sum(vq);
+        vk = warp_sum(vk);
+        if (lane == 0) {
+            atomicAdd(dq_scale + d, vq);
+            atomicAdd(dk_scale + d, vk);
+        }
+    }
 }
 
 }  // namespace
 
-static size_t fwd_smem(int L, int gh, int gw, bool bias) {
+static size_t long_smem(int L, int gh, int gw, bool bias, int row_block, bool bwd_dkv) {
     const int Lp = (L + 63) & ~63;
-    return (size_t)Lp * 128 + 64 * 64 + (bias ? (size_t)(2 * gh - 1) * (2 * gw - 1) * 4 : 0);
+    size_t b = (size_t)Lp * 128 + (size_t)Lp * 4 + (bias ? (size_t)(2 * gh - 1) * (2 * gw - 1) * 4 : 0);
+    b += bwd_dkv ? (size_t)row_block * 128 + (size_t)Lp * 8 : (size_t)row_block * 128;   // 2 tiles (+lse, delta)
+    return b;
+}
+
+template <typename K>
+static int set_smem(K kern, size_t bytes) {
+    CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return CTK_OK;
 }
 
 extern "C" int ctk_attn_fwd(const void* qkv, const float* table, void* out, float* lse, int nseq, int L,
@@ -655,10 +786,17 @@ extern "C" int ctk_attn_fwd(const void* qkv, const float* table, void* out, floa
         CTK_LAUNCH_CHECK();
         return CTK_OK;
     }
-    const size_t sm = fwd_smem(L, gh, gw, table != nullptr);
-    CTK_REQUIRE(sm <= 220 * 1024, CTK_ERR_SHAPE, "attn_fwd: sequence of %d tokens does not fit in shared memory", L);
-    CTK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    attn_fwd_kernel<<<dim3((L + 63) / 64, heads, nseq), 128, sm, s>>>(q, table, o, lse, L, heads, gh, gw);
+    // 9 warps (144 queries) per CTA when the sequence is long enough: 576 = 4 x 144, 2 CTAs / SM
+    if (L >= 144) {
+        const size_t sm = long_smem(L, gh, gw, table != nullptr, 144, false) - 144 * 64;   // one tile (Q) only
+        CTK_REQUIRE(sm <= 220 * 1024, CTK_ERR_SHAPE, "attn_fwd: sequence of %d tokens does not fit in shared memory", L);
+        if ((rc = set_smem(attn_fwd_kernel<9>, sm))) return rc;
+        attn_fwd_kernel<9><<<dim3((L + 143) / 144, heads, nseq), 288, sm, s>>>(q, table, o, lse, L, heads, gh, gw);
+    } else {
+        const size_t sm = long_smem(L, gh, gw, table != nullptr, 64, false) - 64 * 64;
+        if ((rc = set_smem(attn_fwd_kernel<4>, sm))) return rc;
+        attn_fwd_kernel<4><<<dim3((L + 63) / 64, heads, nseq), 128, sm, s>>>(q, table, o, lse, L, heads, gh, gw);
+    }
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
@@ -687,21 +825,38 @@ extern "C" int ctk_attn_bwd(const void* qkv, const float* table, const void* out
     const long long rows = (long long)nseq * L;
     attn_delta_kernel<<<(unsigned)((rows * heads + 255) / 256), 256, 0, s>>>(o, d_o, delta, rows, L, heads);
     CTK_LAUNCH_CHECK();
-    const int Lp = (L + 63) & ~63;
-    const size_t tab = table ? (size_t)(2 * gh - 1) * (2 * gw - 1) * 4 : 0;
-    const size_t sm_dq = (size_t)Lp * 128 + 2 * 64 * 64 + tab;
-    const size_t sm_dkv = (size_t)Lp * 128 + 2 * 64 * 64 + (size_t)Lp * 8 + tab;
-    CTK_REQUIRE(sm_dkv <= 220 * 1024, CTK_ERR_SHAPE, "attn_bwd: sequence of %d tokens does not fit in shared memory", L);
-    CTK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq));
-    CTK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dkv));
-    const dim3 grid((L + 63) / 64, heads, nseq);
-    attn_bwd_dq_kernel<<<grid, 128, sm_dq, s>>>(q, table, d_o, lse, delta, dq, L, heads, gh, gw);
-    CTK_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<<<grid, 128, sm_dkv, s>>>(q, table, d_o, lse, delta, dq, L, heads, gh, gw);
-    CTK_LAUNCH_CHECK();
+    const bool hb = table != nullptr;
+    if (L >= 128) {
+        // dq: 8 warps (128 queries), dk/dv: 6 warps (96 keys; 576 = 6 x 96); 2 CTAs / SM each
+        const size_t sm_dq = long_smem(L, gh, gw, hb, 128, false), sm_dkv = long_smem(L, gh, gw, hb, 96, true);
+        CTK_REQUIRE(sm_dq <= 220 * 1024 && sm_dkv <= 220 * 1024, CTK_ERR_SHAPE,
+                    "attn_bwd: sequence of %d tokens does not fit in shared memory", L);
+        if ((rc = set_smem(attn_bwd_dq_kernel<8>, sm_dq))) return rc;
+        if ((rc = set_smem(attn_bwd_dkv_kernel<6>, sm_dkv))) return rc;
+        attn_bwd_dq_kernel<8><<<dim3((L + 127) / 128, heads, nseq), 256, sm_dq, s>>>(q, table, d_o, lse, delta, dq, L, heads, gh, gw);
+        CTK_LAUNCH_CHECK();
+        attn_bwd_dkv_kernel<6><<<dim3((L + 95) / 96, heads, nseq), 192, sm_dkv, s>>>(q, table, d_o, lse, delta, dq, L, heads, gh, gw);
+        CTK_LAUNCH_CHECK();
+    } else {
+        const size_t sm_dq = long_smem(L, gh, gw, hb, 64, false), sm_dkv = long_smem(L, gh, gw, hb, 64, true);
+        if ((rc = set_smem(attn_bwd_dq_kernel<4>, sm_dq))) return rc;
+        if ((rc = set_smem(attn_bwd_dkv_kernel<4>, sm_dkv))) return rc;
+        const dim3 grid((L + 63) / 64, heads, nseq);
+        attn_bwd_dq_kernel<4><<<grid, 128, sm_dq, s>>>(q, table, d_o, lse, delta, dq, L, heads, gh, gw);
+        CTK_LAUNCH_CHECK();
+        attn_bwd_dkv_kernel<4><<<grid, 128, sm_dkv, s>>>(q, table, d_o, lse, delta, dq, L, heads, gh, gw);
+        CTK_LAUNCH_CHECK();
+    }
     if (table) {
         const int nb = (L + 63) / 64;
-        attn_bwd_dbias_kernel<<<dim3(nb, nb, heads), 128, tab, s>>>(q, table, d_o, lse, delta, dtable, nseq, L, heads, gh, gw);
+        const int Lp = nb * 64;
+        int nchunk = nseq / 16;
+        if (nchunk < 1) nchunk = 1;
+        if (nchunk > 8) nchunk = 8;
+        const size_t sm = 2 * (size_t)DB_STAGE + (size_t)Lp * 4 + 2 * (size_t)(2 * gh - 1) * (2 * gw - 1) * 4;
+        if ((rc = set_smem(attn_bwd_dbias_kernel, sm))) return rc;
+        attn_bwd_dbias_kernel<<<dim3(nb, nb, heads * nchunk), 128, sm, s>>>(q, table, d_o, lse, delta, dtable, nseq, L,
+                                                                           heads, gh, gw, nchunk);
         CTK_LAUNCH_CHECK();
     }
     return CTK_OK;
@@ -715,7 +870,8 @@ extern "C" int ctk_qknorm_bwd(void* dqkv, const void* qkv, const float* rnorm, c
     CTK_REQUIRE(dqkv && qkv && rnorm && q_scale && k_scale && dq_scale && dk_scale && rows > 0 && heads > 0,
                 CTK_ERR_SHAPE, "qknorm_bwd: bad args");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    long long blocks = (rows * 2 * heads + 7) / 8;
+    CTK_REQUIRE(256 % (2 * heads) == 0, CTK_ERR_SHAPE, "qknorm_bwd: heads must divide 128");
+    long long blocks = (rows * 2 * heads + 255) / 256;
     const long long cap = (long long)ctk_num_sms() * 8;
     if (blocks > cap) blocks = cap;
     qknorm_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(dqkv),

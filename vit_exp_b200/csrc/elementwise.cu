@@ -256,31 +256,33 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
 
 // =============================================================================================
 // PEG: depthwise causal 3x3x3 conv + bias + residual on [B, n0, n1, n2, dim] (attention.py:62-90,443)
-// thread.x <-> 2 channels, thread.y <-> one line along n2; sliding 3-wide register window per
-// neighbour line. REVERSE = transposed conv for the input gradient.
+// thread <-> one channel (a warp reads 128 contiguous bytes of a token), blockIdx.y <-> 256-channel
+// slab, work unit = (line along n2, segment of PEG_SEG positions); a 3-wide register window slides
+// over the 9 neighbour lines. REVERSE = transposed conv for the input gradient.
 // =============================================================================================
+constexpr int PEG_SEG = 8;
+
 template <bool REVERSE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 peg_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, int B, int n0, int n1, int n2,
-                int dim) {
-    const int c2 = threadIdx.x;                                   // channel pair
-    const long long line = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-    const long long nlines = (long long)B * n0 * n1;
-    if (line >= nlines || c2 * 2 >= dim) return;
+                int dim, int nseg) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    const long long unit = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    const long long nunits = (long long)B * n0 * n1 * nseg;
+    if (unit >= nunits || c >= dim) return;
+    const int seg = (int)(unit % nseg);
+    const long long line = unit / nseg;
     const int a1 = (int)(line % n1);
     const int a0 = (int)((line / n1) % n0);
     const int bb = (int)(line / ((long long)n1 * n0));
-    // weights (dim,1,3,3,3): w[c][k0][k1][k2]
-    float2 wt[27];
+    const int p_begin = seg * PEG_SEG, p_end = min(n2, p_begin + PEG_SEG);
+    float wt[27];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-        const int tt = REVERSE ? (26 - t) : t;    // flipped taps for the transposed conv
-        wt[t] = make_float2(__ldg(w + (long long)(2 * c2) * 27 + tt), __ldg(w + (long long)(2 * c2 + 1) * 27 + tt));
-    }
-    const float2 bias = (!REVERSE && b) ? make_float2(__ldg(b + 2 * c2), __ldg(b + 2 * c2 + 1)) : make_float2(0.f, 0.f);
+    for (int t = 0; t < 27; ++t) wt[t] = __ldg(w + (long long)c * 27 + (REVERSE ? 26 - t : t));
+    const float bias = (!REVERSE && b) ? __ldg(b + c) : 0.f;
     // neighbour line pointers (nullptr = zero padding). forward: a0 offsets -2,-1,0; reverse: 0,+1,+2
-    const float2* lines[9];
+    const float* lines[9];
 #pragma unroll
     for (int k0 = 0; k0 < 3; ++k0)
 #pragma unroll
@@ -288,103 +290,85 @@ peg_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
             const int q0 = REVERSE ? a0 + k0 : a0 + k0 - 2;
             const int q1 = a1 + k1 - 1;
             const bool ok = q0 >= 0 && q0 < n0 && q1 >= 0 && q1 < n1;
-            lines[k0 * 3 + k1] = ok ? reinterpret_cast<const float2*>(
-                                          x + ((((long long)bb * n0 + q0) * n1 + q1) * n2) * dim) + c2
-                                    : nullptr;
+            lines[k0 * 3 + k1] = ok ? x + ((((long long)bb * n0 + q0) * n1 + q1) * n2) * dim + c : nullptr;
         }
-    const int stride2 = dim / 2;                                   // float2 stride between a2 positions
-    float2 win[9][3];
+    float win[9][3];
 #pragma unroll
     for (int l = 0; l < 9; ++l) {
-        win[l][0] = make_float2(0.f, 0.f);
-        win[l][1] = lines[l] ? lines[l][0] : make_float2(0.f, 0.f);
+        win[l][0] = (lines[l] && p_begin > 0) ? lines[l][(long long)(p_begin - 1) * dim] : 0.f;
+        win[l][1] = lines[l] ? lines[l][(long long)p_begin * dim] : 0.f;
     }
-    const int centre = REVERSE ? 1 : 7;                            // (k0,k1) of the centre line: a0+0, a1+0
-    float2* yo = reinterpret_cast<float2*>(y + ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim) + c2;
-    for (int a2 = 0; a2 < n2; ++a2) {
+    constexpr int centre = REVERSE ? 1 : 7;                     // (k0,k1) of the centre line
+    const long long obase = ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim + c;
+    for (int a2 = p_begin; a2 < p_end; ++a2) {
 #pragma unroll
         for (int l = 0; l < 9; ++l)
-            win[l][2] = (lines[l] && a2 + 1 < n2) ? lines[l][(long long)(a2 + 1) * stride2]
-                                                  : make_float2(0.f, 0.f);
-        float2 acc = make_float2(bias.x + win[centre][1].x, bias.y + win[centre][1].y);   // + residual
+            win[l][2] = (lines[l] && a2 + 1 < n2) ? lines[l][(long long)(a2 + 1) * dim] : 0.f;
+        float acc = bias + win[centre][1];                      // + residual
 #pragma unroll
         for (int l = 0; l < 9; ++l)
 #pragma unroll
-            for (int k2 = 0; k2 < 3; ++k2) {
-                acc.x = fmaf(wt[l * 3 + k2].x, win[l][k2].x, acc.x);
-                acc.y = fmaf(wt[l * 3 + k2].y, win[l][k2].y, acc.y);
-            }
-        yo[(long long)a2 * stride2] = acc;
-        if (y_bf16)
-            reinterpret_cast<uint32_t*>(y_bf16 + ((((long long)bb * n0 + a0) * n1 + a1) * n2 + a2) * dim)[c2] =
-                pack_bf16x2(acc.x, acc.y);
+            for (int k2 = 0; k2 < 3; ++k2) acc = fmaf(wt[l * 3 + k2], win[l][k2], acc);
+        y[obase + (long long)a2 * dim] = acc;
+        if (y_bf16) y_bf16[obase + (long long)a2 * dim] = __float2bfloat16(acc);
 #pragma unroll
         for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
     }
 }
 
-// dw[c][tap] += sum_pos dy[pos] x[pos + off(tap)], db[c] += sum dy. Each thread.y walks lines with
-// a grid stride so the final atomics are amortised.
-__global__ void __launch_bounds__(256)
+// dw[c][tap] += sum_pos dy[pos] x[pos + off(tap)], db[c] += sum dy. Each thread walks units with a
+// grid stride so the final atomics are amortised.
+__global__ void __launch_bounds__(256, 2)
 peg_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
-                 float* __restrict__ db, int B, int n0, int n1, int n2, int dim) {
-    const int c2 = threadIdx.x;
-    if (c2 * 2 >= dim) return;
-    const long long nlines = (long long)B * n0 * n1;
-    const int stride2 = dim / 2;
-    float2 acc[27];
+                 float* __restrict__ db, int B, int n0, int n1, int n2, int dim, int nseg) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= dim) return;
+    const long long nunits = (long long)B * n0 * n1 * nseg;
+    float acc[27];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) acc[t] = make_float2(0.f, 0.f);
-    float2 accb = make_float2(0.f, 0.f);
-    for (long long line = (long long)blockIdx.x * blockDim.y + threadIdx.y; line < nlines;
-         line += (long long)gridDim.x * blockDim.y) {
+    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+    float accb = 0.f;
+    for (long long unit = (long long)blockIdx.x * blockDim.y + threadIdx.y; unit < nunits;
+         unit += (long long)gridDim.x * blockDim.y) {
+        const int seg = (int)(unit % nseg);
+        const long long line = unit / nseg;
         const int a1 = (int)(line % n1);
         const int a0 = (int)((line / n1) % n0);
         const int bb = (int)(line / ((long long)n1 * n0));
-        const float2* lines[9];
+        const int p_begin = seg * PEG_SEG, p_end = min(n2, p_begin + PEG_SEG);
+        const float* lines[9];
 #pragma unroll
         for (int k0 = 0; k0 < 3; ++k0)
 #pragma unroll
             for (int k1 = 0; k1 < 3; ++k1) {
                 const int q0 = a0 + k0 - 2, q1 = a1 + k1 - 1;
                 const bool ok = q0 >= 0 && q1 >= 0 && q1 < n1;
-                lines[k0 * 3 + k1] = ok ? reinterpret_cast<const float2*>(
-                                              x + ((((long long)bb * n0 + q0) * n1 + q1) * n2) * dim) + c2
-                                        : nullptr;
+                lines[k0 * 3 + k1] = ok ? x + ((((long long)bb * n0 + q0) * n1 + q1) * n2) * dim + c : nullptr;
             }
-        const float2* dyl = reinterpret_cast<const float2*>(
-                                dy + ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim) + c2;
-        float2 win[9][3];
+        const float* dyl = dy + ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim + c;
+        float win[9][3];
 #pragma unroll
         for (int l = 0; l < 9; ++l) {
-            win[l][0] = make_float2(0.f, 0.f);
-            win[l][1] = lines[l] ? lines[l][0] : make_float2(0.f, 0.f);
+            win[l][0] = (lines[l] && p_begin > 0) ? lines[l][(long long)(p_begin - 1) * dim] : 0.f;
+            win[l][1] = lines[l] ? lines[l][(long long)p_begin * dim] : 0.f;
         }
-        for (int a2 = 0; a2 < n2; ++a2) {
+        for (int a2 = p_begin; a2 < p_end; ++a2) {
 #pragma unroll
             for (int l = 0; l < 9; ++l)
-                win[l][2] = (lines[l] && a2 + 1 < n2) ? lines[l][(long long)(a2 + 1) * stride2]
-                                                      : make_float2(0.f, 0.f);
-            const float2 g = dyl[(long long)a2 * stride2];
-            accb.x += g.x; accb.y += g.y;
+                win[l][2] = (lines[l] && a2 + 1 < n2) ? lines[l][(long long)(a2 + 1) * dim] : 0.f;
+            const float g = dyl[(long long)a2 * dim];
+            accb += g;
 #pragma unroll
             for (int l = 0; l < 9; ++l)
 #pragma unroll
-                for (int k2 = 0; k2 < 3; ++k2) {
-                    acc[l * 3 + k2].x = fmaf(g.x, win[l][k2].x, acc[l * 3 + k2].x);
-                    acc[l * 3 + k2].y = fmaf(g.y, win[l][k2].y, acc[l * 3 + k2].y);
-                }
+                for (int k2 = 0; k2 < 3; ++k2) acc[l * 3 + k2] = fmaf(g, win[l][k2], acc[l * 3 + k2]);
 #pragma unroll
             for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
         }
     }
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-        atomicAdd(dw + (long long)(2 * c2) * 27 + t, acc[t].x);
-        atomicAdd(dw + (long long)(2 * c2 + 1) * 27 + t, acc[t].y);
-    }
-    atomicAdd(db + 2 * c2, accb.x);
-    atomicAdd(db + 2 * c2 + 1, accb.y);
+    for (int t = 0; t < 27; ++t) atomicAdd(dw + (long long)c * 27 + t, acc[t]);
+    atomicAdd(db + c, accb);
 }
 
 // =============================================================================================
@@ -555,26 +539,26 @@ extern "C" int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
     return CTK_ERR_SHAPE;
 }
 
-static int peg_block(int dim, dim3* block) {
-    const int tx = dim / 2;
-    if (dim % 2 != 0 || tx > 256) return -1;
-    int ty = 256 / tx;
-    if (ty < 1) ty = 1;
-    *block = dim3(tx, ty);
-    return 0;
+static void peg_geometry(int dim, dim3* block, int* slabs) {
+    const int tx = dim >= 256 ? 256 : ((dim + 31) / 32) * 32;     // channels per CTA (threads.x)
+    *slabs = (dim + tx - 1) / tx;
+    *block = dim3(tx, 256 / tx > 0 ? 256 / tx : 1);
 }
 
 extern "C" int ctk_peg_fwd(const float* x, const float* w, const float* b, float* y, int B, int n0,
                            int n1, int n2, int dim, void* stream_) {
     int rc = ctk_check_device();
     if (rc) return rc;
-    CTK_REQUIRE(x && w && b && y && B > 0 && n0 > 0 && n1 > 0 && n2 > 0, CTK_ERR_SHAPE, "peg_fwd: bad args");
-    dim3 block;
-    CTK_REQUIRE(peg_block(dim, &block) == 0, CTK_ERR_SHAPE, "peg: dim %d must be even and <= 512", dim);
+    CTK_REQUIRE(x && w && b && y && B > 0 && n0 > 0 && n1 > 0 && n2 > 0 && dim > 0, CTK_ERR_SHAPE, "peg_fwd: bad args");
     CTK_REQUIRE(x != y, CTK_ERR_SHAPE, "peg_fwd: in-place not supported");
+    dim3 block;
+    int slabs;
+    peg_geometry(dim, &block, &slabs);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    const long long nlines = (long long)B * n0 * n1;
-    peg_conv_kernel<false><<<(unsigned)((nlines + block.y - 1) / block.y), block, 0, s>>>(x, w, b, y, nullptr, B, n0, n1, n2, dim);
+    const int nseg = (n2 + PEG_SEG - 1) / PEG_SEG;
+    const long long nunits = (long long)B * n0 * n1 * nseg;
+    peg_conv_kernel<false><<<dim3((unsigned)((nunits + block.y - 1) / block.y), slabs), block, 0, s>>>(
+        x, w, b, y, nullptr, B, n0, n1, n2, dim, nseg);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
@@ -583,19 +567,22 @@ extern "C" int ctk_peg_bwd(const float* dy, const float* x, const float* w, floa
                            float* dw, float* db, int B, int n0, int n1, int n2, int dim, void* stream_) {
     int rc = ctk_check_device();
     if (rc) return rc;
-    CTK_REQUIRE(dy && x && w && dx && dw && db && B > 0, CTK_ERR_SHAPE, "peg_bwd: bad args");
-    dim3 block;
-    CTK_REQUIRE(peg_block(dim, &block) == 0, CTK_ERR_SHAPE, "peg: dim %d must be even and <= 512", dim);
+    CTK_REQUIRE(dy && x && w && dx && dw && db && B > 0 && dim > 0, CTK_ERR_SHAPE, "peg_bwd: bad args");
     CTK_REQUIRE(dy != dx, CTK_ERR_SHAPE, "peg_bwd: in-place not supported");
+    dim3 block;
+    int slabs;
+    peg_geometry(dim, &block, &slabs);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    const long long nlines = (long long)B * n0 * n1;
-    peg_conv_kernel<true><<<(unsigned)((nlines + block.y - 1) / block.y), block, 0, s>>>(
-        dy, w, nullptr, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), B, n0, n1, n2, dim);
+    const int nseg = (n2 + PEG_SEG - 1) / PEG_SEG;
+    const long long nunits = (long long)B * n0 * n1 * nseg;
+    const long long blocks_full = (nunits + block.y - 1) / block.y;
+    peg_conv_kernel<true><<<dim3((unsigned)blocks_full, slabs), block, 0, s>>>(
+        dy, w, nullptr, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), B, n0, n1, n2, dim, nseg);
     CTK_LAUNCH_CHECK();
-    long long blocks = (nlines + block.y - 1) / block.y;
-    const long long cap = (long long)ctk_num_sms() * 2;
+    long long blocks = blocks_full;
+    const long long cap = (long long)ctk_num_sms() * 6 / slabs;
     if (blocks > cap) blocks = cap;
-    peg_wgrad_kernel<<<(unsigned)blocks, block, 0, s>>>(dy, x, dw, db, B, n0, n1, n2, dim);
+    peg_wgrad_kernel<<<dim3((unsigned)blocks, slabs), block, 0, s>>>(dy, x, dw, db, B, n0, n1, n2, dim, nseg);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
