@@ -84,31 +84,34 @@ __global__ void cpb_dz1_kernel(const float* __restrict__ dtable, const float* __
     }
 }
 
-// dw2[h][c] = sum_n dtable[h][n] h1[n][c];  db2[h] = sum_n dtable[h][n]     grid (heads), block dim threads
+// dw2[h][c] += sum_{n in chunk} dtable[h][n] h1[n][c];  db2[h] += sum dtable[h][n]    grid (heads, chunks)
 __global__ void cpb_dw2_kernel(const float* __restrict__ dtable, const float* __restrict__ h1,
-                               float* __restrict__ dw2, float* __restrict__ db2, int n_off, int dim) {
+                               float* __restrict__ dw2, float* __restrict__ db2, int n_off, int dim, int per) {
     const int h = blockIdx.x;
+    const int n0 = blockIdx.y * per, n1 = min(n_off, n0 + per);
     for (int c = threadIdx.x; c < dim; c += blockDim.x) {
         float a = 0.f;
-        for (int n = 0; n < n_off; ++n) a = fmaf(dtable[(long long)h * n_off + n], h1[(long long)n * dim + c], a);
-        dw2[(long long)h * dim + c] = a;
+        for (int n = n0; n < n1; ++n) a = fmaf(dtable[(long long)h * n_off + n], h1[(long long)n * dim + c], a);
+        atomicAdd(dw2 + (long long)h * dim + c, a);
     }
     if (threadIdx.x < 32) {
         float a = 0.f;
-        for (int n = threadIdx.x; n < n_off; n += 32) a += dtable[(long long)h * n_off + n];
+        for (int n = n0 + threadIdx.x; n < n1; n += 32) a += dtable[(long long)h * n_off + n];
         a = warp_sum(a);
-        if (threadIdx.x == 0) db2[h] = a;
+        if (threadIdx.x == 0) atomicAdd(db2 + h, a);
     }
 }
 
 // column sums of dz [n_off, dim] (-> db); optionally also dw0[c][0..1] = sum_n dz[n][c] * in[n][.]
+// grid (dim / 128, chunks), atomics into pre-zeroed outputs
 __global__ void cpb_colred_kernel(const float* __restrict__ dz, float* __restrict__ db,
-                                  float* __restrict__ dw0, int n_off, int dim, int gh, int gw) {
+                                  float* __restrict__ dw0, int n_off, int dim, int gh, int gw, int per) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= dim) return;
+    const int n0 = blockIdx.y * per, n1 = min(n_off, n0 + per);
     const int ww = 2 * gw - 1;
     float s = 0.f, sy = 0.f, sx = 0.f;
-    for (int n = 0; n < n_off; ++n) {
+    for (int n = n0; n < n1; ++n) {
         const float v = dz[(long long)n * dim + c];
         s += v;
         if (dw0) {
@@ -116,8 +119,8 @@ __global__ void cpb_colred_kernel(const float* __restrict__ dz, float* __restric
             sx = fmaf(v, slog(n % ww - (gw - 1)), sx);
         }
     }
-    db[c] = s;
-    if (dw0) { dw0[2 * c] = sy; dw0[2 * c + 1] = sx; }
+    atomicAdd(db + c, s);
+    if (dw0) { atomicAdd(dw0 + 2 * c, sy); atomicAdd(dw0 + 2 * c + 1, sx); }
 }
 
 }  // namespace
@@ -152,19 +155,26 @@ extern "C" int ctk_cpb_bwd(const float* dtable, const float* w0, const float* w1
     const int n_off = (2 * gh - 1) * (2 * gw - 1);
     float* dz1 = ws;
     float* dz0 = ws + (size_t)n_off * dim;
-    cpb_dw2_kernel<<<heads, 256, 0, s>>>(dtable, h1, dw2, db2, n_off, dim);
+    const int chunks = 32;
+    const int per = (n_off + chunks - 1) / chunks;
+    CTK_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)heads * dim, s));
+    CTK_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * heads, s));
+    CTK_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * dim, s));
+    CTK_CUDA(cudaMemsetAsync(db0, 0, sizeof(float) * dim, s));
+    CTK_CUDA(cudaMemsetAsync(dw0, 0, sizeof(float) * 2 * dim, s));
+    cpb_dw2_kernel<<<dim3(heads, chunks), 256, 0, s>>>(dtable, h1, dw2, db2, n_off, dim, per);
     CTK_LAUNCH_CHECK();
     cpb_dz1_kernel<<<n_off, 128, 0, s>>>(dtable, w2, h1, dz1, n_off, dim, heads);
     CTK_LAUNCH_CHECK();
     // dW1[o][i] = sum_n dz1[n][o] h0[n][i]
     cpb_gemm_kernel<2><<<dim3((dim + 63) / 64, (dim + 63) / 64), 256, 0, s>>>(dz1, h0, dw1, nullptr, nullptr, dim, dim, n_off, dim, dim);
     CTK_LAUNCH_CHECK();
-    cpb_colred_kernel<<<(dim + 127) / 128, 128, 0, s>>>(dz1, db1, nullptr, n_off, dim, gh, gw);
+    cpb_colred_kernel<<<dim3((dim + 127) / 128, chunks), 128, 0, s>>>(dz1, db1, nullptr, n_off, dim, gh, gw, per);
     CTK_LAUNCH_CHECK();
     // dz0 = (dz1 W1) * lrelu'(h0)
     cpb_gemm_kernel<1><<<dim3((dim + 63) / 64, (n_off + 63) / 64), 256, 0, s>>>(dz1, w1, dz0, nullptr, h0, n_off, dim, dim, dim, dim);
     CTK_LAUNCH_CHECK();
-    cpb_colred_kernel<<<(dim + 127) / 128, 128, 0, s>>>(dz0, db0, dw0, n_off, dim, gh, gw);
+    cpb_colred_kernel<<<dim3((dim + 127) / 128, chunks), 128, 0, s>>>(dz0, db0, dw0, n_off, dim, gh, gw, per);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }

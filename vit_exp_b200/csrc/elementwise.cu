@@ -256,119 +256,154 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
 
 // =============================================================================================
 // PEG: depthwise causal 3x3x3 conv + bias + residual on [B, n0, n1, n2, dim] (attention.py:62-90,443)
-// thread <-> one channel (a warp reads 128 contiguous bytes of a token), blockIdx.y <-> 256-channel
-// slab, work unit = (line along n2, segment of PEG_SEG positions); a 3-wide register window slides
-// over the 9 neighbour lines. REVERSE = transposed conv for the input gradient.
+//
+// CTA = (batch b, tile of PEG_T1 rows along axis 1, slab of 32 channels). It walks axis 0 keeping a
+// ring of 3 input planes ((PEG_T1+2) x (n2+2) x 32 floats, zero halo) in shared memory, so every
+// input element is fetched from HBM/L2 once per CTA (1.25x halo overhead) instead of 9-27 times.
+// lane <-> channel (a warp reads 128 contiguous bytes per token, bank-conflict free in smem),
+// warp <-> output row; a 3-wide register window slides along axis 2.
+// MODE 0: y = conv(x) + b + x          MODE 1: dx = conv^T(dy) + dy (flipped taps, planes a0..a0+2)
+// MODE 2: dw, db accumulation (x planes in smem, dy read directly)
 // =============================================================================================
-constexpr int PEG_SEG = 8;
+constexpr int PEG_T1 = 8;
+constexpr int PEG_CS = 32;
 
-template <bool REVERSE>
-__global__ void __launch_bounds__(256, 2)
-peg_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, int B, int n0, int n1, int n2,
-                int dim, int nseg) {
-    const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    const long long unit = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-    const long long nunits = (long long)B * n0 * n1 * nseg;
-    if (unit >= nunits || c >= dim) return;
-    const int seg = (int)(unit % nseg);
-    const long long line = unit / nseg;
-    const int a1 = (int)(line % n1);
-    const int a0 = (int)((line / n1) % n0);
-    const int bb = (int)(line / ((long long)n1 * n0));
-    const int p_begin = seg * PEG_SEG, p_end = min(n2, p_begin + PEG_SEG);
-    float wt[27];
-#pragma unroll
-    for (int t = 0; t < 27; ++t) wt[t] = __ldg(w + (long long)c * 27 + (REVERSE ? 26 - t : t));
-    const float bias = (!REVERSE && b) ? __ldg(b + c) : 0.f;
-    // neighbour line pointers (nullptr = zero padding). forward: a0 offsets -2,-1,0; reverse: 0,+1,+2
-    const float* lines[9];
-#pragma unroll
-    for (int k0 = 0; k0 < 3; ++k0)
-#pragma unroll
-        for (int k1 = 0; k1 < 3; ++k1) {
-            const int q0 = REVERSE ? a0 + k0 : a0 + k0 - 2;
-            const int q1 = a1 + k1 - 1;
-            const bool ok = q0 >= 0 && q0 < n0 && q1 >= 0 && q1 < n1;
-            lines[k0 * 3 + k1] = ok ? x + ((((long long)bb * n0 + q0) * n1 + q1) * n2) * dim + c : nullptr;
+__device__ __forceinline__ void cp_async16_ew(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// load plane q (axis 0 index) rows [r_lo-1, r_lo+PEG_T1+1) into `dst`; invalid planes/rows -> zeros
+__device__ __forceinline__ void peg_load_plane(float* dst, const float* __restrict__ x, int bb, int q, int r_lo,
+                                               int c0, int n0, int n1, int n2, int dim, int tid) {
+    const int W2 = n2 + 2;
+    const bool plane_ok = q >= 0 && q < n0;
+    const int nchunk = (PEG_T1 + 2) * n2 * (PEG_CS / 4);        // 16-byte chunks (4 channels)
+    for (int i = tid; i < nchunk; i += 256) {
+        const int ch4 = i % (PEG_CS / 4);
+        const int pos = (i / (PEG_CS / 4)) % n2;
+        const int rr = i / ((PEG_CS / 4) * n2);                  // 0 .. PEG_T1+1
+        const int a1 = r_lo - 1 + rr;
+        float* d = dst + ((rr * W2 + pos + 1) * PEG_CS + ch4 * 4);
+        if (plane_ok && a1 >= 0 && a1 < n1) {
+            const float* src = x + ((((long long)bb * n0 + q) * n1 + a1) * n2 + pos) * dim + c0 + ch4 * 4;
+            cp_async16_ew(smem_u32(d), src);
+        } else {
+            *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    float win[9][3];
-#pragma unroll
-    for (int l = 0; l < 9; ++l) {
-        win[l][0] = (lines[l] && p_begin > 0) ? lines[l][(long long)(p_begin - 1) * dim] : 0.f;
-        win[l][1] = lines[l] ? lines[l][(long long)p_begin * dim] : 0.f;
-    }
-    constexpr int centre = REVERSE ? 1 : 7;                     // (k0,k1) of the centre line
-    const long long obase = ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim + c;
-    for (int a2 = p_begin; a2 < p_end; ++a2) {
-#pragma unroll
-        for (int l = 0; l < 9; ++l)
-            win[l][2] = (lines[l] && a2 + 1 < n2) ? lines[l][(long long)(a2 + 1) * dim] : 0.f;
-        float acc = bias + win[centre][1];                      // + residual
-#pragma unroll
-        for (int l = 0; l < 9; ++l)
-#pragma unroll
-            for (int k2 = 0; k2 < 3; ++k2) acc = fmaf(wt[l * 3 + k2], win[l][k2], acc);
-        y[obase + (long long)a2 * dim] = acc;
-        if (y_bf16) y_bf16[obase + (long long)a2 * dim] = __float2bfloat16(acc);
-#pragma unroll
-        for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
     }
 }
 
-// dw[c][tap] += sum_pos dy[pos] x[pos + off(tap)], db[c] += sum dy. Each thread walks units with a
-// grid stride so the final atomics are amortised.
+template <int MODE>
 __global__ void __launch_bounds__(256, 2)
-peg_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
-                 float* __restrict__ db, int B, int n0, int n1, int n2, int dim, int nseg) {
-    const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    if (c >= dim) return;
-    const long long nunits = (long long)B * n0 * n1 * nseg;
-    float acc[27];
+peg_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                const float* __restrict__ dy, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
+                float* __restrict__ dw, float* __restrict__ db, int B, int n0, int n1, int n2, int dim) {
+    extern __shared__ __align__(16) float psm[];
+    const int W2 = n2 + 2;
+    const int plane_floats = (PEG_T1 + 2) * W2 * PEG_CS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
+    const int slab = blockIdx.y;
+    const int bb = blockIdx.x / tiles1;
+    const int r_lo = (blockIdx.x % tiles1) * PEG_T1;
+    const int c0 = slab * PEG_CS;
+    const int c = c0 + lane;
+    const int a1 = r_lo + warp;                                  // this warp's output row
+    const bool row_ok = a1 < n1;
+    constexpr bool REV = MODE == 1;
+    constexpr int shift = REV ? 0 : -2;                          // planes a0+shift .. a0+shift+2
+
+    // zero the a2 halo columns of all three slots once (loads never touch them)
+    for (int i = tid; i < 3 * (PEG_T1 + 2) * 2 * PEG_CS; i += 256) {
+        const int ch = i % PEG_CS;
+        const int side = (i / PEG_CS) % 2;
+        const int rr = (i / (2 * PEG_CS)) % (PEG_T1 + 2);
+        const int sl = i / (2 * PEG_CS * (PEG_T1 + 2));
+        psm[sl * plane_floats + (rr * W2 + (side ? W2 - 1 : 0)) * PEG_CS + ch] = 0.f;
+    }
+    float wt[27];
+    if (MODE != 2) {
 #pragma unroll
-    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
-    float accb = 0.f;
-    for (long long unit = (long long)blockIdx.x * blockDim.y + threadIdx.y; unit < nunits;
-         unit += (long long)gridDim.x * blockDim.y) {
-        const int seg = (int)(unit % nseg);
-        const long long line = unit / nseg;
-        const int a1 = (int)(line % n1);
-        const int a0 = (int)((line / n1) % n0);
-        const int bb = (int)(line / ((long long)n1 * n0));
-        const int p_begin = seg * PEG_SEG, p_end = min(n2, p_begin + PEG_SEG);
-        const float* lines[9];
+        for (int t = 0; t < 27; ++t) wt[t] = __ldg(w + (long long)c * 27 + (REV ? 26 - t : t));
+    }
+    const float bias = (MODE == 0 && b) ? __ldg(b + c) : 0.f;
+    float acc_w[27];
+    float acc_b = 0.f;
+    if (MODE == 2) {
 #pragma unroll
-        for (int k0 = 0; k0 < 3; ++k0)
-#pragma unroll
-            for (int k1 = 0; k1 < 3; ++k1) {
-                const int q0 = a0 + k0 - 2, q1 = a1 + k1 - 1;
-                const bool ok = q0 >= 0 && q1 >= 0 && q1 < n1;
-                lines[k0 * 3 + k1] = ok ? x + ((((long long)bb * n0 + q0) * n1 + q1) * n2) * dim + c : nullptr;
+        for (int t = 0; t < 27; ++t) acc_w[t] = 0.f;
+    }
+    const float* src = (MODE == 1) ? dy : x;                     // tensor staged in shared memory
+
+    for (int a0 = 0; a0 < n0; ++a0) {
+        __syncthreads();                                          // previous step finished with the ring
+        if (a0 == 0) {
+            for (int k = 0; k < 3; ++k) {
+                const int q = shift + k;
+                peg_load_plane(psm + (((q % 3) + 3) % 3) * plane_floats, src, bb, q, r_lo, c0, n0, n1, n2, dim, tid);
             }
-        const float* dyl = dy + ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim + c;
+        } else {
+            const int q = a0 + shift + 2;
+            peg_load_plane(psm + (((q % 3) + 3) % 3) * plane_floats, src, bb, q, r_lo, c0, n0, n1, n2, dim, tid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (!row_ok) continue;
+        // smem line (k0, k1): plane a0+shift+k0, local row warp + k1   (local row 0 = a1 - 1)
+        const float* ln[9];
+#pragma unroll
+        for (int k0 = 0; k0 < 3; ++k0) {
+            const int q = a0 + shift + k0;
+            const float* pl = psm + (((q % 3) + 3) % 3) * plane_floats;
+#pragma unroll
+            for (int k1 = 0; k1 < 3; ++k1) ln[k0 * 3 + k1] = pl + ((warp + k1) * W2) * PEG_CS + lane;
+        }
         float win[9][3];
 #pragma unroll
-        for (int l = 0; l < 9; ++l) {
-            win[l][0] = (lines[l] && p_begin > 0) ? lines[l][(long long)(p_begin - 1) * dim] : 0.f;
-            win[l][1] = lines[l] ? lines[l][(long long)p_begin * dim] : 0.f;
-        }
-        for (int a2 = p_begin; a2 < p_end; ++a2) {
+        for (int l = 0; l < 9; ++l) { win[l][0] = ln[l][0]; win[l][1] = ln[l][PEG_CS]; }
+        constexpr int centre = REV ? 1 : 7;                      // (k0,k1) of the un-shifted line
+        const long long obase = ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim + c;
+        for (int a2 = 0; a2 < n2; ++a2) {
 #pragma unroll
-            for (int l = 0; l < 9; ++l)
-                win[l][2] = (lines[l] && a2 + 1 < n2) ? lines[l][(long long)(a2 + 1) * dim] : 0.f;
-            const float g = dyl[(long long)a2 * dim];
-            accb += g;
+            for (int l = 0; l < 9; ++l) win[l][2] = ln[l][(a2 + 2) * PEG_CS];
+            if (MODE == 2) {
+                const float g = dy[obase + (long long)a2 * dim];
+                acc_b += g;
 #pragma unroll
-            for (int l = 0; l < 9; ++l)
+                for (int l = 0; l < 9; ++l)
 #pragma unroll
-                for (int k2 = 0; k2 < 3; ++k2) acc[l * 3 + k2] = fmaf(g, win[l][k2], acc[l * 3 + k2]);
+                    for (int k2 = 0; k2 < 3; ++k2) acc_w[l * 3 + k2] = fmaf(g, win[l][k2], acc_w[l * 3 + k2]);
+            } else {
+                float acc = bias + win[centre][1];               // + residual
+#pragma unroll
+                for (int l = 0; l < 9; ++l)
+#pragma unroll
+                    for (int k2 = 0; k2 < 3; ++k2) acc = fmaf(wt[l * 3 + k2], win[l][k2], acc);
+                y[obase + (long long)a2 * dim] = acc;
+                if (y_bf16) y_bf16[obase + (long long)a2 * dim] = __float2bfloat16(acc);
+            }
 #pragma unroll
             for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
         }
     }
+    if (MODE == 2) {
+        // reduce the 8 rows (warps) of the CTA through shared memory, then one atomic per (c, tap)
+        __syncthreads();
+        float* red = psm;                                        // [8][28][32]
 #pragma unroll
-    for (int t = 0; t < 27; ++t) atomicAdd(dw + (long long)c * 27 + t, acc[t]);
-    atomicAdd(db + c, accb);
+        for (int t = 0; t < 27; ++t) red[(warp * 28 + t) * 32 + lane] = row_ok ? acc_w[t] : 0.f;
+        red[(warp * 28 + 27) * 32 + lane] = row_ok ? acc_b : 0.f;
+        __syncthreads();
+        for (int i = tid; i < 28 * 32; i += 256) {
+            const int t = i / 32, l = i % 32;
+            float sacc = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) sacc += red[(ww * 28 + t) * 32 + l];
+            if (t < 27) atomicAdd(dw + (long long)(c0 + l) * 27 + t, sacc);
+            else atomicAdd(db + c0 + l, sacc);
+        }
+    }
 }
 
 // =============================================================================================
@@ -539,10 +574,19 @@ extern "C" int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
     return CTK_ERR_SHAPE;
 }
 
-static void peg_geometry(int dim, dim3* block, int* slabs) {
-    const int tx = dim >= 256 ? 256 : ((dim + 31) / 32) * 32;     // channels per CTA (threads.x)
-    *slabs = (dim + tx - 1) / tx;
-    *block = dim3(tx, 256 / tx > 0 ? 256 / tx : 1);
+static size_t peg_smem(int n2) { return (size_t)3 * (PEG_T1 + 2) * (n2 + 2) * PEG_CS * sizeof(float); }
+
+template <int MODE>
+static int peg_launch(const float* x, const float* w, const float* b, const float* dy, float* y, void* y_bf16,
+                      float* dw, float* db, int B, int n0, int n1, int n2, int dim, cudaStream_t s) {
+    const size_t sm = peg_smem(n2);
+    CTK_REQUIRE(sm <= 220 * 1024 && sm >= 8 * 28 * 32 * sizeof(float), CTK_ERR_SHAPE, "peg: axis-2 extent %d unsupported", n2);
+    CTK_CUDA(cudaFuncSetAttribute(peg_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
+    peg_tile_kernel<MODE><<<dim3(B * tiles1, dim / PEG_CS), 256, sm, s>>>(
+        x, w, b, dy, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), dw, db, B, n0, n1, n2, dim);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
 }
 
 extern "C" int ctk_peg_fwd(const float* x, const float* w, const float* b, float* y, int B, int n0,
@@ -550,17 +594,10 @@ extern "C" int ctk_peg_fwd(const float* x, const float* w, const float* b, float
     int rc = ctk_check_device();
     if (rc) return rc;
     CTK_REQUIRE(x && w && b && y && B > 0 && n0 > 0 && n1 > 0 && n2 > 0 && dim > 0, CTK_ERR_SHAPE, "peg_fwd: bad args");
+    CTK_REQUIRE(dim % PEG_CS == 0 && CTK_ALIGNED(x, 16), CTK_ERR_ALIGN, "peg: dim must be a multiple of 32, x 16-byte aligned");
     CTK_REQUIRE(x != y, CTK_ERR_SHAPE, "peg_fwd: in-place not supported");
-    dim3 block;
-    int slabs;
-    peg_geometry(dim, &block, &slabs);
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    const int nseg = (n2 + PEG_SEG - 1) / PEG_SEG;
-    const long long nunits = (long long)B * n0 * n1 * nseg;
-    peg_conv_kernel<false><<<dim3((unsigned)((nunits + block.y - 1) / block.y), slabs), block, 0, s>>>(
-        x, w, b, y, nullptr, B, n0, n1, n2, dim, nseg);
-    CTK_LAUNCH_CHECK();
-    return CTK_OK;
+    return peg_launch<0>(x, w, b, nullptr, y, nullptr, nullptr, nullptr, B, n0, n1, n2, dim,
+                         reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int ctk_peg_bwd(const float* dy, const float* x, const float* w, float* dx, void* dx_bf16,
@@ -568,23 +605,13 @@ extern "C" int ctk_peg_bwd(const float* dy, const float* x, const float* w, floa
     int rc = ctk_check_device();
     if (rc) return rc;
     CTK_REQUIRE(dy && x && w && dx && dw && db && B > 0 && dim > 0, CTK_ERR_SHAPE, "peg_bwd: bad args");
+    CTK_REQUIRE(dim % PEG_CS == 0 && CTK_ALIGNED(x, 16) && CTK_ALIGNED(dy, 16), CTK_ERR_ALIGN,
+                "peg: dim must be a multiple of 32, tensors 16-byte aligned");
     CTK_REQUIRE(dy != dx, CTK_ERR_SHAPE, "peg_bwd: in-place not supported");
-    dim3 block;
-    int slabs;
-    peg_geometry(dim, &block, &slabs);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    const int nseg = (n2 + PEG_SEG - 1) / PEG_SEG;
-    const long long nunits = (long long)B * n0 * n1 * nseg;
-    const long long blocks_full = (nunits + block.y - 1) / block.y;
-    peg_conv_kernel<true><<<dim3((unsigned)blocks_full, slabs), block, 0, s>>>(
-        dy, w, nullptr, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), B, n0, n1, n2, dim, nseg);
-    CTK_LAUNCH_CHECK();
-    long long blocks = blocks_full;
-    const long long cap = (long long)ctk_num_sms() * 6 / slabs;
-    if (blocks > cap) blocks = cap;
-    peg_wgrad_kernel<<<dim3((unsigned)blocks, slabs), block, 0, s>>>(dy, x, dw, db, B, n0, n1, n2, dim, nseg);
-    CTK_LAUNCH_CHECK();
-    return CTK_OK;
+    rc = peg_launch<1>(nullptr, w, nullptr, dy, dx, dx_bf16, nullptr, nullptr, B, n0, n1, n2, dim, s);
+    if (rc) return rc;
+    return peg_launch<2>(x, nullptr, nullptr, dy, nullptr, nullptr, dw, db, B, n0, n1, n2, dim, s);
 }
 
 extern "C" int ctk_l2norm_rows(const float* x, void* xn_bf16, float* xn_f32, long long rows, int dim,

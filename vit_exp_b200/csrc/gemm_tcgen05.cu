@@ -7,11 +7,16 @@
 // contraction runs over tokens. Both are fed straight to the tensor core through UMMA shared
 // memory descriptors; nothing is transposed in HBM.
 //
-// Roles per CTA (256 threads, 1 CTA / SM, grid = #SMs, static round-robin tile schedule):
-//   warp 0   : TMA producer (one elected lane)      4-stage smem ring, full/empty mbarriers
-//   warp 1   : MMA issuer   (one elected lane)      tcgen05.mma 128x256x16, 2 TMEM accumulators
-//   warp 2   : TMEM allocator (512 columns)
-//   warps 4-7: epilogue - tcgen05.ld 32 columns at a time, fused epilogue, direct global stores
+// Roles per CTA (384 threads, 1 CTA / SM, grid = #SMs, static round-robin tile schedule):
+//   warp 0    : TMA producer (one elected lane)      3-stage smem ring, full/empty mbarriers
+//   warp 1    : MMA issuer   (one elected lane)      tcgen05.mma 128x256x16, 2 TMEM accumulators
+//   warp 2    : TMEM allocator (512 columns)
+//   warps 4-11: epilogue. Warp e owns TMEM lanes 32*(e%4).. and tile columns 128*(e/4)..: it pulls 32
+//               columns at a time with tcgen05.ld, applies the fused epilogue, writes its 32x32 block
+//               into a swizzled shared-memory staging slot and hands it to the TMA engine
+//               (cp.async.bulk.tensor store) - global writes are full-line bursts and edge clipping is
+//               done by the tensor map. Epilogue inputs (residual stream, GEGLU pre-activations) come
+//               in the same way through TMA loads.
 //
 // Fused epilogues replace the elementwise passes the reference runs as separate ATen kernels
 // (attention.py:45-58 GEGLU, :158-162 qk l2norm+scale, :443-450 residual adds).
@@ -25,12 +30,16 @@ constexpr int BM = 128;          // UMMA M (cta_group::1: TMEM lane == output ro
 constexpr int BN = 256;          // UMMA N
 constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NTHREADS = 256;
+constexpr int NEPI = 8;                // epilogue warps
+constexpr int SLOT_BYTES = 2048;       // one 32x32 bf16 block; an fp32 block takes two slots
+constexpr int SLOTS_PER_WARP = 4;
+constexpr int STAGING_BYTES = NEPI * SLOTS_PER_WARP * SLOT_BYTES;   // 64 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 32 * (4 + NEPI);
 
 struct EpiParams {
     void* C;
@@ -47,30 +56,6 @@ struct EpiParams {
     int i0, i1;
 };
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        d4[i] = u;
-    }
-}
-__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v)[32]) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint4 u = s4[i];
-        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
-               d = unpack_bf16x2(u.w);
-        v[8 * i + 0] = a.x; v[8 * i + 1] = a.y; v[8 * i + 2] = b.x; v[8 * i + 3] = b.y;
-        v[8 * i + 4] = c.x; v[8 * i + 5] = c.y; v[8 * i + 6] = d.x; v[8 * i + 7] = d.y;
-    }
-}
-
 __device__ __forceinline__ void ld_acc(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     tc_ld_32x32(taddr, r);
@@ -79,81 +64,205 @@ __device__ __forceinline__ void ld_acc(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Epilogue for one 128x256 accumulator: `row` is this thread's global output row, `t_row` the
-// TMEM address of (its lane, column 0 of the accumulator), `n0` the tile's first output column.
+// ---- staging slots: 32 rows, swizzled exactly like the TMA tensor maps expect -------------------
+// bf16 block: 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B  (16-byte chunk ^= (row >> 1) & 3)
+// fp32 block: 128-byte rows, CU_TENSOR_MAP_SWIZZLE_128B (16-byte chunk ^= row & 7)
+__device__ __forceinline__ void slot_write_bf16(uint8_t* slot, int row, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(slot + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = u;
+    }
+}
+__device__ __forceinline__ void slot_read_bf16(const uint8_t* slot, int row, float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 u = *reinterpret_cast<const uint4*>(slot + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        v[8 * j + 0] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = b.x; v[8 * j + 3] = b.y;
+        v[8 * j + 4] = c.x; v[8 * j + 5] = c.y; v[8 * j + 6] = d.x; v[8 * j + 7] = d.y;
+    }
+}
+__device__ __forceinline__ void slot_write_f32(uint8_t* slot, int row, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(slot + row * 128 + ((j ^ (row & 7)) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void slot_read_f32(const uint8_t* slot, int row, float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 f = *reinterpret_cast<const float4*>(slot + row * 128 + ((j ^ (row & 7)) << 4));
+        v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+    }
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Per-warp staging context. All lanes call the methods; lane 0 talks to the TMA engine.
+struct Stager {
+    uint8_t* base;        // SLOTS_PER_WARP * SLOT_BYTES, 1024-byte aligned
+    uint64_t* bar;        // this warp's mbarrier for TMA loads
+    uint32_t phase;
+    int lane;
+    // make the slots reusable: all earlier stores have finished reading shared memory
+    __device__ __forceinline__ void begin() {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+    }
+    // TMA-load `n` blocks (each `bytes`) described by (map, c0[i], c1) into slots `slot0 + i*step`
+    __device__ __forceinline__ void load2(const CUtensorMap* m, int slot_a, int ca, int slot_b, int cb, int row0,
+                                          int bytes_each, int nblocks) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, bytes_each * nblocks);
+            tma_load_2d(base + slot_a * SLOT_BYTES, m, bar, ca, row0);
+            if (nblocks > 1) tma_load_2d(base + slot_b * SLOT_BYTES, m, bar, cb, row0);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+    }
+    // publish the generic-proxy writes of the whole warp, then store slot -> global
+    __device__ __forceinline__ void fence() {
+        fence_async_smem();
+        __syncwarp();
+    }
+    __device__ __forceinline__ void store(const CUtensorMap* m, int slot, int c0, int row0) {
+        if (lane == 0) tma_store_2d(m, base + slot * SLOT_BYTES, c0, row0);
+    }
+    __device__ __forceinline__ void commit() {
+        if (lane == 0) bulk_commit();
+    }
+};
+
+// Epilogue of one epilogue warp for one 128x256 accumulator. `t_row` = TMEM address of (this warp's
+// lane quarter, accumulator column 0); `row0` = first global row of the warp's 32 rows; `hf` = which
+// half of the tile's columns this warp owns; n0 = first global column of the tile.
 template <int EPI>
-__device__ __forceinline__ void run_epilogue(const EpiParams& p, uint32_t t_row, long long row,
-                                             int n0, int M, int N) {
+__device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorMap* mc0, const CUtensorMap* mc1,
+                                             Stager& sg, uint32_t t_row, int row0, int hf, int n0, int M, int N) {
+    const int lane = sg.lane;
+    const long long row = (long long)row0 + lane;
     const bool row_ok = row < M;
-    if constexpr (EPI == CTK_EPI_BF16 || EPI == CTK_EPI_F32 || EPI == CTK_EPI_RESID_F32) {
+    if constexpr (EPI == CTK_EPI_BF16 || EPI == CTK_EPI_QKV) {
+        // bf16 out through mc0; QKV: per-head l2norm + scale on the first i0 columns, column offset i1
+        float* rn = reinterpret_cast<float*>(p.aux0);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            const int col = n0 + c;
-            if (col >= N) break;                       // warp-uniform
-            float v[32];
-            ld_acc(t_row + c, v);
-            if (!row_ok) continue;
-            if (p.bias) {
+        for (int cc = 0; cc < 128; cc += 64) {
+            sg.begin();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
-            }
-            if constexpr (EPI == CTK_EPI_BF16) {
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int c = hf * 128 + cc + h2 * 32;
+                const int col = n0 + c;
+                if (col >= N) break;                     // warp-uniform
+                float v[32];
+                ld_acc(t_row + c, v);
+                if constexpr (EPI == CTK_EPI_BF16) {
+                    if (p.bias) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-                store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col, v);
-            } else {
-                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) +
-                                                        row * p.ldc + col);
-                if constexpr (EPI == CTK_EPI_RESID_F32) {
-                    const float4* rs = reinterpret_cast<const float4*>(p.resid + row * p.ldr + col);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 r = rs[i];
-                        dst[i] = make_float4(v[4 * i] + r.x, v[4 * i + 1] + r.y,
-                                             v[4 * i + 2] + r.z, v[4 * i + 3] + r.w);
+                        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
                     }
-                } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                } else {
+                    if (col < p.i0) {
+                        float ss = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) ss += v[i] * v[i];
+                        const float rnorm = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = v[i] * rnorm * __ldg(p.vec0 + i) * p.alpha;
+                        if (row_ok) rn[row * p.ld_aux0 + (col + p.i1) / 32] = rnorm;
+                    }
                 }
+                slot_write_bf16(sg.base + h2 * SLOT_BYTES, lane, v);
+                sg.fence();
+                sg.store(mc0, h2, col + (EPI == CTK_EPI_QKV ? p.i1 : 0), row0);
             }
+            sg.commit();
+        }
+    } else if constexpr (EPI == CTK_EPI_F32 || EPI == CTK_EPI_RESID_F32) {
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 64) {
+            sg.begin();
+            const int cA = hf * 128 + cc, cB = cA + 32;
+            if (n0 + cA >= N) break;
+            const int nblk = (n0 + cB < N) ? 2 : 1;
+            if constexpr (EPI == CTK_EPI_RESID_F32) sg.load2(mc1, 0, n0 + cA, 2, n0 + cB, row0, 4096, nblk);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                if (h2 >= nblk) break;
+                const int c = cA + h2 * 32;
+                const int col = n0 + c;
+                uint8_t* slot = sg.base + h2 * 2 * SLOT_BYTES;
+                float v[32];
+                ld_acc(t_row + c, v);
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+                }
+                if constexpr (EPI == CTK_EPI_RESID_F32) {
+                    float r[32];
+                    slot_read_f32(slot, lane, r);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += r[i];
+                }
+                slot_write_f32(slot, lane, v);
+                sg.fence();
+                sg.store(mc0, h2 * 2, col, row0);
+            }
+            sg.commit();
         }
     } else if constexpr (EPI == CTK_EPI_GEGLU) {
-        // tile columns [0,128) = value rows, [128,256) = gate rows of 128 hidden units
-        // (weights were interleaved by ctk_pack_ff_w1). U (C) keeps the pre-activations for
-        // the backward pass, H (aux0) = gelu(gate) * value (attention.py:45-48).
+        // tile columns [0,128) = value rows, [128,256) = gate rows of 128 hidden units (weights were
+        // interleaved by ctk_pack_ff_w1). U (mc0) keeps the pre-activations for the backward pass,
+        // H (mc1) = gelu(gate) * value (attention.py:45-48). This warp: units hf*64 .. hf*64+63.
         const int tile = n0 / BN;
-        __nv_bfloat16* U = reinterpret_cast<__nv_bfloat16*>(p.C);
-        __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(p.aux0);
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int cc = 0; cc < 64; cc += 32) {
+            sg.begin();
+            const int c = hf * 64 + cc;
             float val[32], gate[32];
             ld_acc(t_row + c, val);
             ld_acc(t_row + 128 + c, gate);
-            if (!row_ok) continue;
-            store_bf16x32(U + row * p.ldc + n0 + c, val);
-            store_bf16x32(U + row * p.ldc + n0 + 128 + c, gate);
+            slot_write_bf16(sg.base, lane, val);
+            slot_write_bf16(sg.base + SLOT_BYTES, lane, gate);
 #pragma unroll
             for (int i = 0; i < 32; ++i) val[i] = gelu_erf(gate[i]) * val[i];
-            store_bf16x32(H + row * p.ld_aux0 + tile * 128 + c, val);
+            slot_write_bf16(sg.base + 2 * SLOT_BYTES, lane, val);
+            sg.fence();
+            sg.store(mc0, 0, n0 + c, row0);
+            sg.store(mc0, 1, n0 + 128 + c, row0);
+            sg.store(mc1, 2, tile * 128 + c, row0);
+            sg.commit();
         }
     } else if constexpr (EPI == CTK_EPI_GEGLU_BWD) {
-        // accumulator = dH for hidden units [n0, n0+256); aux0 = U (value|gate interleaved per
-        // 128 units); C = dU in the same interleaved layout.
-        const __nv_bfloat16* U = reinterpret_cast<const __nv_bfloat16*>(p.aux0);
-        __nv_bfloat16* dU = reinterpret_cast<__nv_bfloat16*>(p.C);
+        // accumulator = dH for hidden units [n0, n0+256); mc1 = U (value|gate interleaved per 128
+        // units); mc0 = dU in the same interleaved layout.
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int cc = 0; cc < 128; cc += 32) {
+            const int c = hf * 128 + cc;
             const int unit = n0 + c;
             if (unit >= N) break;
-            float dh[32];
+            sg.begin();
+            const int ucol = (unit / 128) * 256 + (unit % 128);
+            sg.load2(mc1, 0, ucol, 1, ucol + 128, row0, SLOT_BYTES, 2);
+            float dh[32], val[32], gate[32];
             ld_acc(t_row + c, dh);
-            if (!row_ok) continue;
-            const long long ucol = (long long)(unit / 128) * 256 + (unit % 128);
-            float val[32], gate[32];
-            load_bf16x32(U + row * p.ld_aux0 + ucol, val);
-            load_bf16x32(U + row * p.ld_aux0 + ucol + 128, gate);
+            slot_read_bf16(sg.base, lane, val);
+            slot_read_bf16(sg.base + SLOT_BYTES, lane, gate);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float dv = dh[i] * gelu_erf(gate[i]);
@@ -161,39 +270,19 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, uint32_t t_row,
                 val[i] = dv;
                 gate[i] = dg;
             }
-            store_bf16x32(dU + row * p.ldc + ucol, val);
-            store_bf16x32(dU + row * p.ldc + ucol + 128, gate);
-        }
-    } else if constexpr (EPI == CTK_EPI_QKV) {
-        // Every 32-column chunk is one head (dim_head 32). The first i0 columns are l2-normalised
-        // per head (eps 1e-12) and scaled per channel (attention.py:158-160; the constant logit
-        // scale rides in alpha for q); remaining columns (v) pass through. Output lands in the
-        // packed [M, 3*inner] buffer at column offset i1.
-        __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C);
-        float* rn = reinterpret_cast<float*>(p.aux0);
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            const int col = n0 + c;
-            if (col >= N) break;
-            float v[32];
-            ld_acc(t_row + c, v);
-            if (!row_ok) continue;
-            if (col < p.i0) {
-                float ss = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) ss += v[i] * v[i];
-                const float rnorm = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = v[i] * rnorm * __ldg(p.vec0 + i) * p.alpha;
-                rn[row * p.ld_aux0 + (col + p.i1) / 32] = rnorm;
-            }
-            store_bf16x32(C + row * p.ldc + col + p.i1, v);
+            slot_write_bf16(sg.base, lane, val);
+            slot_write_bf16(sg.base + SLOT_BYTES, lane, gate);
+            sg.fence();
+            sg.store(mc0, 0, ucol, row0);
+            sg.store(mc0, 1, ucol + 128, row0);
+            sg.commit();
         }
     } else if constexpr (EPI == CTK_EPI_ATOMIC_F32) {
         float* C = reinterpret_cast<float*>(p.C);
         const long long orow = row_ok ? (p.row_map ? (long long)p.row_map[row] : row) : -1;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int cc = 0; cc < 128; cc += 32) {
+            const int c = hf * 128 + cc;
             const int col = n0 + c;
             if (col >= N) break;
             float v[32];
@@ -211,7 +300,8 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, uint32_t t_row,
         float bv = -INFINITY;
         int bi = 0;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int cc = 0; cc < 128; cc += 32) {
+            const int c = hf * 128 + cc;
             const int col = n0 + c;
             if (col >= N) break;
             float v[32];
@@ -220,7 +310,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, uint32_t t_row,
             for (int i = 0; i < 32; ++i)
                 if (col + i < N && v[i] > bv) { bv = v[i]; bi = col + i; }
         }
-        if (row_ok) {
+        if (row_ok && bv > -INFINITY) {
             uint32_t u = __float_as_uint(bv);
             u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
             const unsigned long long key =
@@ -233,29 +323,37 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, uint32_t t_row,
 template <int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_c0, const __grid_constant__ CUtensorMap tmap_c1,
             int M, int N, int K, int splits, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;                       // 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
     uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* epi_bar = bars + 2 * STAGES + 4;    // [NEPI]    TMA loads of the epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NEPI);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     const int m_tiles = (M + BM - 1) / BM;
     const int n_tiles = (N + BN - 1) / BN;
+    const long long mn_tiles = (long long)m_tiles * n_tiles;
     const int kb_total = (K + BK - 1) / BK;
     const int kb_per = (kb_total + splits - 1) / splits;
-    const long long total_work = (long long)m_tiles * n_tiles * splits;
+    const long long total_work = mn_tiles * splits;
+    // work item w -> tile = w % mn_tiles (n fastest), split = w / mn_tiles: CTAs that run together
+    // share the k-range (operands hit L2) and cover different output tiles.
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        tma_prefetch_desc(&tmap_c0);
+        tma_prefetch_desc(&tmap_c1);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -264,8 +362,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], NEPI);
         }
+        for (int i = 0; i < NEPI; ++i) mbar_init(&epi_bar[i], 1);
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -283,8 +382,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const int split = (int)(w % splits);
-                const long long t = w / splits;
+                const int split = (int)(w / mn_tiles);
+                const long long t = w % mn_tiles;
                 const int n_blk = (int)(t % n_tiles), m_blk = (int)(t / n_tiles);
                 const int kb0 = split * kb_per;
                 const int kb1 = min(kb0 + kb_per, kb_total);
@@ -322,7 +421,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             int acc = 0;
             uint32_t acc_phase = 0;
             for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const int split = (int)(w % splits);
+                const int split = (int)(w / mn_tiles);
                 const int kb0 = split * kb_per;
                 const int kb1 = min(kb0 + kb_per, kb_total);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -354,22 +453,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 4;                        // == warp % 4 -> TMEM lane quarter
+        const int ew = warp - 4;
+        const int quarter = ew & 3;                     // == warp % 4 -> TMEM lane quarter
+        const int hf = ew >> 2;                         // column half of the tile
+        Stager sg;
+        sg.base = staging + ew * (SLOTS_PER_WARP * SLOT_BYTES);
+        sg.bar = &epi_bar[ew];
+        sg.phase = 0;
+        sg.lane = lane;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const long long t = w / splits;
+            const long long t = w % mn_tiles;
             const int n_blk = (int)(t % n_tiles), m_blk = (int)(t / n_tiles);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
-            const long long row = (long long)m_blk * BM + ew * 32 + lane;
-            run_epilogue<EPI>(ep, t_row, row, n_blk * BN, M, N);
+            const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            run_epilogue<EPI>(ep, &tmap_c0, &tmap_c1, sg, t_row, m_blk * BM + quarter * 32, hf, n_blk * BN, M, N);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) bulk_wait_all();                 // all TMA stores of this warp have landed
     }
 
     tc_fence_before();
@@ -398,25 +504,34 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 tensor map: dim0 = contiguous extent, dim1 = rows with `ld` elements pitch.
-int make_tmap(CUtensorMap* m, const void* ptr, long long dim0, long long dim1, long long ld,
-              int box0, int box1) {
+// 2-D tensor map: dim0 = contiguous extent, dim1 = rows with `ld` elements pitch.
+int make_tmap(CUtensorMap* m, const void* ptr, bool f32, long long dim0, long long dim1, long long ld,
+              int box0, int box1, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = get_encode_fn();
     CTK_REQUIRE(fn != nullptr, CTK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    const int esz = f32 ? 4 : 2;
     cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
     cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CTK_REQUIRE(r == CUDA_SUCCESS, CTK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    CTK_REQUIRE(r == CUDA_SUCCESS, CTK_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): ptr %p dims %lld x %lld ld %lld box %d x %d", (int)r, ptr,
+                dim0, dim1, ld, box0, box1);
     return CTK_OK;
+}
+// 32x32 epilogue block maps
+int make_block_tmap(CUtensorMap* m, const void* ptr, bool f32, long long cols, long long rows, long long ld) {
+    CTK_REQUIRE(ptr && CTK_ALIGNED(ptr, 16) && (ld * (f32 ? 4 : 2)) % 16 == 0, CTK_ERR_ALIGN,
+                "gemm: epilogue tensor needs a 16-byte aligned base and pitch");
+    return make_tmap(m, ptr, f32, cols, rows, ld, 32, 32, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 template <int EPI, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int splits,
-           const EpiParams& ep, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc0, const CUtensorMap& tc1, int M,
+           int N, int K, int splits, const EpiParams& ep, cudaStream_t stream) {
     auto kern = gemm_kernel<EPI, A_MN, B_MN>;
     static bool configured = false;
     if (!configured) {
@@ -425,9 +540,28 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, in
     }
     const long long work = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
     const int grid = (int)(work < ctk_num_sms() ? work : ctk_num_sms());
-    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, splits, ep);
+    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(ta, tb, tc0, tc1, M, N, K, splits, ep);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
+}
+
+// split-K factor for the atomic (weight gradient) epilogue: fill whole waves of SMs
+int pick_splits(long long tiles, int kb_total) {
+    const int sms = ctk_num_sms();
+    int max_splits = kb_total / 4;
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > 64) max_splits = 64;
+    int best = 1;
+    double best_score = -1.0;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+        const long long items = tiles * sp;
+        const long long waves = (items + sms - 1) / sms;
+        double eff = (double)items / (double)(waves * sms);          // wave quantisation
+        if (items < sms) eff *= 0.999;                                // prefer filling the machine
+        const double score = eff - 0.002 * sp;                        // mild bias against extra atomics
+        if (score > best_score) { best_score = score; best = sp; }
+    }
+    return best;
 }
 
 }  // namespace
@@ -455,12 +589,7 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (epilogue != CTK_EPI_ATOMIC_F32) {
         splits = 1;
     } else if (splits <= 0) {
-        // enough (tile, split) work items to cover the SMs ~2x, each with >= 8 k-blocks
-        const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-        long long want = (2LL * ctk_num_sms() + tiles - 1) / tiles;
-        long long cap = kb_total / 8 > 0 ? kb_total / 8 : 1;
-        splits = (int)(want < cap ? want : cap);
-        if (splits < 1) splits = 1;
+        splits = pick_splits((long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN), kb_total);
     }
     if (splits > kb_total) splits = kb_total;
     {   // every split must own at least one k-block
@@ -468,39 +597,64 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
         splits = (kb_total + per - 1) / per;
     }
     if (epilogue == CTK_EPI_BF16 || epilogue == CTK_EPI_F32 || epilogue == CTK_EPI_RESID_F32 ||
-        epilogue == CTK_EPI_QKV || epilogue == CTK_EPI_GEGLU_BWD) {
-        CTK_REQUIRE(N % 32 == 0, CTK_ERR_SHAPE, "gemm: N %% 32 != 0 for a vector epilogue");
-        CTK_REQUIRE(CTK_ALIGNED(e->C, 16) && e->ldc % 8 == 0, CTK_ERR_ALIGN, "gemm: C alignment");
-    }
-    if (epilogue == CTK_EPI_RESID_F32)
-        CTK_REQUIRE(e->resid && CTK_ALIGNED(e->resid, 16) && e->ldr % 4 == 0, CTK_ERR_ALIGN,
-                    "gemm: residual alignment");
+        epilogue == CTK_EPI_QKV || epilogue == CTK_EPI_GEGLU_BWD)
+        CTK_REQUIRE(N % 32 == 0, CTK_ERR_SHAPE, "gemm: N %% 32 != 0 for a block epilogue");
     if (epilogue == CTK_EPI_GEGLU)
-        CTK_REQUIRE(N % BN == 0 && e->aux0 && e->ldc % 8 == 0 && e->ld_aux0 % 8 == 0,
-                    CTK_ERR_SHAPE, "gemm: GEGLU needs N %% 256 == 0 and an H buffer");
+        CTK_REQUIRE(N % BN == 0 && e->aux0, CTK_ERR_SHAPE, "gemm: GEGLU needs N %% 256 == 0 and an H buffer");
     if (epilogue == CTK_EPI_GEGLU_BWD)
         CTK_REQUIRE(N % 128 == 0 && e->aux0, CTK_ERR_SHAPE, "gemm: GEGLU_BWD needs N %% 128 == 0");
     if (epilogue == CTK_EPI_QKV)
         CTK_REQUIRE(e->aux0 && e->vec0 && e->i0 % 32 == 0 && e->i1 % 32 == 0 && e->i0 <= N,
                     CTK_ERR_SHAPE, "gemm: QKV epilogue needs rnorm buffer, scale vector, 32-aligned i0/i1");
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc0, tc1;
     if (!a_mn_major) {
-        rc = make_tmap(&ta, A, K, M, lda, BK, BM);            // [M rows][K]
+        rc = make_tmap(&ta, A, false, K, M, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);   // [M rows][K]
         if (rc) return rc;
-        rc = make_tmap(&tb, B, K, N, ldb, BK, BN);            // [N rows][K]
+        rc = make_tmap(&tb, B, false, K, N, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);   // [N rows][K]
         if (rc) return rc;
     } else {
-        rc = make_tmap(&ta, A, M, K, lda, 64, BK);            // [K rows][M]
+        rc = make_tmap(&ta, A, false, M, K, lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);   // [K rows][M]
         if (rc) return rc;
-        rc = make_tmap(&tb, B, N, K, ldb, 64, BK);            // [K rows][N]
+        rc = make_tmap(&tb, B, false, N, K, ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);   // [K rows][N]
         if (rc) return rc;
     }
+    // epilogue tensor maps (32x32 blocks). Unused ones alias the A map so the kernel always gets
+    // valid descriptors.
+    tc0 = ta;
+    tc1 = ta;
+    switch (epilogue) {
+        case CTK_EPI_BF16:
+            rc = make_block_tmap(&tc0, e->C, false, N, M, e->ldc);
+            break;
+        case CTK_EPI_QKV:
+            rc = make_block_tmap(&tc0, e->C, false, (long long)N + e->i1, M, e->ldc);
+            break;
+        case CTK_EPI_F32:
+            rc = make_block_tmap(&tc0, e->C, true, N, M, e->ldc);
+            break;
+        case CTK_EPI_RESID_F32:
+            CTK_REQUIRE(e->resid, CTK_ERR_SHAPE, "gemm: residual pointer missing");
+            rc = make_block_tmap(&tc0, e->C, true, N, M, e->ldc);
+            if (!rc) rc = make_block_tmap(&tc1, e->resid, true, N, M, e->ldr);
+            break;
+        case CTK_EPI_GEGLU:
+            rc = make_block_tmap(&tc0, e->C, false, N, M, e->ldc);
+            if (!rc) rc = make_block_tmap(&tc1, e->aux0, false, N / 2, M, e->ld_aux0);
+            break;
+        case CTK_EPI_GEGLU_BWD:
+            rc = make_block_tmap(&tc0, e->C, false, 2LL * N, M, e->ldc);
+            if (!rc) rc = make_block_tmap(&tc1, e->aux0, false, 2LL * N, M, e->ld_aux0);
+            break;
+        default:
+            break;
+    }
+    if (rc) return rc;
 
-#define CTK_GEMM_CASE(E)                                                                     \
-    case E:                                                                                  \
-        return a_mn_major ? launch<E, true, true>(ta, tb, M, N, K, splits, ep, stream)       \
-                          : launch<E, false, false>(ta, tb, M, N, K, splits, ep, stream);
+#define CTK_GEMM_CASE(E)                                                                         \
+    case E:                                                                                      \
+        return a_mn_major ? launch<E, true, true>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream) \
+                          : launch<E, false, false>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream);
     switch (epilogue) {
         CTK_GEMM_CASE(CTK_EPI_BF16)
         CTK_GEMM_CASE(CTK_EPI_F32)
