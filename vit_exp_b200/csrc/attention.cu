@@ -619,77 +619,106 @@ attn_short_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     lse[((long long)s * heads + h) * L + i] = m * LN2 + logf(l);
 }
 
-// smem: qkv block | dO block [L][inner] | lse [heads][32] | delta [heads][32]
-__global__ void __launch_bounds__(256)
+// smem (all fp32, converted once while staging): qkv block [L][3 inner] | dO block [L][inner] |
+// P [heads][L][L+1] | dP [heads][L][L+1] | delta [heads][32]
+// 3*heads warps. Phase 1: group 0 (lane = query) fills P = softmax probabilities, group 1 fills
+// dP = dO v^T, group 2 computes delta. Phase 2: group 0 -> dq, group 1 -> dk, group 2 -> dv, each
+// thread owning one output row with dS_ij = P_ij (dP_ij - delta_i) formed on the fly.
+__device__ __forceinline__ void load_row32f(const float* p, float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 f = reinterpret_cast<const float4*>(p)[c];
+        v[4 * c] = f.x; v[4 * c + 1] = f.y; v[4 * c + 2] = f.z; v[4 * c + 3] = f.w;
+    }
+}
+__device__ __forceinline__ void stage_bf16_as_f32(float* dst, const __nv_bfloat16* src, int n8, int tid, int nthr) {
+    for (int i = tid; i < n8; i += nthr) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        reinterpret_cast<float4*>(dst)[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+        reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+    }
+}
+
+__global__ void __launch_bounds__(768, 1)
 attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                       const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                       __nv_bfloat16* __restrict__ dqkv, int L, int heads) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     const int inner = heads * 32, ld = 3 * inner;
-    __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem);
-    __nv_bfloat16* sdo = sq + L * ld;
-    float* sL = reinterpret_cast<float*>(sdo + L * inner);
-    float* sD = sL + heads * 32;
+    const int PS = L + 1;
+    float* sq = reinterpret_cast<float*>(smem);
+    float* sdo = sq + L * ld;
+    float* sP = sdo + L * inner;
+    float* sdP = sP + heads * L * PS;
+    float* sD = sdP + heads * L * PS;
     const int s = blockIdx.x;
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(qkv + (long long)s * L * ld);
-        for (int i = threadIdx.x; i < L * ld / 8; i += blockDim.x) reinterpret_cast<uint4*>(sq)[i] = __ldg(src + i);
-        const uint4* src2 = reinterpret_cast<const uint4*>(dout + (long long)s * L * inner);
-        for (int i = threadIdx.x; i < L * inner / 8; i += blockDim.x) reinterpret_cast<uint4*>(sdo)[i] = __ldg(src2 + i);
-    }
-    const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
-    const bool active = h < heads && i < L;
+    stage_bf16_as_f32(sq, qkv + (long long)s * L * ld, L * ld / 8, threadIdx.x, blockDim.x);
+    stage_bf16_as_f32(sdo, dout + (long long)s * L * inner, L * inner / 8, threadIdx.x, blockDim.x);
+    const int wg = (threadIdx.x >> 5) / heads;              // warp group 0..2
+    const int h = (threadIdx.x >> 5) % heads, i = threadIdx.x & 31;
+    const bool active = i < L;
+    float* Ph = sP + h * L * PS;
+    float* dPh = sdP + h * L * PS;
     __syncthreads();
     if (active) {
-        float a[32], b[32];
-        load_row32(out + ((long long)s * L + i) * inner + h * 32, a);
-        load_row32(sdo + i * inner + h * 32, b);
-        sD[h * 32 + i] = dot32(a, b);
-        sL[h * 32 + i] = lse[((long long)s * heads + h) * L + i] * LOG2E;
+        if (wg == 0) {
+            float q[32];
+            load_row32f(sq + i * ld + h * 32, q);
+            const float li = lse[((long long)s * heads + h) * L + i] * LOG2E;
+            for (int j = 0; j < L; ++j) {
+                float kk[32];
+                load_row32f(sq + j * ld + inner + h * 32, kk);
+                Ph[i * PS + j] = exp2f(dot32(q, kk) * LOG2E - li);
+            }
+        } else if (wg == 1) {
+            float dO[32];
+            load_row32f(sdo + i * inner + h * 32, dO);
+            for (int j = 0; j < L; ++j) {
+                float vv[32];
+                load_row32f(sq + j * ld + 2 * inner + h * 32, vv);
+                dPh[i * PS + j] = dot32(dO, vv);
+            }
+        } else {
+            float a[32], b[32];
+            load_row32(out + ((long long)s * L + i) * inner + h * 32, a);
+            load_row32f(sdo + i * inner + h * 32, b);
+            sD[h * 32 + i] = dot32(a, b);
+        }
     }
     __syncthreads();
     if (!active) return;
-    // pass A: lane = query i -> dq
-    {
-        float q[32], dO[32], dq[32];
-        load_row32(sq + i * ld + h * 32, q);
-        load_row32(sdo + i * inner + h * 32, dO);
+    float acc[32];
 #pragma unroll
-        for (int d = 0; d < 32; ++d) dq[d] = 0.f;
-        const float li = sL[h * 32 + i], di = sD[h * 32 + i];
+    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+    if (wg == 0) {                                           // dq_i = sum_j dS_ij k_j
+        const float di = sD[h * 32 + i];
         for (int j = 0; j < L; ++j) {
-            float kk[32], vv[32];
-            load_row32(sq + j * ld + inner + h * 32, kk);
-            load_row32(sq + j * ld + 2 * inner + h * 32, vv);
-            const float p = exp2f(dot32(q, kk) * LOG2E - li);
-            const float ds = p * (dot32(dO, vv) - di);
+            float kk[32];
+            load_row32f(sq + j * ld + inner + h * 32, kk);
+            const float ds = Ph[i * PS + j] * (dPh[i * PS + j] - di);
 #pragma unroll
-            for (int d = 0; d < 32; ++d) dq[d] = fmaf(ds, kk[d], dq[d]);
+            for (int d = 0; d < 32; ++d) acc[d] = fmaf(ds, kk[d], acc[d]);
         }
-        store_row32(dqkv + ((long long)s * L + i) * ld + h * 32, dq);
-    }
-    // pass B: lane = key j -> dk, dv
-    {
-        const int j = i;
-        float kk[32], vv[32], dk[32], dv[32];
-        load_row32(sq + j * ld + inner + h * 32, kk);
-        load_row32(sq + j * ld + 2 * inner + h * 32, vv);
-#pragma unroll
-        for (int d = 0; d < 32; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+        store_row32(dqkv + ((long long)s * L + i) * ld + h * 32, acc);
+    } else if (wg == 1) {                                    // dk_j = sum_i dS_ij q_i   (lane = j)
         for (int qi = 0; qi < L; ++qi) {
-            float q[32], dO[32];
-            load_row32(sq + qi * ld + h * 32, q);
-            load_row32(sdo + qi * inner + h * 32, dO);
-            const float p = exp2f(dot32(q, kk) * LOG2E - sL[h * 32 + qi]);
-            const float ds = p * (dot32(dO, vv) - sD[h * 32 + qi]);
+            float q[32];
+            load_row32f(sq + qi * ld + h * 32, q);
+            const float ds = Ph[qi * PS + i] * (dPh[qi * PS + i] - sD[h * 32 + qi]);
 #pragma unroll
-            for (int d = 0; d < 32; ++d) {
-                dk[d] = fmaf(ds, q[d], dk[d]);
-                dv[d] = fmaf(p, dO[d], dv[d]);
-            }
+            for (int d = 0; d < 32; ++d) acc[d] = fmaf(ds, q[d], acc[d]);
         }
-        store_row32(dqkv + ((long long)s * L + j) * ld + inner + h * 32, dk);
-        store_row32(dqkv + ((long long)s * L + j) * ld + 2 * inner + h * 32, dv);
+        store_row32(dqkv + ((long long)s * L + i) * ld + inner + h * 32, acc);
+    } else {                                                 // dv_j = sum_i P_ij dO_i   (lane = j)
+        for (int qi = 0; qi < L; ++qi) {
+            float dO[32];
+            load_row32f(sdo + qi * inner + h * 32, dO);
+            const float pv = Ph[qi * PS + i];
+#pragma unroll
+            for (int d = 0; d < 32; ++d) acc[d] = fmaf(pv, dO[d], acc[d]);
+        }
+        store_row32(dqkv + ((long long)s * L + i) * ld + 2 * inner + h * 32, acc);
     }
 }
 
@@ -703,55 +732,63 @@ qknorm_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, const __nv_bfloat16* __restr
                   const float* __restrict__ rnorm, const float* __restrict__ q_scale,
                   const float* __restrict__ k_scale, float alpha, float* __restrict__ dq_scale,
                   float* __restrict__ dk_scale, long long rows, int heads) {
-    // thread per (row, q|k head): 32 channels = 64 contiguous bytes. The thread's slot type (q or k)
-    // is fixed across its grid-stride loop (stride is a multiple of 2*heads), so the per-channel
-    // scale gradient accumulates in registers.
+    // 4 threads per (row, q|k head), 8 channels (16 bytes) each: fully coalesced 16-byte accesses,
+    // the head-wide dot product is two shuffles. A thread's (slot type, channel group) is fixed
+    // across its grid-stride loop (the stride is a multiple of 8*heads), so the per-channel scale
+    // gradients accumulate in 8 registers and are folded through shared memory at the end.
+    __shared__ float red[2][32];
+    if (threadIdx.x < 64) red[threadIdx.x >> 5][threadIdx.x & 31] = 0.f;
+    __syncthreads();
     const int inner = heads * 32;
     const long long ld = 3LL * inner;
     const int nslot = 2 * heads;
-    const long long total = rows * nslot;
-    const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of 2*heads (host guarantees)
+    const long long total = rows * nslot * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
     const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = (int)(idx0 % nslot);
+    const int grp = (int)(idx0 & 3);
+    const int slot = (int)((idx0 >> 2) % nslot);
     const bool is_q = slot < heads;
-    const float* scp = is_q ? q_scale : k_scale;
+    const float* scp = (is_q ? q_scale : k_scale) + grp * 8;
     const float a = is_q ? alpha : 1.f;
-    float sc[32], acc[32];
+    float sc[8], acc[8];
 #pragma unroll
-    for (int d = 0; d < 32; ++d) { sc[d] = __ldg(scp + d) * a; acc[d] = 0.f; }
+    for (int d = 0; d < 8; ++d) { sc[d] = __ldg(scp + d) * a; acc[d] = 0.f; }
     for (long long idx = idx0; idx < total; idx += stride) {
-        const long long row = idx / nslot;
-        const long long off = row * ld + (long long)slot * 32;
-        float y[32], dy[32];
-        load_row32(qkv + off, y);
-        load_row32(dqkv + off, dy);
+        const long long row = (idx >> 2) / nslot;
+        const long long off = row * ld + (long long)slot * 32 + grp * 8;
+        const uint4 yu = *reinterpret_cast<const uint4*>(qkv + off);
+        const uint4 du = *reinterpret_cast<const uint4*>(dqkv + off);
+        const uint32_t yw[4] = {yu.x, yu.y, yu.z, yu.w}, dw_[4] = {du.x, du.y, du.z, du.w};
+        float xh[8], g[8];
         float dotv = 0.f;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) {
-            const float xh = sc[d] != 0.f ? __fdividef(y[d], sc[d]) : 0.f;
-            acc[d] = fmaf(dy[d], xh, acc[d]);
-            y[d] = xh;
-            dy[d] *= sc[d];                                  // g = d loss / d xhat
-            dotv = fmaf(xh, dy[d], dotv);
+        for (int e = 0; e < 4; ++e) {
+            const float2 yy = unpack_bf16x2(yw[e]), dd = unpack_bf16x2(dw_[e]);
+            const float y2[2] = {yy.x, yy.y}, d2[2] = {dd.x, dd.y};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int d = 2 * e + q;
+                xh[d] = sc[d] != 0.f ? __fdividef(y2[q], sc[d]) : 0.f;
+                acc[d] = fmaf(d2[q], xh[d], acc[d]);
+                g[d] = d2[q] * sc[d];                          // d loss / d xhat
+                dotv = fmaf(xh[d], g[d], dotv);
+            }
         }
+        dotv += __shfl_xor_sync(0xffffffffu, dotv, 1);
+        dotv += __shfl_xor_sync(0xffffffffu, dotv, 2);
         const float rn = rnorm[row * nslot + slot];
-#pragma unroll
-        for (int d = 0; d < 32; ++d) dy[d] = rn * (dy[d] - y[d] * dotv);
-        store_row32(dqkv + off, dy);
+        uint4 o;
+        o.x = pack_bf16x2(rn * (g[0] - xh[0] * dotv), rn * (g[1] - xh[1] * dotv));
+        o.y = pack_bf16x2(rn * (g[2] - xh[2] * dotv), rn * (g[3] - xh[3] * dotv));
+        o.z = pack_bf16x2(rn * (g[4] - xh[4] * dotv), rn * (g[5] - xh[5] * dotv));
+        o.w = pack_bf16x2(rn * (g[6] - xh[6] * dotv), rn * (g[7] - xh[7] * dotv));
+        *reinterpret_cast<uint4*>(dqkv + off) = o;
     }
-    // reduce the scale gradients: lanes with the same slot type sit 2*heads apart... reduce over the
-    // whole warp per type with a masked butterfly, then one atomic per channel per warp and type
-    const unsigned lane = threadIdx.x & 31;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) {
-        float vq = is_q ? acc[d] * a : 0.f, vk = is_q ? 0.f : acc[d];
-        vq = warp_sum(vq);
-        vk = warp_sum(vk);
-        if (lane == 0) {
-            atomicAdd(dq_scale + d, vq);
-            atomicAdd(dk_scale + d, vk);
-        }
-    }
+    for (int d = 0; d < 8; ++d) atomicAdd(&red[is_q ? 0 : 1][grp * 8 + d], acc[d] * a);
+    __syncthreads();
+    if (threadIdx.x < 32) atomicAdd(dq_scale + threadIdx.x, red[0][threadIdx.x]);
+    else if (threadIdx.x < 64) atomicAdd(dk_scale + threadIdx.x - 32, red[1][threadIdx.x - 32]);
 }
 
 }  // namespace
@@ -816,9 +853,11 @@ extern "C" int ctk_attn_bwd(const void* qkv, const float* table, const void* out
     auto dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
     const int inner = heads * 32;
     if (!table && L <= 32) {
-        const size_t sm = (size_t)L * 3 * inner * 2 + (size_t)L * inner * 2 + (size_t)heads * 32 * 4 * 2;
+        const size_t sm = (size_t)L * 3 * inner * 4 + (size_t)L * inner * 4 +
+                          2 * (size_t)heads * L * (L + 1) * 4 + (size_t)heads * 32 * 4;
+        CTK_REQUIRE(sm <= 220 * 1024, CTK_ERR_SHAPE, "attn_bwd: short sequence of %d tokens does not fit", L);
         CTK_CUDA(cudaFuncSetAttribute(attn_short_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        attn_short_bwd_kernel<<<nseq, heads * 32, sm, s>>>(q, o, d_o, lse, dq, L, heads);
+        attn_short_bwd_kernel<<<nseq, heads * 96, sm, s>>>(q, o, d_o, lse, dq, L, heads);
         CTK_LAUNCH_CHECK();
         return CTK_OK;
     }
@@ -870,9 +909,9 @@ extern "C" int ctk_qknorm_bwd(void* dqkv, const void* qkv, const float* rnorm, c
     CTK_REQUIRE(dqkv && qkv && rnorm && q_scale && k_scale && dq_scale && dk_scale && rows > 0 && heads > 0,
                 CTK_ERR_SHAPE, "qknorm_bwd: bad args");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    CTK_REQUIRE(256 % (2 * heads) == 0, CTK_ERR_SHAPE, "qknorm_bwd: heads must divide 128");
-    long long blocks = (rows * 2 * heads + 255) / 256;
-    const long long cap = (long long)ctk_num_sms() * 8;
+    CTK_REQUIRE(256 % (8 * heads) == 0, CTK_ERR_SHAPE, "qknorm_bwd: heads must divide 32");
+    long long blocks = (rows * 8 * heads + 255) / 256;
+    const long long cap = (long long)ctk_num_sms() * 16;
     if (blocks > cap) blocks = cap;
     qknorm_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(dqkv),
                                                        reinterpret_cast<const __nv_bfloat16*>(qkv), rnorm,

@@ -574,13 +574,17 @@ extern "C" int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
     return CTK_ERR_SHAPE;
 }
 
-static size_t peg_smem(int n2) { return (size_t)3 * (PEG_T1 + 2) * (n2 + 2) * PEG_CS * sizeof(float); }
+static size_t peg_smem(int n2) {
+    const size_t ring = (size_t)3 * (PEG_T1 + 2) * (n2 + 2) * PEG_CS * sizeof(float);
+    const size_t red = (size_t)8 * 28 * 32 * sizeof(float);          // MODE 2 cross-warp reduction
+    return ring > red ? ring : red;
+}
 
 template <int MODE>
 static int peg_launch(const float* x, const float* w, const float* b, const float* dy, float* y, void* y_bf16,
                       float* dw, float* db, int B, int n0, int n1, int n2, int dim, cudaStream_t s) {
     const size_t sm = peg_smem(n2);
-    CTK_REQUIRE(sm <= 220 * 1024 && sm >= 8 * 28 * 32 * sizeof(float), CTK_ERR_SHAPE, "peg: axis-2 extent %d unsupported", n2);
+    CTK_REQUIRE(sm <= 220 * 1024, CTK_ERR_SHAPE, "peg: axis-2 extent %d does not fit in shared memory", n2);
     CTK_CUDA(cudaFuncSetAttribute(peg_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
     peg_tile_kernel<MODE><<<dim3(B * tiles1, dim / PEG_CS), 256, sm, s>>>(
