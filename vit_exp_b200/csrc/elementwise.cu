@@ -258,14 +258,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
 // PEG: depthwise causal 3x3x3 conv + bias + residual on [B, n0, n1, n2, dim] (attention.py:62-90,443)
 //
 // CTA = (batch b, tile of PEG_T1 rows along axis 1, slab of 32 channels). It walks axis 0 keeping a
-// ring of 3 input planes ((PEG_T1+2) x (n2+2) x 32 floats, zero halo) in shared memory, so every
-// input element is fetched from HBM/L2 once per CTA (1.25x halo overhead) instead of 9-27 times.
+// ring of 4 input planes ((PEG_T1+2) x (n2+2) x 32 floats, zero halo) in shared memory: 3 feed the
+// current output plane while cp.async fills the 4th for the next step, so every input element is
+// fetched from HBM/L2 once per CTA (1.5x halo overhead) instead of 9-27 times.
 // lane <-> channel (a warp reads 128 contiguous bytes per token, bank-conflict free in smem),
-// warp <-> output row; a 3-wide register window slides along axis 2.
+// warp <-> (output row, half of axis 2); a 3-wide register window slides along axis 2.
 // MODE 0: y = conv(x) + b + x          MODE 1: dx = conv^T(dy) + dy (flipped taps, planes a0..a0+2)
 // MODE 2: dw, db accumulation (x planes in smem, dy read directly)
 // =============================================================================================
-constexpr int PEG_T1 = 8;
+constexpr int PEG_T1 = 4;
+constexpr int PEG_RING = 4;
 constexpr int PEG_CS = 32;
 
 __device__ __forceinline__ void cp_async16_ew(uint32_t dst, const void* src) {
@@ -308,13 +310,16 @@ peg_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     const int r_lo = (blockIdx.x % tiles1) * PEG_T1;
     const int c0 = slab * PEG_CS;
     const int c = c0 + lane;
-    const int a1 = r_lo + warp;                                  // this warp's output row
+    const int lrow = warp % PEG_T1, half = warp / PEG_T1;        // 8 warps = 4 rows x 2 halves of axis 2
+    const int a1 = r_lo + lrow;                                   // this warp's output row
     const bool row_ok = a1 < n1;
+    const int p_lo = half * ((n2 + 1) / 2), p_hi = half == 0 ? min(n2, (n2 + 1) / 2) : n2;
     constexpr bool REV = MODE == 1;
     constexpr int shift = REV ? 0 : -2;                          // planes a0+shift .. a0+shift+2
+    auto slot_of = [&](int q) { return psm + (((q % PEG_RING) + PEG_RING) % PEG_RING) * plane_floats; };
 
-    // zero the a2 halo columns of all three slots once (loads never touch them)
-    for (int i = tid; i < 3 * (PEG_T1 + 2) * 2 * PEG_CS; i += 256) {
+    // zero the a2 halo columns of all ring slots once (loads never touch them)
+    for (int i = tid; i < PEG_RING * (PEG_T1 + 2) * 2 * PEG_CS; i += 256) {
         const int ch = i % PEG_CS;
         const int side = (i / PEG_CS) % 2;
         const int rr = (i / (2 * PEG_CS)) % (PEG_T1 + 2);
@@ -335,38 +340,34 @@ peg_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     }
     const float* src = (MODE == 1) ? dy : x;                     // tensor staged in shared memory
 
+    // prologue: the three planes of step 0
+    for (int k = 0; k < 3; ++k) peg_load_plane(slot_of(shift + k), src, bb, shift + k, r_lo, c0, n0, n1, n2, dim, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     for (int a0 = 0; a0 < n0; ++a0) {
-        __syncthreads();                                          // previous step finished with the ring
-        if (a0 == 0) {
-            for (int k = 0; k < 3; ++k) {
-                const int q = shift + k;
-                peg_load_plane(psm + (((q % 3) + 3) % 3) * plane_floats, src, bb, q, r_lo, c0, n0, n1, n2, dim, tid);
-            }
-        } else {
-            const int q = a0 + shift + 2;
-            peg_load_plane(psm + (((q % 3) + 3) % 3) * plane_floats, src, bb, q, r_lo, c0, n0, n1, n2, dim, tid);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();          // planes of this step landed; every warp finished the previous step
+        if (a0 + 1 < n0) {        // prefetch the one new plane of the next step into the free slot
+            const int q = a0 + 1 + shift + 2;
+            peg_load_plane(slot_of(q), src, bb, q, r_lo, c0, n0, n1, n2, dim, tid);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        if (!row_ok) continue;
-        // smem line (k0, k1): plane a0+shift+k0, local row warp + k1   (local row 0 = a1 - 1)
+        if (!row_ok || p_lo >= p_hi) continue;
+        // smem line (k0, k1): plane a0+shift+k0, local row lrow + k1   (local row 0 = a1 - 1)
         const float* ln[9];
 #pragma unroll
         for (int k0 = 0; k0 < 3; ++k0) {
-            const int q = a0 + shift + k0;
-            const float* pl = psm + (((q % 3) + 3) % 3) * plane_floats;
+            const float* pl = slot_of(a0 + shift + k0);
 #pragma unroll
-            for (int k1 = 0; k1 < 3; ++k1) ln[k0 * 3 + k1] = pl + ((warp + k1) * W2) * PEG_CS + lane;
+            for (int k1 = 0; k1 < 3; ++k1) ln[k0 * 3 + k1] = pl + ((lrow + k1) * W2 + p_lo) * PEG_CS + lane;
         }
         float win[9][3];
 #pragma unroll
         for (int l = 0; l < 9; ++l) { win[l][0] = ln[l][0]; win[l][1] = ln[l][PEG_CS]; }
         constexpr int centre = REV ? 1 : 7;                      // (k0,k1) of the un-shifted line
         const long long obase = ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim + c;
-        for (int a2 = 0; a2 < n2; ++a2) {
+        for (int a2 = p_lo; a2 < p_hi; ++a2) {
 #pragma unroll
-            for (int l = 0; l < 9; ++l) win[l][2] = ln[l][(a2 + 2) * PEG_CS];
+            for (int l = 0; l < 9; ++l) win[l][2] = ln[l][(a2 - p_lo + 2) * PEG_CS];
             if (MODE == 2) {
                 const float g = dy[obase + (long long)a2 * dim];
                 acc_b += g;
@@ -388,12 +389,14 @@ peg_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
         }
     }
     if (MODE == 2) {
-        // reduce the 8 rows (warps) of the CTA through shared memory, then one atomic per (c, tap)
+        // reduce the 8 warps of the CTA through shared memory, then one atomic per (c, tap)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         float* red = psm;                                        // [8][28][32]
+        const bool contributes = row_ok && p_lo < p_hi;
 #pragma unroll
-        for (int t = 0; t < 27; ++t) red[(warp * 28 + t) * 32 + lane] = row_ok ? acc_w[t] : 0.f;
-        red[(warp * 28 + 27) * 32 + lane] = row_ok ? acc_b : 0.f;
+        for (int t = 0; t < 27; ++t) red[(warp * 28 + t) * 32 + lane] = contributes ? acc_w[t] : 0.f;
+        red[(warp * 28 + 27) * 32 + lane] = contributes ? acc_b : 0.f;
         __syncthreads();
         for (int i = tid; i < 28 * 32; i += 256) {
             const int t = i / 32, l = i % 32;
@@ -575,7 +578,7 @@ extern "C" int ctk_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
 }
 
 static size_t peg_smem(int n2) {
-    const size_t ring = (size_t)3 * (PEG_T1 + 2) * (n2 + 2) * PEG_CS * sizeof(float);
+    const size_t ring = (size_t)PEG_RING * (PEG_T1 + 2) * (n2 + 2) * PEG_CS * sizeof(float);
     const size_t red = (size_t)8 * 28 * 32 * sizeof(float);          // MODE 2 cross-warp reduction
     return ring > red ? ring : red;
 }
