@@ -15,6 +15,10 @@
 void ctk_set_error(const char* fmt, ...);
 void ctk_count_launch();  // diagnostic counter behind ctk_launch_count() (bench.py's gpu_launches)
 int ctk_check_device();   // CTK_OK or CTK_ERR_ARCH (no CPU / non-sm_100 fallback)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
+// dims/box innermost first; strides_bytes has rank-1 entries (dims 1..rank-1). swizzle: 0 none, 1 32B, 2 64B, 3 128B.
+int ctk_make_tmap(CUtensorMap* m, const void* ptr, bool f32, int rank, const unsigned long long* dims,
+                  const unsigned long long* strides_bytes, const unsigned int* box, int swizzle);
 
 #define CTK_REQUIRE(cond, code, ...)                                                   \
     do {                                                                               \
@@ -156,6 +160,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,

@@ -258,9 +258,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
 // PEG: depthwise causal 3x3x3 conv + bias + residual on [B, n0, n1, n2, dim] (attention.py:62-90,443)
 //
 // CTA = (batch b, tile of PEG_T1 rows along axis 1, slab of 32 channels). It walks axis 0 keeping a
-// ring of 4 input planes ((PEG_T1+2) x (n2+2) x 32 floats, zero halo) in shared memory: 3 feed the
-// current output plane while cp.async fills the 4th for the next step, so every input element is
-// fetched from HBM/L2 once per CTA (1.5x halo overhead) instead of 9-27 times.
+// ring of 4 input planes in shared memory: 3 feed the current output plane while the TMA engine
+// fills the 4th for the next step. Each plane is ONE 5-D TMA box {32 ch, n2+2, PEG_T1+2, 1, 1}
+// whose out-of-range coordinates (halo rows/columns, planes before the causal start) are
+// zero-filled by the hardware, so every input element is fetched once per CTA (1.5x halo
+// overhead) instead of 9-27 times and there is no index arithmetic on the load path.
 // lane <-> channel (a warp reads 128 contiguous bytes per token, bank-conflict free in smem),
 // warp <-> (output row, half of axis 2); a 3-wide register window slides along axis 2.
 // MODE 0: y = conv(x) + b + x          MODE 1: dx = conv^T(dy) + dy (flipped taps, planes a0..a0+2)
@@ -270,44 +272,22 @@ constexpr int PEG_T1 = 4;
 constexpr int PEG_RING = 4;
 constexpr int PEG_CS = 32;
 
-__device__ __forceinline__ void cp_async16_ew(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
-// load plane q (axis 0 index) rows [r_lo-1, r_lo+PEG_T1+1) into `dst`; invalid planes/rows -> zeros
-__device__ __forceinline__ void peg_load_plane(float* dst, const float* __restrict__ x, int bb, int q, int r_lo,
-                                               int c0, int n0, int n1, int n2, int dim, int tid) {
-    const int W2 = n2 + 2;
-    const bool plane_ok = q >= 0 && q < n0;
-    const int nchunk = (PEG_T1 + 2) * n2 * (PEG_CS / 4);        // 16-byte chunks (4 channels)
-    for (int i = tid; i < nchunk; i += 256) {
-        const int ch4 = i % (PEG_CS / 4);
-        const int pos = (i / (PEG_CS / 4)) % n2;
-        const int rr = i / ((PEG_CS / 4) * n2);                  // 0 .. PEG_T1+1
-        const int a1 = r_lo - 1 + rr;
-        float* d = dst + ((rr * W2 + pos + 1) * PEG_CS + ch4 * 4);
-        if (plane_ok && a1 >= 0 && a1 < n1) {
-            const float* src = x + ((((long long)bb * n0 + q) * n1 + a1) * n2 + pos) * dim + c0 + ch4 * 4;
-            cp_async16_ew(smem_u32(d), src);
-        } else {
-            *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(256, 2)
-peg_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                const float* __restrict__ dy, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
-                float* __restrict__ dw, float* __restrict__ db, int B, int n0, int n1, int n2, int dim) {
-    extern __shared__ __align__(16) float psm[];
+peg_tile_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w,
+                const float* __restrict__ b, const float* __restrict__ dy, float* __restrict__ y,
+                __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ dw, float* __restrict__ db, int B,
+                int n0, int n1, int n2, int dim) {
+    extern __shared__ __align__(128) float psm[];
+    __shared__ __align__(8) uint64_t full_bar[PEG_RING];
     const int W2 = n2 + 2;
     const int plane_floats = (PEG_T1 + 2) * W2 * PEG_CS;
+    const uint32_t plane_bytes = (uint32_t)plane_floats * 4u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
-    const int slab = blockIdx.y;
-    const int bb = blockIdx.x / tiles1;
-    const int r_lo = (blockIdx.x % tiles1) * PEG_T1;
+    const int slab = blockIdx.x;                                  // slabs of a tile run together (L2 reuse)
+    const int bb = blockIdx.y / tiles1;
+    const int r_lo = (blockIdx.y % tiles1) * PEG_T1;
     const int c0 = slab * PEG_CS;
     const int c = c0 + lane;
     const int lrow = warp % PEG_T1, half = warp / PEG_T1;        // 8 warps = 4 rows x 2 halves of axis 2
@@ -315,17 +295,18 @@ peg_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     const bool row_ok = a1 < n1;
     const int p_lo = half * ((n2 + 1) / 2), p_hi = half == 0 ? min(n2, (n2 + 1) / 2) : n2;
     constexpr bool REV = MODE == 1;
-    constexpr int shift = REV ? 0 : -2;                          // planes a0+shift .. a0+shift+2
-    auto slot_of = [&](int q) { return psm + (((q % PEG_RING) + PEG_RING) % PEG_RING) * plane_floats; };
-
-    // zero the a2 halo columns of all ring slots once (loads never touch them)
-    for (int i = tid; i < PEG_RING * (PEG_T1 + 2) * 2 * PEG_CS; i += 256) {
-        const int ch = i % PEG_CS;
-        const int side = (i / PEG_CS) % 2;
-        const int rr = (i / (2 * PEG_CS)) % (PEG_T1 + 2);
-        const int sl = i / (2 * PEG_CS * (PEG_T1 + 2));
-        psm[sl * plane_floats + (rr * W2 + (side ? W2 - 1 : 0)) * PEG_CS + ch] = 0.f;
+    constexpr int shift = REV ? 0 : -2;                          // load n holds plane n + shift
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < PEG_RING; ++i) mbar_init(&full_bar[i], 1);
+        mbar_fence_init();
     }
+    __syncthreads();
+    auto issue = [&](int n) {                                     // thread 0 only
+        const int sl = n % PEG_RING;
+        mbar_expect_tx(&full_bar[sl], plane_bytes);
+        tma_load_5d(psm + sl * plane_floats, &tmap, &full_bar[sl], c0, -1, r_lo - 1, n + shift, bb);
+    };
     float wt[27];
     if (MODE != 2) {
 #pragma unroll
@@ -338,25 +319,22 @@ peg_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 #pragma unroll
         for (int t = 0; t < 27; ++t) acc_w[t] = 0.f;
     }
-    const float* src = (MODE == 1) ? dy : x;                     // tensor staged in shared memory
-
-    // prologue: the three planes of step 0
-    for (int k = 0; k < 3; ++k) peg_load_plane(slot_of(shift + k), src, bb, shift + k, r_lo, c0, n0, n1, n2, dim, tid);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid == 0) { issue(0); issue(1); issue(2); }
     for (int a0 = 0; a0 < n0; ++a0) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();          // planes of this step landed; every warp finished the previous step
-        if (a0 + 1 < n0) {        // prefetch the one new plane of the next step into the free slot
-            const int q = a0 + 1 + shift + 2;
-            peg_load_plane(slot_of(q), src, bb, q, r_lo, c0, n0, n1, n2, dim, tid);
+        // loads a0, a0+1, a0+2 feed this step; the first two were awaited by earlier steps
+        if (a0 == 0) {
+            mbar_wait(&full_bar[0], 0);
+            mbar_wait(&full_bar[1], 0);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        mbar_wait(&full_bar[(a0 + 2) % PEG_RING], ((a0 + 2) / PEG_RING) & 1);
+        __syncthreads();          // every warp finished step a0-1 -> slot of load a0-1 is free
+        if (tid == 0 && a0 + 1 < n0) issue(a0 + 3);
         if (!row_ok || p_lo >= p_hi) continue;
-        // smem line (k0, k1): plane a0+shift+k0, local row lrow + k1   (local row 0 = a1 - 1)
+        // smem line (k0, k1): load a0+k0, local row lrow + k1   (local row 0 = a1 - 1)
         const float* ln[9];
 #pragma unroll
         for (int k0 = 0; k0 < 3; ++k0) {
-            const float* pl = slot_of(a0 + shift + k0);
+            const float* pl = psm + ((a0 + k0) % PEG_RING) * plane_floats;
 #pragma unroll
             for (int k1 = 0; k1 < 3; ++k1) ln[k0 * 3 + k1] = pl + ((lrow + k1) * W2 + p_lo) * PEG_CS + lane;
         }
@@ -390,7 +368,6 @@ peg_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     }
     if (MODE == 2) {
         // reduce the 8 warps of the CTA through shared memory, then one atomic per (c, tap)
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         float* red = psm;                                        // [8][28][32]
         const bool contributes = row_ok && p_lo < p_hi;
@@ -584,14 +561,23 @@ static size_t peg_smem(int n2) {
 }
 
 template <int MODE>
-static int peg_launch(const float* x, const float* w, const float* b, const float* dy, float* y, void* y_bf16,
+static int peg_launch(const float* staged, const float* w, const float* b, const float* dy, float* y, void* y_bf16,
                       float* dw, float* db, int B, int n0, int n1, int n2, int dim, cudaStream_t s) {
     const size_t sm = peg_smem(n2);
-    CTK_REQUIRE(sm <= 220 * 1024, CTK_ERR_SHAPE, "peg: axis-2 extent %d does not fit in shared memory", n2);
+    CTK_REQUIRE(sm <= 200 * 1024 && n2 + 2 <= 256, CTK_ERR_SHAPE, "peg: axis-2 extent %d does not fit in shared memory", n2);
+    // 5-D view {dim, n2, n1, n0, B} of the tensor that is staged through shared memory
+    CUtensorMap tm;
+    const unsigned long long dims[5] = {(unsigned long long)dim, (unsigned long long)n2, (unsigned long long)n1,
+                                        (unsigned long long)n0, (unsigned long long)B};
+    const unsigned long long st[4] = {(unsigned long long)dim * 4, (unsigned long long)dim * n2 * 4,
+                                      (unsigned long long)dim * n2 * n1 * 4, (unsigned long long)dim * n2 * n1 * n0 * 4};
+    const unsigned int box[5] = {PEG_CS, (unsigned)(n2 + 2), PEG_T1 + 2, 1, 1};
+    int rc = ctk_make_tmap(&tm, staged, true, 5, dims, st, box, 0);
+    if (rc) return rc;
     CTK_CUDA(cudaFuncSetAttribute(peg_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
-    peg_tile_kernel<MODE><<<dim3(B * tiles1, dim / PEG_CS), 256, sm, s>>>(
-        x, w, b, dy, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), dw, db, B, n0, n1, n2, dim);
+    peg_tile_kernel<MODE><<<dim3(dim / PEG_CS, B * tiles1), 256, sm, s>>>(
+        tm, w, b, dy, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), dw, db, B, n0, n1, n2, dim);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
@@ -616,7 +602,7 @@ extern "C" int ctk_peg_bwd(const float* dy, const float* x, const float* w, floa
                 "peg: dim must be a multiple of 32, tensors 16-byte aligned");
     CTK_REQUIRE(dy != dx, CTK_ERR_SHAPE, "peg_bwd: in-place not supported");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    rc = peg_launch<1>(nullptr, w, nullptr, dy, dx, dx_bf16, nullptr, nullptr, B, n0, n1, n2, dim, s);
+    rc = peg_launch<1>(dy, w, nullptr, dy, dx, dx_bf16, nullptr, nullptr, B, n0, n1, n2, dim, s);
     if (rc) return rc;
     return peg_launch<2>(x, nullptr, nullptr, dy, nullptr, nullptr, dw, db, B, n0, n1, n2, dim, s);
 }
