@@ -109,6 +109,85 @@ patch_norm_kernel(const float* __restrict__ video, __nv_bfloat16* __restrict__ x
     }
 }
 
+// TMA variant for the production patch geometry: the G patches of a CTA are ONE 3-D TMA box
+// {G*P2, P1, PT} of the fp32 volume (64 KB for 4 patches of 20x20x10), landed in shared memory in
+// exactly the (pt p1 p2) K-order of ctvit.py:171; statistics and the bf16 write-out then run out
+// of shared memory with compile-time index arithmetic.
+template <int PT, int P1, int P2, int G>
+__global__ void __launch_bounds__(256)
+patch_norm_tma_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __restrict__ xhat, long long ld,
+                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int D, int H, int W, float eps) {
+    constexpr int K = PT * P1 * P2, RUNW = G * P2, NRUN = PT * P1;
+    extern __shared__ __align__(128) float sm[];          // [NRUN][RUNW]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float red[8][G];
+    __shared__ float stat[G][2];
+    const int T = D / PT, Hp = H / P1, Wp = W / P2;
+    const int wg = Wp / G;
+    long long cta = blockIdx.x;
+    const int wgi = (int)(cta % wg); cta /= wg;
+    const int hp = (int)(cta % Hp);  cta /= Hp;
+    const int tp = (int)(cta % T);   cta /= T;
+    const int b = (int)cta;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, NRUN * RUNW * 4);
+        tma_load_3d(sm, &tmap, &bar, wgi * RUNW, hp * P1, b * D + tp * PT);
+    }
+    mbar_wait(&bar, 0);
+    // thread <-> column x of the box (fixed patch g = x / P2), strided over the NRUN rows
+    constexpr int TPR = 256 / RUNW;                         // row lanes per column
+    const int x = tid % RUNW, r0 = tid / RUNW;
+    const bool act = tid < TPR * RUNW;
+    const int g = x / P2;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (tid < 8 * G) red[tid / G][tid % G] = 0.f;
+        __syncthreads();
+        if (act) {
+            float a = 0.f;
+            if (pass == 0) {
+                for (int r = r0; r < NRUN; r += TPR) a += sm[r * RUNW + x];
+            } else {
+                const float mu = stat[g][0];
+                for (int r = r0; r < NRUN; r += TPR) { const float d = sm[r * RUNW + x] - mu; a = fmaf(d, d, a); }
+            }
+            atomicAdd(&red[warp][g], a);
+        }
+        __syncthreads();
+        if (tid < G) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += red[w][tid];
+            if (pass == 0) stat[tid][0] = a / (float)K;
+            else stat[tid][1] = rsqrtf(a / (float)K + eps);
+        }
+        __syncthreads();
+    }
+    const long long row0 = (((long long)b * T + tp) * Hp + hp) * Wp + (long long)wgi * G;
+    if (tid < G) { mean_out[row0 + tid] = stat[tid][0]; rstd_out[row0 + tid] = stat[tid][1]; }
+    // write xhat (bf16): 4 elements (8 B) per thread-iteration, consecutive threads -> consecutive k
+    constexpr int Q = K / 4;
+    static_assert(P2 % 4 == 0, "P2 must be a multiple of 4");
+    for (int i = tid; i < G * Q; i += 256) {
+        const int gg = i / Q, q = i % Q;
+        const int r = q / (P2 / 4), dx = (q % (P2 / 4)) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(sm + r * RUNW + gg * P2 + dx);
+        const float mu = stat[gg][0], rs = stat[gg][1];
+        uint2 u;
+        u.x = pack_bf16x2((v.x - mu) * rs, (v.y - mu) * rs);
+        u.y = pack_bf16x2((v.z - mu) * rs, (v.w - mu) * rs);
+        *reinterpret_cast<uint2*>(xhat + (row0 + gg) * ld + 4 * q) = u;
+    }
+    // pad columns [K, ld)
+    for (int i = tid; i < G * (int)(ld - K); i += 256)
+        xhat[(row0 + i / (int)(ld - K)) * ld + K + i % (int)(ld - K)] = __float2bfloat16(0.f);
+}
+
 // =============================================================================================
 // LayerNorm forward: one warp per row, NV float2 pairs per lane (dim = 64 * NV)
 // =============================================================================================
@@ -495,6 +574,22 @@ extern "C" int ctk_patch_norm_fwd(const float* video, void* xhat, long long ld, 
                 "patch_norm: xhat pitch must be a multiple of 8 and >= %d", K);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     const int Wp = W / p2;
+    if (pt == 10 && p1 == 20 && p2 == 20 && Wp % 4 == 0 && W % 4 == 0) {
+        // production geometry (run_train.py:56-66): TMA-staged boxes
+        CUtensorMap tm;
+        const unsigned long long dims[3] = {(unsigned long long)W, (unsigned long long)H, (unsigned long long)B * D};
+        const unsigned long long st[2] = {(unsigned long long)W * 4, (unsigned long long)W * H * 4};
+        const unsigned int box[3] = {80, 20, 10};
+        rc = ctk_make_tmap(&tm, video, true, 3, dims, st, box, 0);
+        if (rc) return rc;
+        const size_t smem = (size_t)4 * K * sizeof(float);
+        auto kern = patch_norm_tma_kernel<10, 20, 20, 4>;
+        CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long ctas = (long long)B * (D / pt) * (H / p1) * (Wp / 4);
+        kern<<<(unsigned)ctas, 256, smem, s>>>(tm, reinterpret_cast<__nv_bfloat16*>(xhat), ld, mean, rstd, D, H, W, eps);
+        CTK_LAUNCH_CHECK();
+        return CTK_OK;
+    }
     const int G = (Wp % 4 == 0 && (size_t)4 * K * 4 <= 96 * 1024) ? 4 : (Wp % 2 == 0 && (size_t)2 * K * 4 <= 96 * 1024) ? 2 : 1;
     const size_t smem = (size_t)G * K * sizeof(float);
     CTK_REQUIRE(smem <= 200 * 1024, CTK_ERR_SHAPE, "patch_norm: patch of %d voxels too large", K);
