@@ -199,13 +199,13 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__
         }
         mx0 = quad_max(mx0); mx1 = quad_max(mx1);
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float r0 = exp2f(m0 - mn0), r1 = exp2f(m1 - mn1);
+        const float r0 = fast_exp2(m0 - mn0), r1 = fast_exp2(m1 - mn1);
         m0 = mn0; m1 = mn1;
         float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            sc[nt][0] = exp2f(sc[nt][0] - mn0); sc[nt][1] = exp2f(sc[nt][1] - mn0);
-            sc[nt][2] = exp2f(sc[nt][2] - mn1); sc[nt][3] = exp2f(sc[nt][3] - mn1);
+            sc[nt][0] = fast_exp2(sc[nt][0] - mn0); sc[nt][1] = fast_exp2(sc[nt][1] - mn0);
+            sc[nt][2] = fast_exp2(sc[nt][2] - mn1); sc[nt][3] = fast_exp2(sc[nt][3] - mn1);
             ps0 += sc[nt][0] + sc[nt][1];
             ps1 += sc[nt][2] + sc[nt][3];
         }
@@ -288,7 +288,7 @@ __device__ __forceinline__ void ds_from_scores(float (&sc)[8][4], const float (&
             if (ROWS_ARE_QUERIES) { lsev = e < 2 ? rstat0 : rstat1; delv = e < 2 ? rdel0 : rdel1; }
             else { lsev = sL[cc]; delv = sD[cc]; }
             const float x = fmaf(sc[nt][e], LOG2E, b[e]);
-            const float p = (cc < L && rr < L) ? exp2f(x - lsev) : 0.f;
+            const float p = (cc < L && rr < L) ? fast_exp2(x - lsev) : 0.f;
             if (keep_p) pout[nt][e] = p;
             sc[nt][e] = p * (dpv[nt][e] - delv);
         }
@@ -605,7 +605,7 @@ attn_short_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
         load_row32(sq + j * ld + inner + h * 32, kv);
         const float x = dot32(q, kv) * LOG2E;
         const float mn = fmaxf(m, x);
-        const float r = exp2f(m - mn), p = exp2f(x - mn);
+        const float r = fast_exp2(m - mn), p = fast_exp2(x - mn);
         m = mn;
         l = l * r + p;
         load_row32(sq + j * ld + 2 * inner + h * 32, kv);
@@ -669,7 +669,7 @@ attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
             for (int j = 0; j < L; ++j) {
                 float kk[32];
                 load_row32f(sq + j * ld + inner + h * 32, kk);
-                Ph[i * PS + j] = exp2f(dot32(q, kk) * LOG2E - li);
+                Ph[i * PS + j] = fast_exp2(dot32(q, kk) * LOG2E - li);
             }
         } else if (wg == 1) {
             float dO[32];
