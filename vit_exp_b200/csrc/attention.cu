@@ -257,8 +257,9 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
 
 // dS for a 16x64 accumulator pair: sc <- p * (dp - delta), p = exp2(s*log2e + bias - lse)
 // (rows = the thread's fixed index pair, columns = the looped index). ROWS_ARE_QUERIES selects
-// which of (row, column) is the query for the bias / lse / delta lookups.
-template <bool ROWS_ARE_QUERIES>
+// which of (row, column) is the query for the bias / lse / delta lookups. MASKED adds the validity
+// tests needed when the sequence or the row block is padded.
+template <bool ROWS_ARE_QUERIES, bool MASKED>
 __device__ __forceinline__ void ds_from_scores(float (&sc)[8][4], const float (&dpv)[8][4], const BiasIdx& bias,
                                                bool has_bias, int c0, int t, int r0, int r1, int L,
                                                float rstat0, float rstat1, float rdel0, float rdel1,
@@ -269,9 +270,9 @@ __device__ __forceinline__ void ds_from_scores(float (&sc)[8][4], const float (&
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         const int c = c0 + nt * 8 + 2 * t;
-        const int2 pc = *reinterpret_cast<const int2*>(bias.pos + c);
         float b[4] = {0.f, 0.f, 0.f, 0.f};
         if (has_bias) {
+            const int2 pc = *reinterpret_cast<const int2*>(bias.pos + c);
             if (ROWS_ARE_QUERIES) {
                 b[0] = bias.tab[pr0 + bias.off - pc.x]; b[1] = bias.tab[pr0 + bias.off - pc.y];
                 b[2] = bias.tab[pr1 + bias.off - pc.x]; b[3] = bias.tab[pr1 + bias.off - pc.y];
@@ -280,17 +281,26 @@ __device__ __forceinline__ void ds_from_scores(float (&sc)[8][4], const float (&
                 b[2] = bias.tab[pc.x + bias.off - pr1]; b[3] = bias.tab[pc.y + bias.off - pr1];
             }
         }
+        float ls[4], dl[4];
+        if (ROWS_ARE_QUERIES) {
+            ls[0] = ls[1] = rstat0; ls[2] = ls[3] = rstat1;
+            dl[0] = dl[1] = rdel0; dl[2] = dl[3] = rdel1;
+        } else {
+            const float2 l2 = *reinterpret_cast<const float2*>(sL + c);
+            const float2 d2 = *reinterpret_cast<const float2*>(sD + c);
+            ls[0] = ls[2] = l2.x; ls[1] = ls[3] = l2.y;
+            dl[0] = dl[2] = d2.x; dl[1] = dl[3] = d2.y;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int cc = c + (e & 1);
-            const int rr = e < 2 ? r0 : r1;
-            float lsev, delv;
-            if (ROWS_ARE_QUERIES) { lsev = e < 2 ? rstat0 : rstat1; delv = e < 2 ? rdel0 : rdel1; }
-            else { lsev = sL[cc]; delv = sD[cc]; }
-            const float x = fmaf(sc[nt][e], LOG2E, b[e]);
-            const float p = (cc < L && rr < L) ? fast_exp2(x - lsev) : 0.f;
+            float p = fast_exp2(fmaf(sc[nt][e], LOG2E, b[e]) - ls[e]);
+            if (MASKED) {
+                const int cc = c + (e & 1);
+                const int rr = e < 2 ? r0 : r1;
+                if (!(cc < L && rr < L)) p = 0.f;
+            }
             if (keep_p) pout[nt][e] = p;
-            sc[nt][e] = p * (dpv[nt][e] - delv);
+            sc[nt][e] = p * (dpv[nt][e] - dl[e]);
         }
     }
 }
@@ -345,8 +355,11 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
         float sc[8][4], dpv[8][4];
         mma_16x64(sc, qa, tK, kb, lane);
         mma_16x64(dpv, da, tV, kb, lane);
-        ds_from_scores<true>(sc, dpv, bias, table != nullptr, kb, t, i0, i1, L, lse0, lse1, dl0, dl1, nullptr,
-                             nullptr, false, dpv);
+        // padded key columns must contribute nothing; padded query rows only feed their own (unstored) dq
+        if (Lp != L) ds_from_scores<true, true>(sc, dpv, bias, table != nullptr, kb, t, i0, i1, L, lse0, lse1, dl0, dl1,
+                                                nullptr, nullptr, false, dpv);
+        else ds_from_scores<true, false>(sc, dpv, bias, table != nullptr, kb, t, i0, i1, L, lse0, lse1, dl0, dl1,
+                                         nullptr, nullptr, false, dpv);
         mma_acc_16x32(dq, sc, tK, kb, lane);
     }
     __nv_bfloat16* ob = dqkv + (long long)s * L * ld + h * 32;
@@ -416,8 +429,11 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
         float st[8][4], dpt[8][4], pt[8][4];
         mma_16x64(st, ka, tQ, ib, lane);          // S^T[key, query] = K Q^T
         mma_16x64(dpt, va, tdO, ib, lane);        // dP^T[key, query] = V dO^T
-        ds_from_scores<false>(st, dpt, bias, table != nullptr, ib, t, j0, j1, L, 0.f, 0.f, 0.f, 0.f, sL, sD,
-                              true, pt);          // st <- dS^T, pt <- P^T
+        // st <- dS^T, pt <- P^T. Padded queries (columns) or keys (rows) must contribute nothing.
+        if (Lp != L || (L % KB) != 0)
+            ds_from_scores<false, true>(st, dpt, bias, table != nullptr, ib, t, j0, j1, L, 0.f, 0.f, 0.f, 0.f, sL, sD, true, pt);
+        else
+            ds_from_scores<false, false>(st, dpt, bias, table != nullptr, ib, t, j0, j1, L, 0.f, 0.f, 0.f, 0.f, sL, sD, true, pt);
         mma_acc_16x32(dv, pt, tdO, ib, lane);     // dV += P^T dO
         mma_acc_16x32(dk, st, tQ, ib, lane);      // dK += dS^T Q
     }
@@ -526,8 +542,10 @@ attn_bwd_dbias_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __rest
         const BiasIdx bias = make_bias(sT, sP, gh, gw);
         // columns are addressed globally (jb*64 + ...) for the bias / validity tests
         const float lse0 = sLs[r0] * LOG2E, lse1 = sLs[r1] * LOG2E;
-        ds_from_scores<true>(sc, dpv, bias, true, jb * 64, t, i0, i1, L, lse0, lse1, sDs[r0], sDs[r1], nullptr,
-                             nullptr, false, dpv);
+        if (Lp != L) ds_from_scores<true, true>(sc, dpv, bias, true, jb * 64, t, i0, i1, L, lse0, lse1, sDs[r0], sDs[r1],
+                                                nullptr, nullptr, false, dpv);
+        else ds_from_scores<true, false>(sc, dpv, bias, true, jb * 64, t, i0, i1, L, lse0, lse1, sDs[r0], sDs[r1],
+                                         nullptr, nullptr, false, dpv);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -583,47 +601,6 @@ __device__ __forceinline__ float dot32(const float (&a)[32], const float (&b)[32
     return s;
 }
 
-__global__ void __launch_bounds__(256)
-attn_short_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                      float* __restrict__ lse, int L, int heads) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem);
-    const int s = blockIdx.x;
-    const int inner = heads * 32, ld = 3 * inner;
-    const uint4* src = reinterpret_cast<const uint4*>(qkv + (long long)s * L * ld);
-    for (int i = threadIdx.x; i < L * ld / 8; i += blockDim.x) reinterpret_cast<uint4*>(sq)[i] = __ldg(src + i);
-    __syncthreads();
-    const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
-    if (h >= heads || i >= L) return;
-    float q[32], o[32];
-    load_row32(sq + i * ld + h * 32, q);
-#pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < L; ++j) {
-        float kv[32];
-        load_row32(sq + j * ld + inner + h * 32, kv);
-        const float x = dot32(q, kv) * LOG2E;
-        const float mn = fmaxf(m, x);
-        const float r = fast_exp2(m - mn), p = fast_exp2(x - mn);
-        m = mn;
-        l = l * r + p;
-        load_row32(sq + j * ld + 2 * inner + h * 32, kv);
-#pragma unroll
-        for (int d = 0; d < 32; ++d) o[d] = fmaf(p, kv[d], o[d] * r);
-    }
-    const float inv = 1.f / l;
-#pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] *= inv;
-    store_row32(out + ((long long)s * L + i) * inner + h * 32, o);
-    lse[((long long)s * heads + h) * L + i] = m * LN2 + logf(l);
-}
-
-// smem (all fp32, converted once while staging): qkv block [L][3 inner] | dO block [L][inner] |
-// P [heads][L][L+1] | dP [heads][L][L+1] | delta [heads][32]
-// 3*heads warps. Phase 1: group 0 (lane = query) fills P = softmax probabilities, group 1 fills
-// dP = dO v^T, group 2 computes delta. Phase 2: group 0 -> dq, group 1 -> dk, group 2 -> dv, each
-// thread owning one output row with dS_ij = P_ij (dP_ij - delta_i) formed on the fly.
 __device__ __forceinline__ void load_row32f(const float* p, float (&v)[32]) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -640,6 +617,46 @@ __device__ __forceinline__ void stage_bf16_as_f32(float* dst, const __nv_bfloat1
     }
 }
 
+__global__ void __launch_bounds__(256)
+attn_short_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                      float* __restrict__ lse, int L, int heads) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float* sq = reinterpret_cast<float*>(smem);             // fp32 copy of the sequence's qkv block
+    const int s = blockIdx.x;
+    const int inner = heads * 32, ld = 3 * inner;
+    stage_bf16_as_f32(sq, qkv + (long long)s * L * ld, L * ld / 8, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
+    if (h >= heads || i >= L) return;
+    float q[32], o[32];
+    load_row32f(sq + i * ld + h * 32, q);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < L; ++j) {
+        float kv[32];
+        load_row32f(sq + j * ld + inner + h * 32, kv);
+        const float x = dot32(q, kv) * LOG2E;
+        const float mn = fmaxf(m, x);
+        const float r = fast_exp2(m - mn), p = fast_exp2(x - mn);
+        m = mn;
+        l = l * r + p;
+        load_row32f(sq + j * ld + 2 * inner + h * 32, kv);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[d] = fmaf(p, kv[d], o[d] * r);
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] *= inv;
+    store_row32(out + ((long long)s * L + i) * inner + h * 32, o);
+    lse[((long long)s * heads + h) * L + i] = m * LN2 + logf(l);
+}
+
+// smem (all fp32, converted once while staging): qkv block [L][3 inner] | dO block [L][inner] |
+// P [heads][L][L+1] | dP [heads][L][L+1] | delta [heads][32]
+// 3*heads warps. Phase 1: group 0 (lane = query) fills P = softmax probabilities, group 1 fills
+// dP = dO v^T, group 2 computes delta. Phase 2: group 0 -> dq, group 1 -> dk, group 2 -> dv, each
+// thread owning one output row with dS_ij = P_ij (dP_ij - delta_i) formed on the fly.
 __global__ void __launch_bounds__(768, 1)
 attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                       const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
@@ -817,7 +834,7 @@ extern "C" int ctk_attn_fwd(const void* qkv, const float* table, void* out, floa
     auto q = reinterpret_cast<const __nv_bfloat16*>(qkv);
     auto o = reinterpret_cast<__nv_bfloat16*>(out);
     if (!table && L <= 32) {
-        const size_t sm = (size_t)L * 3 * heads * 32 * 2;
+        const size_t sm = (size_t)L * 3 * heads * 32 * 4;
         CTK_CUDA(cudaFuncSetAttribute(attn_short_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         attn_short_fwd_kernel<<<nseq, heads * 32, sm, s>>>(q, o, lse, L, heads);
         CTK_LAUNCH_CHECK();

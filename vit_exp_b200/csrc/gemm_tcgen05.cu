@@ -21,6 +21,7 @@
 // Fused epilogues replace the elementwise passes the reference runs as separate ATen kernels
 // (attention.py:45-58 GEGLU, :158-162 qk l2norm+scale, :443-450 residual adds).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -30,15 +31,20 @@ constexpr int BM = 128;          // UMMA M (cta_group::1: TMEM lane == output ro
 constexpr int BN = 256;          // UMMA N
 constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
-constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// single-CTA tiles: B = 256 rows (32 KB), 3 stages. CTA pairs (cta_group::2): each CTA stages its own
+// 128 rows of A and HALF of the 256-row B tile (16 KB) -> 4 stages and 1/3 less L2->SM traffic.
+template <bool PAIR> struct Cfg {
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = PAIR ? 4 : 3;
+};
 constexpr int NEPI = 8;                // epilogue warps
 constexpr int SLOT_BYTES = 2048;       // one 32x32 bf16 block; an fp32 block takes two slots
 constexpr int SLOTS_PER_WARP = 4;
 constexpr int STAGING_BYTES = NEPI * SLOTS_PER_WARP * SLOT_BYTES;   // 64 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 3 * (A_BYTES + BN * BK * 2) + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(4 * (A_BYTES + (BN / 2) * BK * 2) <= 3 * (A_BYTES + BN * BK * 2), "pair ring must fit the same budget");
 constexpr int NTHREADS = 32 * (4 + NEPI);
 
 struct EpiParams {
@@ -320,33 +326,40 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
     }
 }
 
-template <int EPI, bool A_MN, bool B_MN>
+template <int EPI, bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c0, const __grid_constant__ CUtensorMap tmap_c1,
             int M, int N, int K, int splits, EpiParams ep) {
+    constexpr int STAGES = Cfg<PAIR>::STAGES;
+    constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
+    constexpr int BN_LOCAL = PAIR ? BN / 2 : BN;                 // B rows staged by this CTA
+    constexpr int ROWS_PER_ITEM = PAIR ? 2 * BM : BM;            // output rows per work item
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* staging = smem + STAGES * STAGE_BYTES;                       // 1024-byte aligned
+    uint8_t* staging = smem + 3 * (A_BYTES + BN * BK * 2);                // 1024-byte aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
-    uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
-    uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
-    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
-    uint64_t* epi_bar = bars + 2 * STAGES + 4;    // [NEPI]    TMA loads of the epilogue warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NEPI);
+    uint64_t* full_bar = bars;                    // [4]  TMA -> MMA        (pair: leader's are used)
+    uint64_t* empty_bar = bars + 4;               // [4]  MMA -> TMA        (pair: multicast commit)
+    uint64_t* tfull_bar = bars + 8;               // [2]  MMA -> epilogue   (pair: multicast commit)
+    uint64_t* tempty_bar = bars + 10;             // [2]  epilogue -> MMA   (pair: leader's, both CTAs arrive)
+    uint64_t* epi_bar = bars + 12;                // [NEPI] TMA loads of the epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + NEPI);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;          // 0 = leader of the pair
+    const int unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;        // scheduling unit (CTA or CTA pair)
+    const int nunits = PAIR ? gridDim.x >> 1 : gridDim.x;
 
-    const int m_tiles = (M + BM - 1) / BM;
+    const int m_tiles = (M + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM;
     const int n_tiles = (N + BN - 1) / BN;
     const long long mn_tiles = (long long)m_tiles * n_tiles;
     const int kb_total = (K + BK - 1) / BK;
     const int kb_per = (kb_total + splits - 1) / splits;
     const long long total_work = mn_tiles * splits;
-    // work item w -> tile = w % mn_tiles (n fastest), split = w / mn_tiles: CTAs that run together
+    // work item w -> tile = w % mn_tiles (n fastest), split = w / mn_tiles: units that run together
     // share the k-range (operands hit L2) and cover different output tiles.
 
     if (warp == 0 && lane == 0) {
@@ -362,65 +375,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], NEPI);
+            mbar_init(&tempty_bar[i], PAIR ? 2 * NEPI : NEPI);
         }
         for (int i = 0; i < NEPI; ++i) mbar_init(&epi_bar[i], 1);
         mbar_fence_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs of a pair load their own halves) ==========
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (long long w = unit; w < total_work; w += nunits) {
                 const int split = (int)(w / mn_tiles);
                 const long long t = w % mn_tiles;
                 const int n_blk = (int)(t % n_tiles), m_blk = (int)(t / n_tiles);
+                const int m0 = m_blk * ROWS_PER_ITEM + (int)rank * BM;
+                const int n0 = n_blk * BN + (int)rank * BN_LOCAL;
                 const int kb0 = split * kb_per;
                 const int kb1 = min(kb0 + kb_per, kb_total);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-                    } else {
+                    if constexpr (PAIR) {
+                        // bytes of both CTAs land on the leader's barrier
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                        if constexpr (!A_MN) {
+                            tma_load_2d_pair(sa, &tmap_a, fb, kb * BK, m0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)
-                            tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage],
-                                        m_blk * BM + j * 64, kb * BK);
-                    }
-                    if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
-                    } else {
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_2d_pair(sa + j * (BK * 128), &tmap_a, fb, m0 + j * 64, kb * BK);
+                        }
+                        if constexpr (!B_MN) {
+                            tma_load_2d_pair(sb, &tmap_b, fb, kb * BK, n0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage],
-                                        n_blk * BN + j * 64, kb * BK);
+                            for (int j = 0; j < BN_LOCAL / 64; ++j)
+                                tma_load_2d_pair(sb + j * (BK * 128), &tmap_b, fb, n0 + j * 64, kb * BK);
+                        }
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        if constexpr (!A_MN) {
+                            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m0 + j * 64, kb * BK);
+                        }
+                        if constexpr (!B_MN) {
+                            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN_LOCAL / 64; ++j)
+                                tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, kb * BK);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        // ===================== MMA issuer (leader CTA only for a pair) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (long long w = unit; w < total_work; w += nunits) {
                 const int split = (int)(w / mn_tiles);
                 const int kb0 = split * kb_per;
                 const int kb1 = min(kb0 + kb_per, kb_total);
@@ -442,12 +475,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         const uint64_t bdesc =
                             B_MN ? umma_desc_sw128(sb + k * (UK * 128), BK * 128, 1024)
                                  : umma_desc_sw128(sb + k * (UK * 2), 16, 1024);
-                        tc_mma_f16(tacc, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if constexpr (PAIR) tc_mma_f16_pair(tacc, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else tc_mma_f16(tacc, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(&empty_bar[stage]);      // frees the smem slot when MMAs retire
+                    // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+                    if constexpr (PAIR) tc_commit_pair_mc(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[acc]);            // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps (of both CTAs)
+                if constexpr (PAIR) tc_commit_pair_mc(&tfull_bar[acc], 3); else tc_commit(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -463,24 +499,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         sg.lane = lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long long w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (long long w = unit; w < total_work; w += nunits) {
             const long long t = w % mn_tiles;
             const int n_blk = (int)(t % n_tiles), m_blk = (int)(t / n_tiles);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
-            run_epilogue<EPI>(ep, &tmap_c0, &tmap_c1, sg, t_row, m_blk * BM + quarter * 32, hf, n_blk * BN, M, N);
+            run_epilogue<EPI>(ep, &tmap_c0, &tmap_c1, sg, t_row,
+                              m_blk * ROWS_PER_ITEM + (int)rank * BM + quarter * 32, hf, n_blk * BN, M, N);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) bulk_wait_all();                 // all TMA stores of this warp have landed
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -529,25 +571,42 @@ int make_block_tmap(CUtensorMap* m, const void* ptr, bool f32, long long cols, l
     return make_tmap(m, ptr, f32, cols, rows, ld, 32, 32, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
-template <int EPI, bool A_MN, bool B_MN>
+template <int EPI, bool A_MN, bool B_MN, bool PAIR>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc0, const CUtensorMap& tc1, int M,
            int N, int K, int splits, const EpiParams& ep, cudaStream_t stream) {
-    auto kern = gemm_kernel<EPI, A_MN, B_MN>;
+    auto kern = gemm_kernel<EPI, A_MN, B_MN, PAIR>;
     static bool configured = false;
     if (!configured) {
         CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
-    const long long work = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
-    const int grid = (int)(work < ctk_num_sms() ? work : ctk_num_sms());
-    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(ta, tb, tc0, tc1, M, N, K, splits, ep);
+    const int rows = PAIR ? 2 * BM : BM;
+    const long long work = (long long)((M + rows - 1) / rows) * ((N + BN - 1) / BN) * splits;
+    const int sms = ctk_num_sms();
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    if (PAIR) {
+        const long long units = work < sms / 2 ? work : sms / 2;
+        cfg.gridDim = dim3((unsigned)(2 * units));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3((unsigned)(work < sms ? work : sms));
+    }
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    CTK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc0, tc1, M, N, K, splits, ep));
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
 
 // split-K factor for the atomic (weight gradient) epilogue: fill whole waves of SMs
-int pick_splits(long long tiles, int kb_total) {
-    const int sms = ctk_num_sms();
+int pick_splits(long long tiles, int kb_total, int sms) {
     int max_splits = kb_total / 4;
     if (max_splits < 1) max_splits = 1;
     if (max_splits > 64) max_splits = 64;
@@ -589,7 +648,9 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (epilogue != CTK_EPI_ATOMIC_F32) {
         splits = 1;
     } else if (splits <= 0) {
-        splits = pick_splits((long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN), kb_total);
+        const int rows_item = (M > BM) ? 2 * BM : BM;     // CTA pairs own 256 rows
+        splits = pick_splits((long long)((M + rows_item - 1) / rows_item) * ((N + BN - 1) / BN), kb_total,
+                             M > BM ? ctk_num_sms() / 2 : ctk_num_sms());
     }
     if (splits > kb_total) splits = kb_total;
     {   // every split must own at least one k-block
@@ -607,11 +668,18 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
         CTK_REQUIRE(e->aux0 && e->vec0 && e->i0 % 32 == 0 && e->i1 % 32 == 0 && e->i0 <= N,
                     CTK_ERR_SHAPE, "gemm: QKV epilogue needs rnorm buffer, scale vector, 32-aligned i0/i1");
 
+    // CTA pairs (cta_group::2) unless disabled (CTK_GEMM_PAIR=0) or the problem is a single tile row
+    static int pair_env = -1;
+    if (pair_env < 0) {
+        const char* v = getenv("CTK_GEMM_PAIR");
+        pair_env = (v && v[0] == '0') ? 0 : 1;
+    }
+    const bool pair = pair_env == 1 && M > BM;
     CUtensorMap ta, tb, tc0, tc1;
     if (!a_mn_major) {
         rc = make_tmap(&ta, A, false, K, M, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);   // [M rows][K]
         if (rc) return rc;
-        rc = make_tmap(&tb, B, false, K, N, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);   // [N rows][K]
+        rc = make_tmap(&tb, B, false, K, N, ldb, BK, pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);   // [N rows][K]
         if (rc) return rc;
     } else {
         rc = make_tmap(&ta, A, false, M, K, lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);   // [K rows][M]
@@ -651,10 +719,13 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     }
     if (rc) return rc;
 
-#define CTK_GEMM_CASE(E)                                                                         \
-    case E:                                                                                      \
-        return a_mn_major ? launch<E, true, true>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream) \
-                          : launch<E, false, false>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream);
+#define CTK_GEMM_CASE(E)                                                                                   \
+    case E:                                                                                                \
+        if (pair)                                                                                          \
+            return a_mn_major ? launch<E, true, true, true>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream)   \
+                              : launch<E, false, false, true>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream); \
+        return a_mn_major ? launch<E, true, true, false>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream)      \
+                          : launch<E, false, false, false>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream);
     switch (epilogue) {
         CTK_GEMM_CASE(CTK_EPI_BF16)
         CTK_GEMM_CASE(CTK_EPI_F32)
