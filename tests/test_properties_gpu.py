@@ -50,14 +50,15 @@ def test_loss_stable_beyond_reference_overflow(cuda_dev):
     from vit_exp_b200 import ops
     N, d = 64, 512
     T = _lat(N, d, 0, cuda_dev)
-    I = T.clone()                                  # matched pairs: diagonal logits reach exp(log_temp)
+    # nearly matched pairs: diagonal logits reach ~exp(log_temp)
+    I = F.normalize(T + 0.05 * torch.randn(N, d, generator=_g(9)).to(cuda_dev), dim=-1)
     for lt, ref_finite in ((4.4, True), (6.0, False)):
         out, _ = ops.clip_loss_fwd_bwd(T, I, torch.full((1,), lt, device=cuda_dev), 8, 0)
         ref32 = orc.clip_loss_reference_form(T.cpu(), I.cpu(), torch.tensor(lt), 8)
         exact = orc.clip_loss_open_clip(T.cpu().double(), I.cpu().double(), torch.tensor(lt).double().exp()) / 8
         assert torch.isfinite(ref32).item() == ref_finite
         assert torch.isfinite(out[0]).item()
-        assert abs(out[0].item() - exact.item()) < 1e-4 * abs(exact.item())
+        assert abs(out[0].item() - exact.item()) <= 1e-4 * abs(exact.item()) + 1e-7
 
 
 def test_peg_is_causal_along_axis0(cuda_dev):

@@ -118,7 +118,6 @@ struct BiasIdx {
     const int* pos;        // shared memory, [Lp]
     int off;
     __device__ __forceinline__ int index(int i, int j) const { return pos[i] + off - pos[j]; }
-    __device__ __forceinline__ float operator()(int i, int j) const { return tab ? tab[index(i, j)] : 0.f; }
 };
 
 __device__ __forceinline__ void fill_pos(int* pos, int Lp, int L, int gw, int tid, int nthreads) {
@@ -199,13 +198,13 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__
         }
         mx0 = quad_max(mx0); mx1 = quad_max(mx1);
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float r0 = fast_exp2(m0 - mn0), r1 = fast_exp2(m1 - mn1);
+        const float r0 = exp2f(m0 - mn0), r1 = exp2f(m1 - mn1);
         m0 = mn0; m1 = mn1;
         float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            sc[nt][0] = fast_exp2(sc[nt][0] - mn0); sc[nt][1] = fast_exp2(sc[nt][1] - mn0);
-            sc[nt][2] = fast_exp2(sc[nt][2] - mn1); sc[nt][3] = fast_exp2(sc[nt][3] - mn1);
+            sc[nt][0] = exp2f(sc[nt][0] - mn0); sc[nt][1] = exp2f(sc[nt][1] - mn0);
+            sc[nt][2] = exp2f(sc[nt][2] - mn1); sc[nt][3] = exp2f(sc[nt][3] - mn1);
             ps0 += sc[nt][0] + sc[nt][1];
             ps1 += sc[nt][2] + sc[nt][3];
         }

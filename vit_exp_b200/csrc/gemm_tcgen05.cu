@@ -43,7 +43,7 @@ constexpr int NEPI = 8;                // epilogue warps
 constexpr int SLOT_BYTES = 2048;       // one 32x32 bf16 block; an fp32 block takes two slots
 constexpr int SLOTS_PER_WARP = 4;
 constexpr int STAGING_BYTES = NEPI * SLOTS_PER_WARP * SLOT_BYTES;   // 64 KB
-constexpr int SMEM_BYTES = 3 * (A_BYTES + BN * BK * 2) + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 3 * (A_BYTES + BN * BK * 2) + STAGING_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 static_assert(4 * (A_BYTES + (BN / 2) * BK * 2) <= 3 * (A_BYTES + BN * BK * 2), "pair ring must fit the same budget");
 constexpr int NTHREADS = 32 * (4 + NEPI);
 
@@ -121,24 +121,26 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // Per-warp staging context. All lanes call the methods; lane 0 talks to the TMA engine.
 struct Stager {
     uint8_t* base;        // SLOTS_PER_WARP * SLOT_BYTES, 1024-byte aligned
-    uint64_t* bar;        // this warp's mbarrier for TMA loads
-    uint32_t phase;
+    uint64_t* bar;        // this warp's two mbarriers for TMA loads (double-buffered prefetch)
+    uint32_t phase[2];
     int lane;
     // make the slots reusable: all earlier stores have finished reading shared memory
     __device__ __forceinline__ void begin() {
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
     }
-    // TMA-load `n` blocks (each `bytes`) described by (map, c0[i], c1) into slots `slot0 + i*step`
-    __device__ __forceinline__ void load2(const CUtensorMap* m, int slot_a, int ca, int slot_b, int cb, int row0,
-                                          int bytes_each, int nblocks) {
+    // start TMA loads of 1 or 2 blocks (`bytes_each` each) into slot_a / slot_b, tracked by barrier `which`
+    __device__ __forceinline__ void issue_load(int which, const CUtensorMap* m, int slot_a, int ca, int slot_b, int cb,
+                                               int row0, int bytes_each, int nblocks) {
         if (lane == 0) {
-            mbar_expect_tx(bar, bytes_each * nblocks);
-            tma_load_2d(base + slot_a * SLOT_BYTES, m, bar, ca, row0);
-            if (nblocks > 1) tma_load_2d(base + slot_b * SLOT_BYTES, m, bar, cb, row0);
+            mbar_expect_tx(&bar[which], bytes_each * nblocks);
+            tma_load_2d(base + slot_a * SLOT_BYTES, m, &bar[which], ca, row0);
+            if (nblocks > 1) tma_load_2d(base + slot_b * SLOT_BYTES, m, &bar[which], cb, row0);
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
+    }
+    __device__ __forceinline__ void wait_load(int which) {
+        mbar_wait(&bar[which], phase[which]);
+        phase[which] ^= 1;
     }
     // publish the generic-proxy writes of the whole warp, then store slot -> global
     __device__ __forceinline__ void fence() {
@@ -200,36 +202,44 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
             sg.commit();
         }
     } else if constexpr (EPI == CTK_EPI_F32 || EPI == CTK_EPI_RESID_F32) {
-#pragma unroll 1
-        for (int cc = 0; cc < 128; cc += 64) {
+        // four 32-column fp32 blocks per warp; block i lives in slots 2*(i&1), 2*(i&1)+1 (4 KB) and the
+        // residual block i+1 is prefetched by TMA while block i is processed
+        constexpr bool RES = EPI == CTK_EPI_RESID_F32;
+        const int cbase = n0 + hf * 128;
+        int nvalid = (N - cbase + 31) / 32;
+        nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
+        if (nvalid > 0) {
             sg.begin();
-            const int cA = hf * 128 + cc, cB = cA + 32;
-            if (n0 + cA >= N) break;
-            const int nblk = (n0 + cB < N) ? 2 : 1;
-            if constexpr (EPI == CTK_EPI_RESID_F32) sg.load2(mc1, 0, n0 + cA, 2, n0 + cB, row0, 4096, nblk);
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                if (h2 >= nblk) break;
-                const int c = cA + h2 * 32;
-                const int col = n0 + c;
-                uint8_t* slot = sg.base + h2 * 2 * SLOT_BYTES;
+            if (RES) sg.issue_load(0, mc1, 0, cbase, 0, 0, row0, 4096, 1);
+#pragma unroll 1
+            for (int i = 0; i < nvalid; ++i) {
+                const int par = i & 1;
+                const int col = cbase + i * 32;
+                uint8_t* slot = sg.base + par * 2 * SLOT_BYTES;
+                if (i + 1 < nvalid) {
+                    if (i >= 1) sg.begin();                 // block i-1's store has left the other buffer
+                    if (RES) sg.issue_load(par ^ 1, mc1, (par ^ 1) * 2, col + 32, 0, 0, row0, 4096, 1);
+                } else if (!RES && i >= 2) {
+                    sg.begin();
+                }
                 float v[32];
-                ld_acc(t_row + c, v);
+                ld_acc(t_row + hf * 128 + i * 32, v);
                 if (p.bias) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+                    for (int q = 0; q < 32; ++q) v[q] += __ldg(p.bias + col + q);
                 }
-                if constexpr (EPI == CTK_EPI_RESID_F32) {
+                if (RES) {
+                    sg.wait_load(par);
                     float r[32];
                     slot_read_f32(slot, lane, r);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += r[i];
+                    for (int q = 0; q < 32; ++q) v[q] += r[q];
                 }
                 slot_write_f32(slot, lane, v);
                 sg.fence();
-                sg.store(mc0, h2 * 2, col, row0);
+                sg.store(mc0, par * 2, col, row0);
+                sg.commit();
             }
-            sg.commit();
         }
     } else if constexpr (EPI == CTK_EPI_GEGLU) {
         // tile columns [0,128) = value rows, [128,256) = gate rows of 128 hidden units (weights were
@@ -246,7 +256,11 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
             slot_write_bf16(sg.base, lane, val);
             slot_write_bf16(sg.base + SLOT_BYTES, lane, gate);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) val[i] = gelu_erf(gate[i]) * val[i];
+            for (int i = 0; i < 32; ++i) {
+                float cdf, pdf;
+                normal_cdf_pdf(gate[i], cdf, pdf);
+                val[i] = gate[i] * cdf * val[i];                 // gelu(gate) * value
+            }
             slot_write_bf16(sg.base + 2 * SLOT_BYTES, lane, val);
             sg.fence();
             sg.store(mc0, 0, n0 + c, row0);
@@ -256,32 +270,47 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
         }
     } else if constexpr (EPI == CTK_EPI_GEGLU_BWD) {
         // accumulator = dH for hidden units [n0, n0+256); mc1 = U (value|gate interleaved per 128
-        // units); mc0 = dU in the same interleaved layout.
-#pragma unroll 1
-        for (int cc = 0; cc < 128; cc += 32) {
-            const int c = hf * 128 + cc;
-            const int unit = n0 + c;
-            if (unit >= N) break;
+        // units); mc0 = dU in the same interleaved layout. Chunk i (32 units) uses slots 2*(i&1),
+        // 2*(i&1)+1; the U blocks of chunk i+1 are prefetched while chunk i is processed.
+        const int ubase = n0 + hf * 128;
+        int nvalid = (N - ubase + 31) / 32;
+        nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
+        auto ucol_of = [&](int i) { const int unit = ubase + i * 32; return (unit / 128) * 256 + (unit % 128); };
+        if (nvalid > 0) {
             sg.begin();
-            const int ucol = (unit / 128) * 256 + (unit % 128);
-            sg.load2(mc1, 0, ucol, 1, ucol + 128, row0, SLOT_BYTES, 2);
-            float dh[32], val[32], gate[32];
-            ld_acc(t_row + c, dh);
-            slot_read_bf16(sg.base, lane, val);
-            slot_read_bf16(sg.base + SLOT_BYTES, lane, gate);
+            sg.issue_load(0, mc1, 0, ucol_of(0), 1, ucol_of(0) + 128, row0, SLOT_BYTES, 2);
+#pragma unroll 1
+            for (int i = 0; i < nvalid; ++i) {
+                const int par = i & 1;
+                const int ucol = ucol_of(i);
+                if (i + 1 < nvalid) {
+                    if (i >= 1) sg.begin();                 // chunk i-1's stores have left the other buffer
+                    sg.issue_load(par ^ 1, mc1, (par ^ 1) * 2, ucol_of(i + 1), (par ^ 1) * 2 + 1, ucol_of(i + 1) + 128,
+                                  row0, SLOT_BYTES, 2);
+                }
+                float dh[32], val[32], gate[32];
+                ld_acc(t_row + hf * 128 + i * 32, dh);
+                sg.wait_load(par);
+                uint8_t* sv = sg.base + (par * 2) * SLOT_BYTES;
+                uint8_t* sgt = sv + SLOT_BYTES;
+                slot_read_bf16(sv, lane, val);
+                slot_read_bf16(sgt, lane, gate);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float dv = dh[i] * gelu_erf(gate[i]);
-                const float dg = dh[i] * val[i] * gelu_erf_grad(gate[i]);
-                val[i] = dv;
-                gate[i] = dg;
+                for (int q = 0; q < 32; ++q) {
+                    float cdf, pdf;
+                    normal_cdf_pdf(gate[q], cdf, pdf);
+                    const float dv = dh[q] * gate[q] * cdf;                          // dh * gelu(gate)
+                    const float dg = dh[q] * val[q] * fmaf(gate[q], pdf, cdf);       // dh * value * gelu'(gate)
+                    val[q] = dv;
+                    gate[q] = dg;
+                }
+                slot_write_bf16(sv, lane, val);
+                slot_write_bf16(sgt, lane, gate);
+                sg.fence();
+                sg.store(mc0, par * 2, ucol, row0);
+                sg.store(mc0, par * 2 + 1, ucol + 128, row0);
+                sg.commit();
             }
-            slot_write_bf16(sg.base, lane, val);
-            slot_write_bf16(sg.base + SLOT_BYTES, lane, gate);
-            sg.fence();
-            sg.store(mc0, 0, ucol, row0);
-            sg.store(mc0, 1, ucol + 128, row0);
-            sg.commit();
         }
     } else if constexpr (EPI == CTK_EPI_ATOMIC_F32) {
         float* C = reinterpret_cast<float*>(p.C);
@@ -295,9 +324,19 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
             ld_acc(t_row + c, v);
             if (orow < 0) continue;
             float* dst = C + orow * p.ldc + col;
+            if ((p.ldc & 3) == 0 && col + 32 <= N) {
+                // 16-byte vector reductions: 8 instead of 32 atomics per thread and chunk
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (col + i < N) atomicAdd(dst + i, v[i] * p.alpha);
+                for (int i = 0; i < 32; i += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
+                                 "f"(v[i] * p.alpha), "f"(v[i + 1] * p.alpha), "f"(v[i + 2] * p.alpha),
+                                 "f"(v[i + 3] * p.alpha)
+                                 : "memory");
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (col + i < N) atomicAdd(dst + i, v[i] * p.alpha);
+            }
         }
     } else if constexpr (EPI == CTK_EPI_ARGMAX) {
         // per-row running arg-max over all N columns: 64-bit atomicMax of
@@ -344,8 +383,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint64_t* empty_bar = bars + 4;               // [4]  MMA -> TMA        (pair: multicast commit)
     uint64_t* tfull_bar = bars + 8;               // [2]  MMA -> epilogue   (pair: multicast commit)
     uint64_t* tempty_bar = bars + 10;             // [2]  epilogue -> MMA   (pair: leader's, both CTAs arrive)
-    uint64_t* epi_bar = bars + 12;                // [NEPI] TMA loads of the epilogue warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + NEPI);
+    uint64_t* epi_bar = bars + 12;                // [2 * NEPI] TMA loads of the epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * NEPI);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -377,7 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], PAIR ? 2 * NEPI : NEPI);
         }
-        for (int i = 0; i < NEPI; ++i) mbar_init(&epi_bar[i], 1);
+        for (int i = 0; i < 2 * NEPI; ++i) mbar_init(&epi_bar[i], 1);
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -494,8 +533,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int hf = ew >> 2;                         // column half of the tile
         Stager sg;
         sg.base = staging + ew * (SLOTS_PER_WARP * SLOT_BYTES);
-        sg.bar = &epi_bar[ew];
-        sg.phase = 0;
+        sg.bar = &epi_bar[2 * ew];
+        sg.phase[0] = sg.phase[1] = 0;
         sg.lane = lane;
         int acc = 0;
         uint32_t acc_phase = 0;

@@ -129,6 +129,8 @@ class CTCLIP(nn.Module):
         self.to_visual_latent_extra = copy.deepcopy(self.to_visual_latent)
         self.tokenizer = tokenizer       # the reference downloads CXR-BERT's tokenizer here (ct_clip.py:650)
         self.fix_text_encoder = config.get("fix_text_encoder", False)
+        self.overlap_text_encoder = config.get("overlap_text_encoder", True)
+        self._side_stream = None
         if self.fix_text_encoder:
             for p in self.text_transformer.parameters():
                 p.requires_grad = False
@@ -148,6 +150,24 @@ class CTCLIP(nn.Module):
             self.text_transformer.eval()
         return self.text_transformer(text.input_ids, attention_mask=text.attention_mask)[0]
 
+    def _encode_both(self, text, image):
+        """Text tower (stock PyTorch, hundreds of small kernels) on a side stream while the image
+        encoder (libctk) runs on the current stream; autograd replays each backward on the stream of
+        its forward, so the two towers overlap in both directions. Results are identical."""
+        if not (self.overlap_text_encoder and image.is_cuda):
+            return self._encode_text(text), self.visual_transformer(image, return_encoded_tokens=True)
+        cur = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=image.device)
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            enc_text = self._encode_text(text)
+        enc_image = self.visual_transformer(image, return_encoded_tokens=True)
+        cur.wait_stream(side)
+        enc_text.record_stream(cur)
+        return enc_text, enc_image
+
     def forward(self, batch, device=None, accelerator=None, **kwargs):
         if batch["data_type"][0] == "imagereport":
             return self.forward_batch_image_report(batch, device=device, accelerator=accelerator, **kwargs)
@@ -158,8 +178,7 @@ class CTCLIP(nn.Module):
         """ct_clip.py:1252-1388."""
         assert accelerator is not None, "accelerator is not provided"
         text, image = batch["text"], batch["image"]
-        enc_text = self._encode_text(text)
-        enc_image = self.visual_transformer(image, return_encoded_tokens=True)       # (B, t, h, w, C)
+        enc_text, enc_image = self._encode_both(text, image)                        # (B, L, dt), (B, t, h, w, C)
         loss, _, _ = _ClipHead.apply(enc_text[:, 0, :], enc_image, self.to_text_latent.weight,
                                      self.to_visual_latent.weight, self.temperature, accelerator)
         return loss, {"cl_loss": loss.item()}      # the reference also syncs here (ct_clip.py:1384)
