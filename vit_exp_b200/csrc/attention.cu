@@ -15,6 +15,7 @@
 // NOTE: this round the long-sequence path uses the legacy mma.sync tensor-core path; moving it to
 // tcgen05/TMEM is tracked in DESIGN.md (attention is ~5% of the encoder FLOPs).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -656,50 +657,80 @@ attn_short_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 // 3*heads warps. Phase 1: group 0 (lane = query) fills P = softmax probabilities, group 1 fills
 // dP = dO v^T, group 2 computes delta. Phase 2: group 0 -> dq, group 1 -> dk, group 2 -> dv, each
 // thread owning one output row with dS_ij = P_ij (dP_ij - delta_i) formed on the fly.
-__global__ void __launch_bounds__(768, 1)
+// One CTA = (sequence, group of HG <= 4 heads): 3*HG warps, ~70 KB of shared memory -> 2-3 CTAs / SM so
+// the staging of one CTA overlaps the arithmetic of the others.
+__global__ void __launch_bounds__(384, 2)
 attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                       const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                      __nv_bfloat16* __restrict__ dqkv, int L, int heads) {
+                      __nv_bfloat16* __restrict__ dqkv, int L, int heads, int HG) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int inner = heads * 32, ld = 3 * inner;
+    const int gw = HG * 32;                                  // channels of the head group
+    const int lds = 3 * gw;                                  // smem row: [q | k | v] of the group
     const int PS = L + 1;
     float* sq = reinterpret_cast<float*>(smem);
-    float* sdo = sq + L * ld;
-    float* sP = sdo + L * inner;
-    float* sdP = sP + heads * L * PS;
-    float* sD = sdP + heads * L * PS;
-    const int s = blockIdx.x;
-    stage_bf16_as_f32(sq, qkv + (long long)s * L * ld, L * ld / 8, threadIdx.x, blockDim.x);
-    stage_bf16_as_f32(sdo, dout + (long long)s * L * inner, L * inner / 8, threadIdx.x, blockDim.x);
-    const int wg = (threadIdx.x >> 5) / heads;              // warp group 0..2
-    const int h = (threadIdx.x >> 5) % heads, i = threadIdx.x & 31;
+    float* sdo = sq + L * lds;
+    float* sP = sdo + L * gw;
+    float* sdP = sP + HG * L * PS;
+    float* sD = sdP + HG * L * PS;
+    const int ngroups = heads / HG;
+    const int s = blockIdx.x / ngroups, hg = blockIdx.x % ngroups;
+    const int h0 = hg * HG;
+    // stage the group's q, k, v and dO as fp32: 8-element (16-byte) chunks
+    {
+        const int cpr = gw / 8;                              // chunks per (row, part)
+        for (int i = threadIdx.x; i < L * 3 * cpr; i += blockDim.x) {
+            const int c8 = i % cpr, part = (i / cpr) % 3, row = i / (3 * cpr);
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(
+                qkv + ((long long)s * L + row) * ld + part * inner + h0 * 32 + c8 * 8));
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+            float4* dst = reinterpret_cast<float4*>(sq + row * lds + part * gw + c8 * 8);
+            dst[0] = make_float4(a.x, a.y, b.x, b.y);
+            dst[1] = make_float4(c.x, c.y, d.x, d.y);
+        }
+        for (int i = threadIdx.x; i < L * cpr; i += blockDim.x) {
+            const int c8 = i % cpr, row = i / cpr;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(dout + ((long long)s * L + row) * inner + h0 * 32 + c8 * 8));
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+            float4* dst = reinterpret_cast<float4*>(sdo + row * gw + c8 * 8);
+            dst[0] = make_float4(a.x, a.y, b.x, b.y);
+            dst[1] = make_float4(c.x, c.y, d.x, d.y);
+        }
+    }
+    const int wg = (threadIdx.x >> 5) / HG;                 // warp group 0..2
+    const int hl = (threadIdx.x >> 5) % HG, i = threadIdx.x & 31;
+    const int h = h0 + hl;
     const bool active = i < L;
-    float* Ph = sP + h * L * PS;
-    float* dPh = sdP + h * L * PS;
+    float* Ph = sP + hl * L * PS;
+    float* dPh = sdP + hl * L * PS;
+    const float* qrow = sq + hl * 32;                       // + row * lds
+    const float* krow = sq + gw + hl * 32;
+    const float* vrow = sq + 2 * gw + hl * 32;
+    const float* dorow = sdo + hl * 32;                     // + row * gw
     __syncthreads();
     if (active) {
         if (wg == 0) {
             float q[32];
-            load_row32f(sq + i * ld + h * 32, q);
+            load_row32f(qrow + i * lds, q);
             const float li = lse[((long long)s * heads + h) * L + i] * LOG2E;
             for (int j = 0; j < L; ++j) {
                 float kk[32];
-                load_row32f(sq + j * ld + inner + h * 32, kk);
+                load_row32f(krow + j * lds, kk);
                 Ph[i * PS + j] = fast_exp2(dot32(q, kk) * LOG2E - li);
             }
         } else if (wg == 1) {
             float dO[32];
-            load_row32f(sdo + i * inner + h * 32, dO);
+            load_row32f(dorow + i * gw, dO);
             for (int j = 0; j < L; ++j) {
                 float vv[32];
-                load_row32f(sq + j * ld + 2 * inner + h * 32, vv);
+                load_row32f(vrow + j * lds, vv);
                 dPh[i * PS + j] = dot32(dO, vv);
             }
         } else {
             float a[32], b[32];
             load_row32(out + ((long long)s * L + i) * inner + h * 32, a);
-            load_row32f(sdo + i * inner + h * 32, b);
-            sD[h * 32 + i] = dot32(a, b);
+            load_row32f(dorow + i * gw, b);
+            sD[hl * 32 + i] = dot32(a, b);
         }
     }
     __syncthreads();
@@ -708,10 +739,10 @@ attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
 #pragma unroll
     for (int d = 0; d < 32; ++d) acc[d] = 0.f;
     if (wg == 0) {                                           // dq_i = sum_j dS_ij k_j
-        const float di = sD[h * 32 + i];
+        const float di = sD[hl * 32 + i];
         for (int j = 0; j < L; ++j) {
             float kk[32];
-            load_row32f(sq + j * ld + inner + h * 32, kk);
+            load_row32f(krow + j * lds, kk);
             const float ds = Ph[i * PS + j] * (dPh[i * PS + j] - di);
 #pragma unroll
             for (int d = 0; d < 32; ++d) acc[d] = fmaf(ds, kk[d], acc[d]);
@@ -720,8 +751,8 @@ attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
     } else if (wg == 1) {                                    // dk_j = sum_i dS_ij q_i   (lane = j)
         for (int qi = 0; qi < L; ++qi) {
             float q[32];
-            load_row32f(sq + qi * ld + h * 32, q);
-            const float ds = Ph[qi * PS + i] * (dPh[qi * PS + i] - sD[h * 32 + qi]);
+            load_row32f(qrow + qi * lds, q);
+            const float ds = Ph[qi * PS + i] * (dPh[qi * PS + i] - sD[hl * 32 + qi]);
 #pragma unroll
             for (int d = 0; d < 32; ++d) acc[d] = fmaf(ds, q[d], acc[d]);
         }
@@ -729,7 +760,7 @@ attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
     } else {                                                 // dv_j = sum_i P_ij dO_i   (lane = j)
         for (int qi = 0; qi < L; ++qi) {
             float dO[32];
-            load_row32f(sdo + qi * inner + h * 32, dO);
+            load_row32f(dorow + qi * gw, dO);
             const float pv = Ph[qi * PS + i];
 #pragma unroll
             for (int d = 0; d < 32; ++d) acc[d] = fmaf(pv, dO[d], acc[d]);
@@ -816,6 +847,13 @@ static size_t long_smem(int L, int gh, int gw, bool bias, int row_block, bool bw
     return b;
 }
 
+// CTK_ATTN_LEGACY=1 keeps the 24x24 spatial stack on the mma.sync kernels (A/B measurements)
+static bool attn_legacy() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CTK_ATTN_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 template <typename K>
 static int set_smem(K kern, size_t bytes) {
     CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -839,7 +877,9 @@ extern "C" int ctk_attn_fwd(const void* qkv, const float* table, void* out, floa
         CTK_LAUNCH_CHECK();
         return CTK_OK;
     }
-    // 9 warps (144 queries) per CTA when the sequence is long enough: 576 = 4 x 144, 2 CTAs / SM
+    if (table && L == 576 && gh == 24 && gw == 24 && !attn_legacy()) return ctk_attn_fwd_tc(qkv, table, out, lse, nseq, heads, s);
+    // legacy mma.sync path for other shapes. 9 warps (144 queries) per CTA when the sequence is long
+    // enough: 576 = 4 x 144, 2 CTAs / SM
     if (L >= 144) {
         const size_t sm = long_smem(L, gh, gw, table != nullptr, 144, false) - 144 * 64;   // one tile (Q) only
         CTK_REQUIRE(sm <= 220 * 1024, CTK_ERR_SHAPE, "attn_fwd: sequence of %d tokens does not fit in shared memory", L);
@@ -869,11 +909,11 @@ extern "C" int ctk_attn_bwd(const void* qkv, const float* table, const void* out
     auto dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
     const int inner = heads * 32;
     if (!table && L <= 32) {
-        const size_t sm = (size_t)L * 3 * inner * 4 + (size_t)L * inner * 4 +
-                          2 * (size_t)heads * L * (L + 1) * 4 + (size_t)heads * 32 * 4;
-        CTK_REQUIRE(sm <= 220 * 1024, CTK_ERR_SHAPE, "attn_bwd: short sequence of %d tokens does not fit", L);
+        const int HG = heads % 4 == 0 ? 4 : (heads % 2 == 0 ? 2 : 1);
+        const size_t sm = (size_t)L * 3 * HG * 32 * 4 + (size_t)L * HG * 32 * 4 + 2 * (size_t)HG * L * (L + 1) * 4 +
+                          (size_t)HG * 32 * 4;
         CTK_CUDA(cudaFuncSetAttribute(attn_short_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        attn_short_bwd_kernel<<<nseq, heads * 96, sm, s>>>(q, o, d_o, lse, dq, L, heads);
+        attn_short_bwd_kernel<<<nseq * (heads / HG), HG * 96, sm, s>>>(q, o, d_o, lse, dq, L, heads, HG);
         CTK_LAUNCH_CHECK();
         return CTK_OK;
     }

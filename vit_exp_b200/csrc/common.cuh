@@ -20,6 +20,9 @@ int ctk_check_device();   // CTK_OK or CTK_ERR_ARCH (no CPU / non-sm_100 fallbac
 int ctk_make_tmap(CUtensorMap* m, const void* ptr, bool f32, int rank, const unsigned long long* dims,
                   const unsigned long long* strides_bytes, const unsigned int* box, int swizzle);
 
+// tcgen05/TMEM spatial attention (attention_tc.cu); 24x24-token slices, head dim 32, bias table required
+int ctk_attn_fwd_tc(const void* qkv, const float* table, void* out, float* lse, int nseq, int heads, cudaStream_t stream);
+
 #define CTK_REQUIRE(cond, code, ...)                                                   \
     do {                                                                               \
         if (!(cond)) {                                                                 \

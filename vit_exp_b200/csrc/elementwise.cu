@@ -337,8 +337,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
 // PEG: depthwise causal 3x3x3 conv + bias + residual on [B, n0, n1, n2, dim] (attention.py:62-90,443)
 //
 // CTA = (batch b, tile of PEG_T1 rows along axis 1, slab of 32 channels). It walks axis 0 keeping a
-// ring of 4 input planes in shared memory: 3 feed the current output plane while the TMA engine
-// fills the 4th for the next step. Each plane is ONE 5-D TMA box {32 ch, n2+2, PEG_T1+2, 1, 1}
+// ring of 5 input planes in shared memory: 3 feed the current output plane while the TMA engine
+// fills the other two for the next steps. Each plane is ONE 5-D TMA box {32 ch, n2+2, PEG_T1+2, 1, 1}
 // whose out-of-range coordinates (halo rows/columns, planes before the causal start) are
 // zero-filled by the hardware, so every input element is fetched once per CTA (1.5x halo
 // overhead) instead of 9-27 times and there is no index arithmetic on the load path.
@@ -348,7 +348,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
 // MODE 2: dw, db accumulation (x planes in smem, dy read directly)
 // =============================================================================================
 constexpr int PEG_T1 = 4;
-constexpr int PEG_RING = 4;
+constexpr int PEG_RING = 5;            // 3 planes in use + 2 in flight
 constexpr int PEG_CS = 32;
 
 template <int MODE>
@@ -398,7 +398,10 @@ peg_tile_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
 #pragma unroll
         for (int t = 0; t < 27; ++t) acc_w[t] = 0.f;
     }
-    if (tid == 0) { issue(0); issue(1); issue(2); }
+    if (tid == 0) {               // n0 + 2 loads in total; never leave one un-awaited
+        issue(0); issue(1); issue(2);
+        if (n0 >= 2) issue(3);
+    }
     for (int a0 = 0; a0 < n0; ++a0) {
         // loads a0, a0+1, a0+2 feed this step; the first two were awaited by earlier steps
         if (a0 == 0) {
@@ -407,7 +410,7 @@ peg_tile_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
         }
         mbar_wait(&full_bar[(a0 + 2) % PEG_RING], ((a0 + 2) / PEG_RING) & 1);
         __syncthreads();          // every warp finished step a0-1 -> slot of load a0-1 is free
-        if (tid == 0 && a0 + 1 < n0) issue(a0 + 3);
+        if (tid == 0 && a0 + 2 < n0) issue(a0 + 4);
         if (!row_ok || p_lo >= p_hi) continue;
         // smem line (k0, k1): load a0+k0, local row lrow + k1   (local row 0 = a1 - 1)
         const float* ln[9];
