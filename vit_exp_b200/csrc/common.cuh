@@ -22,6 +22,9 @@ int ctk_make_tmap(CUtensorMap* m, const void* ptr, bool f32, int rank, const uns
 
 // tcgen05/TMEM spatial attention (attention_tc.cu); 24x24-token slices, head dim 32, bias table required
 int ctk_attn_fwd_tc(const void* qkv, const float* table, void* out, float* lse, int nseq, int heads, cudaStream_t stream);
+// dq / dk / dv of the same (attention_tc_bwd.cu); delta = rowsum(dO o O) must already be in `delta`
+int ctk_attn_bwd_tc(const void* qkv, const float* table, const void* dout, const float* lse, const float* delta,
+                    void* dqkv, int nseq, int heads, cudaStream_t stream);
 
 #define CTK_REQUIRE(cond, code, ...)                                                   \
     do {                                                                               \
