@@ -26,6 +26,12 @@ int ctk_attn_fwd_tc(const void* qkv, const float* table, void* out, float* lse, 
 int ctk_attn_bwd_tc(const void* qkv, const float* table, const void* dout, const float* lse, const float* delta,
                     void* dqkv, int nseq, int heads, cudaStream_t stream);
 
+// temporal stack (24-token sequences, no bias): TMA ring + warp-level MMA (attention_seq24.cu)
+bool ctk_attn_seq24_supported(int L, int heads);
+int ctk_attn_seq24_fwd(const void* qkv, void* out, float* lse, int nseq, int heads, cudaStream_t stream);
+int ctk_attn_seq24_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int nseq,
+                       int heads, cudaStream_t stream);
+
 #define CTK_REQUIRE(cond, code, ...)                                                   \
     do {                                                                               \
         if (!(cond)) {                                                                 \
