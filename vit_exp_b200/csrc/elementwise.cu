@@ -281,7 +281,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
         const long long drow = bcast_rows > 0 ? row / bcast_rows : perm_row(row, perm_outer, perm_inner);
         const float mu = mean[row], rs = rstd[row];
         const float2* xr = reinterpret_cast<const float2*>(x + row * DIM);
-        float2 xh[NV], g[NV];
+        float2 xh[NV], g[NV], prev[NV];
+        float2* dxr = reinterpret_cast<float2*>(dx + row * DIM);
+        // the accumulation target is fetched with the inputs, not after the row reductions
+#pragma unroll
+        for (int j = 0; j < NV; ++j) prev[j] = dx_accum ? dxr[j * 32 + lane] : make_float2(0.f, 0.f);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
@@ -300,14 +304,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __r
         }
         s1 = warp_sum(s1) * (1.0f / DIM);
         s2 = warp_sum(s2) * (1.0f / DIM);
-        float2* dxr = reinterpret_cast<float2*>(dx + row * DIM);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            float2 o = make_float2(rs * (g[j].x - s1 - xh[j].x * s2), rs * (g[j].y - s1 - xh[j].y * s2));
-            if (dx_accum) {
-                const float2 p = dxr[j * 32 + lane];
-                o.x += p.x; o.y += p.y;
-            }
+            const float2 o = make_float2(rs * (g[j].x - s1 - xh[j].x * s2) + prev[j].x,
+                                         rs * (g[j].y - s1 - xh[j].y * s2) + prev[j].y);
             dxr[j * 32 + lane] = o;
             if (dx_bf16)
                 reinterpret_cast<uint32_t*>(dx_bf16 + row * DIM)[j * 32 + lane] = pack_bf16x2(o.x, o.y);
@@ -425,17 +425,43 @@ peg_tile_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
         for (int l = 0; l < 9; ++l) { win[l][0] = ln[l][0]; win[l][1] = ln[l][PEG_CS]; }
         constexpr int centre = REV ? 1 : 7;                      // (k0,k1) of the un-shifted line
         const long long obase = ((((long long)bb * n0 + a0) * n1 + a1) * n2) * dim + c;
-        for (int a2 = p_lo; a2 < p_hi; ++a2) {
+        // MODE 2: the warp's output gradients of this step are fetched up front (16 positions cover
+        // n2 <= 32), so the walk below never waits on global memory
+        constexpr int GMAX = 16;
+        float gv[GMAX];
+        if (MODE == 2) {
 #pragma unroll
-            for (int l = 0; l < 9; ++l) win[l][2] = ln[l][(a2 - p_lo + 2) * PEG_CS];
-            if (MODE == 2) {
+            for (int q = 0; q < GMAX; ++q) gv[q] = p_lo + q < p_hi ? dy[obase + (long long)(p_lo + q) * dim] : 0.f;
+        }
+        if (MODE == 2) {
+            // fully unrolled walk: the 3-wide window rotates at compile time (no register moves)
+#pragma unroll
+            for (int q = 0; q < GMAX; ++q) {
+                if (p_lo + q < p_hi) {
+#pragma unroll
+                    for (int l = 0; l < 9; ++l) win[l][(q + 2) % 3] = ln[l][(q + 2) * PEG_CS];
+                    const float g = gv[q];
+                    acc_b += g;
+#pragma unroll
+                    for (int l = 0; l < 9; ++l)
+#pragma unroll
+                        for (int k2 = 0; k2 < 3; ++k2)
+                            acc_w[l * 3 + k2] = fmaf(g, win[l][(q + k2) % 3], acc_w[l * 3 + k2]);
+                }
+            }
+            for (int a2 = p_lo + GMAX; a2 < p_hi; ++a2) {          // n2 > 32 only
                 const float g = dy[obase + (long long)a2 * dim];
                 acc_b += g;
 #pragma unroll
                 for (int l = 0; l < 9; ++l)
 #pragma unroll
-                    for (int k2 = 0; k2 < 3; ++k2) acc_w[l * 3 + k2] = fmaf(g, win[l][k2], acc_w[l * 3 + k2]);
-            } else {
+                    for (int k2 = 0; k2 < 3; ++k2)
+                        acc_w[l * 3 + k2] = fmaf(g, ln[l][(a2 - p_lo + k2) * PEG_CS], acc_w[l * 3 + k2]);
+            }
+        } else {
+            for (int a2 = p_lo; a2 < p_hi; ++a2) {
+#pragma unroll
+                for (int l = 0; l < 9; ++l) win[l][2] = ln[l][(a2 - p_lo + 2) * PEG_CS];
                 float acc = bias + win[centre][1];               // + residual
 #pragma unroll
                 for (int l = 0; l < 9; ++l)
@@ -443,9 +469,9 @@ peg_tile_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
                     for (int k2 = 0; k2 < 3; ++k2) acc = fmaf(wt[l * 3 + k2], win[l][k2], acc);
                 y[obase + (long long)a2 * dim] = acc;
                 if (y_bf16) y_bf16[obase + (long long)a2 * dim] = __float2bfloat16(acc);
-            }
 #pragma unroll
-            for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
+                for (int l = 0; l < 9; ++l) { win[l][0] = win[l][1]; win[l][1] = win[l][2]; }
+            }
         }
     }
     if (MODE == 2) {
@@ -464,6 +490,126 @@ peg_tile_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             for (int ww = 0; ww < 8; ++ww) sacc += red[(ww * 28 + t) * 32 + l];
             if (t < 27) atomicAdd(dw + (long long)(c0 + l) * 27 + t, sacc);
             else atomicAdd(db + c0 + l, sacc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PEG forward / input gradient with packed fp32 math.  Same CTA tile, TMA plane ring and shared
+// memory layout as peg_tile_kernel, different thread mapping: the kernel above is bound by
+// instruction issue (27 FFMA + 9 LDS + stores per output), so here a thread owns TWO adjacent
+// channels and uses fma.rn.f32x2 (FFMA2: two fp32 FMAs per issue slot) on 8-byte shared-memory
+// loads.  lane = (row of a row pair, channel pair); warp = (row pair, quarter of axis 2).  The
+// three input planes are walked one after the other over the warp's positions, partial sums in
+// registers, so only a 3x3 window of float2 is live and the 27 weights are re-read per plane from
+// a float2 copy in shared memory.
+// MODE 0: y = conv(x) + b + x          MODE 1: dx = conv^T(dy) + dy
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+constexpr int PEG_QMAX = 8;            // positions per warp walk (ceil(n2 / 4) <= 8, i.e. n2 <= 32)
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+peg_pair_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, int B, int n0, int n1, int n2, int dim) {
+    extern __shared__ __align__(128) float psm[];
+    __shared__ __align__(8) uint64_t full_bar[PEG_RING];
+    __shared__ __align__(8) float2 swt[27][16];                  // weights of the slab, [tap][channel pair]
+    const int W2 = n2 + 2;
+    const int plane_floats = (PEG_T1 + 2) * W2 * PEG_CS;
+    const uint32_t plane_bytes = (uint32_t)plane_floats * 4u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
+    const int slab = blockIdx.x;
+    const int bb = blockIdx.y / tiles1;
+    const int r_lo = (blockIdx.y % tiles1) * PEG_T1;
+    const int c0 = slab * PEG_CS;
+    const int cp = lane & 15;
+    const int lrow = 2 * (warp & 1) + (lane >> 4);               // row of the 4-row tile
+    const int a1 = r_lo + lrow;
+    const bool row_ok = a1 < n1;
+    const int qlen = (n2 + 3) / 4;
+    const int p_lo = (warp >> 1) * qlen, p_hi = min(n2, p_lo + qlen);
+    constexpr bool REV = MODE == 1;
+    constexpr int shift = REV ? 0 : -2;
+    constexpr int centre_k0 = REV ? 0 : 2;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < PEG_RING; ++i) mbar_init(&full_bar[i], 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 27 * 16; i += 256) {
+        const int t = i / 16, q = i % 16;
+        const int tt = REV ? 26 - t : t;
+        swt[t][q] = make_float2(__ldg(w + (long long)(c0 + 2 * q) * 27 + tt), __ldg(w + (long long)(c0 + 2 * q + 1) * 27 + tt));
+    }
+    float2 bias = make_float2(0.f, 0.f);
+    if (MODE == 0 && b) bias = make_float2(__ldg(b + c0 + 2 * cp), __ldg(b + c0 + 2 * cp + 1));
+    __syncthreads();
+    auto issue = [&](int n) {
+        const int sl = n % PEG_RING;
+        mbar_expect_tx(&full_bar[sl], plane_bytes);
+        tma_load_5d(psm + sl * plane_floats, &tmap, &full_bar[sl], c0, -1, r_lo - 1, n + shift, bb);
+    };
+    if (tid == 0) {
+        issue(0); issue(1); issue(2);
+        if (n0 >= 2) issue(3);
+    }
+    for (int a0 = 0; a0 < n0; ++a0) {
+        if (a0 == 0) {
+            mbar_wait(&full_bar[0], 0);
+            mbar_wait(&full_bar[1], 0);
+        }
+        mbar_wait(&full_bar[(a0 + 2) % PEG_RING], ((a0 + 2) / PEG_RING) & 1);
+        __syncthreads();
+        if (tid == 0 && a0 + 2 < n0) issue(a0 + 4);
+        if (!row_ok || p_lo >= p_hi) continue;
+        float2 acc[PEG_QMAX];
+#pragma unroll
+        for (int q = 0; q < PEG_QMAX; ++q) acc[q] = bias;
+#pragma unroll
+        for (int k0 = 0; k0 < 3; ++k0) {
+            const float* pl = psm + ((a0 + k0) % PEG_RING) * plane_floats + (lrow * W2 + p_lo) * PEG_CS + 2 * cp;
+            float2 wk[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wk[t] = swt[k0 * 9 + t][cp];
+            float2 win[3][3];
+#pragma unroll
+            for (int k1 = 0; k1 < 3; ++k1) {
+                win[k1][0] = *reinterpret_cast<const float2*>(pl + (k1 * W2) * PEG_CS);
+                win[k1][1] = *reinterpret_cast<const float2*>(pl + (k1 * W2 + 1) * PEG_CS);
+            }
+#pragma unroll
+            for (int q = 0; q < PEG_QMAX; ++q) {
+                if (p_lo + q < p_hi) {
+#pragma unroll
+                    for (int k1 = 0; k1 < 3; ++k1)
+                        win[k1][(q + 2) % 3] = *reinterpret_cast<const float2*>(pl + (k1 * W2 + q + 2) * PEG_CS);
+                    if (k0 == centre_k0) {                        // + residual (the un-shifted input)
+                        const float2 ctr = win[1][(q + 1) % 3];
+                        acc[q].x += ctr.x;
+                        acc[q].y += ctr.y;
+                    }
+#pragma unroll
+                    for (int k1 = 0; k1 < 3; ++k1)
+#pragma unroll
+                        for (int k2 = 0; k2 < 3; ++k2) acc[q] = ffma2(wk[k1 * 3 + k2], win[k1][(q + k2) % 3], acc[q]);
+                }
+            }
+        }
+        const long long obase = ((((long long)bb * n0 + a0) * n1 + a1) * n2 + p_lo) * dim + c0 + 2 * cp;
+#pragma unroll
+        for (int q = 0; q < PEG_QMAX; ++q) {
+            if (p_lo + q < p_hi) {
+                *reinterpret_cast<float2*>(y + obase + (long long)q * dim) = acc[q];
+                if (y_bf16) *reinterpret_cast<uint32_t*>(y_bf16 + obase + (long long)q * dim) = pack_bf16x2(acc[q].x, acc[q].y);
+            }
         }
     }
 }
@@ -672,8 +818,17 @@ static int peg_launch(const float* staged, const float* w, const float* b, const
     const unsigned int box[5] = {PEG_CS, (unsigned)(n2 + 2), PEG_T1 + 2, 1, 1};
     int rc = ctk_make_tmap(&tm, staged, true, 5, dims, st, box, 0);
     if (rc) return rc;
-    CTK_CUDA(cudaFuncSetAttribute(peg_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
+    if constexpr (MODE != 2) {
+        if (n2 <= 4 * PEG_QMAX) {
+            CTK_CUDA(cudaFuncSetAttribute(peg_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            peg_pair_kernel<MODE><<<dim3(dim / PEG_CS, B * tiles1), 256, sm, s>>>(
+                tm, w, b, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), B, n0, n1, n2, dim);
+            CTK_LAUNCH_CHECK();
+            return CTK_OK;
+        }
+    }
+    CTK_CUDA(cudaFuncSetAttribute(peg_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     peg_tile_kernel<MODE><<<dim3(dim / PEG_CS, B * tiles1), 256, sm, s>>>(
         tm, w, b, dy, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), dw, db, B, n0, n1, n2, dim);
     CTK_LAUNCH_CHECK();
