@@ -90,7 +90,9 @@ def test_layernorm_bwd_broadcast(cuda_dev):
 
 
 # ----------------------------------------------------------------------------- PEG
-@pytest.mark.parametrize("shape,dim", [((2, 3, 2, 2), 64), ((1, 5, 4, 6), 64), ((1, 24, 24, 24), 512)])
+# axis-2 extents <= 32 take the packed-fp32 channel-pair kernel, longer ones the one-channel-per-lane kernel
+@pytest.mark.parametrize("shape,dim", [((2, 3, 2, 2), 64), ((1, 5, 4, 6), 64), ((1, 24, 24, 24), 512), ((2, 3, 5, 7), 32),
+                                       ((1, 2, 3, 40), 32)])
 def test_peg_fwd_bwd(cuda_dev, shape, dim):
     from vit_exp_b200 import ops
     n = shape[0] * shape[1] * shape[2] * shape[3]
@@ -158,13 +160,19 @@ def _attn_ref(qkv, table, nseq, L, heads, gh, gw):
     return out.permute(0, 2, 1, 3).reshape(nseq * L, inner), torch.logsumexp(sim, dim=-1)
 
 
-@pytest.mark.parametrize("nseq,L,heads,gh,gw", [(3, 4, 2, 2, 2), (2, 576, 8, 24, 24), (5, 24, 8, 0, 0), (4, 3, 2, 0, 0),
-                                                 (2, 100, 4, 10, 10), (2, 40, 2, 0, 0)])
-def test_attention_fwd_bwd(cuda_dev, nseq, L, heads, gh, gw):
+# (nseq, L, heads, gh, gw, qmul): 576-token cases run the tcgen05 kernels (9 slices: CTAs whose tile range starts
+# inside an item; qmul 40: logits far above the Cauchy-Schwarz fast-path bound -> exact row maximum), 24-token
+# cases the TMA-ring + warp-MMA kernels (more sequences than resident CTAs; 2 / 4 / 8 heads), the rest the
+# legacy mma.sync / SIMT kernels
+@pytest.mark.parametrize("nseq,L,heads,gh,gw,qmul", [(3, 4, 2, 2, 2, 8.0), (2, 576, 8, 24, 24, 8.0), (9, 576, 8, 24, 24, 8.0),
+                                                      (3, 576, 4, 24, 24, 40.0), (5, 24, 8, 0, 0, 8.0), (700, 24, 8, 0, 0, 8.0),
+                                                      (333, 24, 4, 0, 0, 8.0), (50, 24, 2, 0, 0, 8.0), (4, 3, 2, 0, 0, 8.0),
+                                                      (2, 100, 4, 10, 10, 8.0), (2, 40, 2, 0, 0, 8.0)])
+def test_attention_fwd_bwd(cuda_dev, nseq, L, heads, gh, gw, qmul):
     from vit_exp_b200 import ops
     inner = heads * 32
     g = _g(7)
-    q = F.normalize(torch.randn(nseq * L, heads, 32, generator=g), dim=-1) * 8.0 * (1 + 0.1 * torch.randn(32, generator=g))
+    q = F.normalize(torch.randn(nseq * L, heads, 32, generator=g), dim=-1) * qmul * (1 + 0.1 * torch.randn(32, generator=g))
     k = F.normalize(torch.randn(nseq * L, heads, 32, generator=g), dim=-1) * (1 + 0.1 * torch.randn(32, generator=g))
     v = torch.randn(nseq * L, heads, 32, generator=g)
     qkv = torch.cat([q.reshape(-1, inner), k.reshape(-1, inner), v.reshape(-1, inner)], dim=1).bfloat16()

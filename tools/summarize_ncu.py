@@ -1,12 +1,17 @@
-"""Turn gpurun_out/launches.csv and gpurun_out/prof_full.ncu-rep into small tracked summaries under profiles/."""
+"""Turn gpurun_out/launches.csv and .ncu-rep captures into small tracked summaries under profiles/.
+usage: summarize_ncu.py <tag> [report.ncu-rep:name ...]"""
 import collections, csv, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
+def short(n):
+    n = re.sub(r"\((CUtensorMap_st|const |float|__nv_bfloat16|int|long).*", "", n)
+    return n.replace("<unnamed>::", "").replace("void ", "")[:80]
+
 lc = os.path.join(ROOT, "gpurun_out", "launches.csv")
-if os.path.exists(lc):
+if os.path.exists(lc) and len(sys.argv) <= 2:
     lines = [l for l in open(lc) if not l.startswith("==")]
     tot, cnt = collections.defaultdict(float), collections.Counter()
     for d in csv.DictReader(lines):
@@ -14,7 +19,7 @@ if os.path.exists(lc):
             continue
         v = float(d["Metric Value"].replace(",", ""))
         v *= {"ns": 1.0, "us": 1e3, "ms": 1e6}.get(d["Metric Unit"], 1.0)
-        k = re.sub(r"\(.*", "", d["Kernel Name"]).replace("<unnamed>::", "")[:80]
+        k = short(d["Kernel Name"])
         tot[k] += v
         cnt[k] += 1
     T = sum(tot.values())
@@ -22,26 +27,31 @@ if os.path.exists(lc):
         f.write(f"# ncu launch list, one train step (B=8/GPU): {sum(cnt.values())} launches, {T/1e6:.2f} ms serialised\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` on `python bench.py --steps 2 --warmup 3 "
                 "--no-cpu-baseline`; cold-cache, serialised - compare shares, not absolutes.\n\n| ms | share | launches | kernel |\n|---|---|---|---|\n")
-        for k, v in sorted(tot.items(), key=lambda x: -x[1])[:40]:
+        for k, v in sorted(tot.items(), key=lambda x: -x[1])[:45]:
             f.write(f"| {v/1e6:.3f} | {100*v/T:.1f}% | {cnt[k]} | `{k}` |\n")
     print("wrote launches summary")
 
-rep = os.path.join(ROOT, "gpurun_out", "prof_full.ncu-rep")
-if os.path.exists(rep):
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size"]
+for spec in sys.argv[2:]:
+    rep, name = spec.split(":")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
-    want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-            "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "lts__t_bytes.sum"]
     idx = [hdr.index(w) for w in want if w in hdr]
-    with open(os.path.join(out_dir, f"{tag}_ncu_full_summary.csv"), "w", newline="") as f:
+    seen = collections.Counter()
+    with open(os.path.join(out_dir, f"{tag}_ncu_{name}.csv"), "w", newline="") as f:
         wr = csv.writer(f)
-        wr.writerow([hdr[i] for i in idx])
-        wr.writerow([rows[1][i] for i in idx])
+        wr.writerow(["kernel"] + [hdr[i] for i in idx])
+        wr.writerow(["unit"] + [rows[1][i] for i in idx])
         for r in rows[2:]:
-            r2 = [r[i] for i in idx]
-            r2[0] = re.sub(r"\(CUtensorMap_st.*|\(float const.*|\(__nv_bfloat16.*", "", r2[0]).replace("<unnamed>::", "")
-            wr.writerow(r2)
-    print("wrote full summary", len(rows) - 2, "kernels")
+            k = short(r[hdr.index("Kernel Name")])
+            key = (k, r[hdr.index("launch__grid_size")], r[hdr.index("dram__bytes_read.sum")][:4])
+            seen[key] += 1
+            if seen[key] > 2:          # repeated identical launches: keep two
+                continue
+            wr.writerow([k] + [r[i] for i in idx])
+    print("wrote", name, len(rows) - 2, "launches")
