@@ -134,3 +134,41 @@ def test_ctvit_batch_independence(cuda_dev):
         _, _, pre_one = vit.encode_with_aux(v[1:2].contiguous())
     n = pre_one.shape[0]
     assert torch.equal(pre_all[n:2 * n], pre_one)
+
+
+def test_bias_table_gradient_tcgen05_variant(cuda_dev):
+    """The opt-in tcgen05 bias-gradient kernel (CTK_DBIAS_TC=1: dS summed over slices by an identity MMA into
+    TMEM) agrees with the default mma.sync kernel; the switch is read once per process, hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch, torch.nn.functional as F
+sys.path.insert(0, %r)
+from vit_exp_b200 import ops
+g = torch.Generator().manual_seed(3)
+nseq, L, heads = 5, 576, 8
+inner = heads * 32
+q = F.normalize(torch.randn(nseq * L, heads, 32, generator=g), dim=-1) * 8
+k = F.normalize(torch.randn(nseq * L, heads, 32, generator=g), dim=-1)
+v = torch.randn(nseq * L, heads, 32, generator=g)
+qkv = torch.cat([q.reshape(-1, inner), k.reshape(-1, inner), v.reshape(-1, inner)], dim=1).bfloat16().cuda()
+table = torch.randn(heads, 47, 47, generator=g).cuda()
+dout = torch.randn(nseq * L, inner, generator=g).bfloat16().cuda()
+out, lse = ops.attn_fwd(qkv, table, nseq, L, heads, 24, 24)
+dtable = torch.zeros_like(table)
+dqkv = ops.attn_bwd(qkv, table, out, dout, lse, dtable, nseq, L, heads, 24, 24)
+torch.cuda.synchronize()
+torch.save({"dtable": dtable.cpu(), "dqkv": dqkv.float().cpu()}, sys.argv[1])
+''' % root
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("0", "1"):
+            path = os.path.join(td, f"r{flag}.pt")
+            env = dict(os.environ, CTK_DBIAS_TC=flag)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+            res[flag] = torch.load(path)
+    a, b = res["0"]["dtable"], res["1"]["dtable"]
+    assert torch.isfinite(b).all()
+    assert ((a - b).norm() / a.norm()).item() < 1e-2        # bf16 dS in the tcgen05 variant, fp32 dS in the default
+    assert torch.equal(res["0"]["dqkv"], res["1"]["dqkv"])

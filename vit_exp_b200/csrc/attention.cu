@@ -837,8 +837,12 @@ extern "C" int ctk_attn_bwd(const void* qkv, const float* table, const void* out
     attn_delta_kernel<<<(unsigned)((rows * heads + 255) / 256), 256, 0, s>>>(o, d_o, delta, rows, L, heads);
     CTK_LAUNCH_CHECK();
     const bool hb = table != nullptr;
-    if (hb && L == 576 && gh == 24 && gw == 24 && !attn_legacy()) {
-        if ((rc = ctk_attn_bwd_tc(qkv, table, dout, lse, delta, dqkv, nseq, heads, s))) return rc;
+    const bool tc_path = hb && L == 576 && gh == 24 && gw == 24 && !attn_legacy();
+    static int dbias_tc = -1;
+    if (dbias_tc < 0) { const char* e = getenv("CTK_DBIAS_TC"); dbias_tc = (e && e[0] == '1') ? 1 : 0; }
+    if (tc_path) {
+        if ((rc = ctk_attn_bwd_tc(qkv, table, dout, lse, delta, dqkv, dtable, dbias_tc, nseq, heads, s))) return rc;
+        if (dbias_tc) return CTK_OK;
     } else if (L >= 128) {
         // dq: 8 warps (128 queries), dk/dv: 6 warps (96 keys; 576 = 6 x 96); 2 CTAs / SM each
         const size_t sm_dq = long_smem(L, gh, gw, hb, 128, false), sm_dkv = long_smem(L, gh, gw, hb, 96, true);

@@ -12,7 +12,8 @@
 //   DKV = false : T1 = Q_t, T2 = dO_t, R1 = K, R2 = V;   acc0 += dS R1_c
 //   DKV = true  : T1 = K_t, T2 = V_t,  R1 = Q, R2 = dO;  acc0 += dS^T R1_c (dK), acc1 += P^T R2_c (dV)
 // TMEM columns: X1 [0,96)  X2 [96,192)  acc0 [192,224)  acc1 [224,256); two CTAs per SM.
-// The bias-table gradient stays in attention.cu (attn_bwd_dbias_kernel).
+// The bias-table gradient has a tcgen05 formulation too (attn_dbias_tc_kernel below, opt-in: CTK_DBIAS_TC=1); the
+// default is attn_bwd_dbias_kernel of attention.cu.
 #include "attention_tc.cuh"
 
 using namespace attn_tc;
@@ -311,6 +312,284 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_box, const __gri
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bias-table gradient: dtable[h][rel(i, j)] += sum over slices of dS[s, h, i, j].
+// "Stationary" formulation: a CTA owns one (head, 128-query tile, 64-key chunk) block and walks a
+// range of slices; the block's dS (bf16, as for dK) is summed over the slices by the tensor core
+// itself - G += dS * I_64 (tcgen05.mma TS against an identity tile in shared memory, fp32
+// accumulation in TMEM) - so the softmax warps spend no instruction on the reduction.  After the
+// last slice G is scattered once into a shared-memory copy of the table and flushed with one
+// atomic per touched entry.  Operands of the next four slices are in flight in a 5-stage TMA ring and
+// the logit products are double-buffered in TMEM, so the tensor core works on slice n+1 while the
+// softmax warps turn slice n into dS.  One CTA per SM (512 TMEM columns):
+// X buffer b: X1 = Q K^T [128 b, +64), X2 = dO V^T [128 b + 64, +64);  G [256, 320).
+// ---------------------------------------------------------------------------------------------
+constexpr int DC = 64;                      // keys per block
+constexpr int NDC = TL / DC;                // 9
+constexpr int D_STAGES = 5;
+constexpr int D_NSOFT = 16;                // softmax warps: 4 per TMEM lane quarter, 16 keys of the chunk each
+constexpr int D_NTHR = 32 * (1 + D_NSOFT);
+constexpr int D_STAGE_BYTES = 2 * Q_BYTES + 2 * DC * 64;
+constexpr int D_OFF_ID = D_STAGES * D_STAGE_BYTES;
+constexpr int D_OFF_TAB = D_OFF_ID + 2 * DC * 64;
+constexpr int D_OFF_ACC = D_OFF_TAB + TWW * TPW * 4;
+constexpr int D_OFF_BAR = D_OFF_ACC + TWW * TPW * 4;
+constexpr int D_NBAR = 2 * D_STAGES + 5;
+constexpr int D_OFF_SLOT = D_OFF_BAR + D_NBAR * 8;
+constexpr int D_SMEM_BYTES = D_OFF_SLOT + 16 + 1024;
+constexpr uint32_t D_COL_X1 = 0, D_COL_X2 = 64, D_COL_G = 256, D_XBUF = 128, D_TMEM_COLS = 512;   // X buffer b at columns 128 b
+
+// 16 columns (keys base + J0 .. base + J0 + 15, base = PHASE mod 24 inside its grid row) -> bf16 pairs of dS
+__device__ __forceinline__ void dsoft_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * D_NSOFT) : "memory"); }
+
+template <int PHASE, int J0>
+__device__ __forceinline__ void dbias_block(const uint32_t (&x1)[16], const uint32_t (&x2)[16], uint32_t (&ds)[8],
+                                            uint32_t bias_addr, float lse2, float delta) {
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) {
+        float d[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = PHASE + J0 + e + u;
+            const float b = lds_f32(bias_addr - 4u * (uint32_t)((j / TGW) * TPW + j % TGW));
+            const float p = fast_exp2(fmaf(__uint_as_float(x1[e + u]), LOG2E, b) - lse2);
+            d[u] = p * (__uint_as_float(x2[e + u]) - delta);
+        }
+        ds[e >> 1] = pack_bf16x2(d[0], d[1]);
+    }
+}
+template <int PHASE>
+__device__ __forceinline__ void dbias_chunk(uint32_t t_x1, uint32_t t_x2, uint32_t bias_addr, float lse2, float delta) {
+    uint32_t x1[16], x2[16], ds[8];
+    tc_ld_32x32_x16(t_x1, x1);
+    tc_ld_32x32_x16(t_x2, x2);
+    tc_wait_ld();
+    dbias_block<PHASE, 0>(x1, x2, ds, bias_addr, lse2, delta);
+    tc_st_32x32_x8(t_x2, ds);
+    tc_wait_st();
+}
+
+__global__ void __launch_bounds__(D_NTHR, 1)
+attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __grid_constant__ CUtensorMap tmap_do_tile,
+                     const __grid_constant__ CUtensorMap tmap_qkv_chunk, const float* __restrict__ table,
+                     const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dtable, int nseq,
+                     int heads, int nsplit) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sId = smem + D_OFF_ID;
+    float* sTab = reinterpret_cast<float*>(smem + D_OFF_TAB);
+    float* sAcc = reinterpret_cast<float*>(smem + D_OFF_ACC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + D_OFF_BAR);
+    uint64_t* full = bars;                       // [3] TMA -> MMA
+    uint64_t* empty = bars + D_STAGES;           // [3] MMA -> TMA (X products of the stage have retired)
+    uint64_t* bar_S = bars + 2 * D_STAGES;       // [2] MMA -> softmax: X buffer b is ready
+    uint64_t* bar_P = bar_S + 2;                 // [2] softmax -> MMA: dS is in X buffer b
+    uint64_t* bar_O = bar_S + 4;                 // MMA -> softmax: G of the item is complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D_OFF_SLOT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int inner = heads * 32;
+    // item = (split of the slices, head, query tile, key chunk); items of one CTA: blockIdx.x, + gridDim.x, ...
+    const int items = nsplit * heads * NQT * NDC;
+    auto decode = [&](int item, int& sp, int& h, int& t, int& c) {
+        c = item % NDC; item /= NDC;
+        t = item % NQT; item /= NQT;
+        h = item % heads; sp = item / heads;
+    };
+    auto s_begin = [&](int sp) { return (int)((long long)nseq * sp / nsplit); };
+
+    // identity tile (B operand of the accumulation): [64 n][64 k] bf16 as two 32-wide K blocks, 64 B rows, SW64
+    for (int i = threadIdx.x; i < 2 * DC * 64 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sId)[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x < DC) {
+        const int n = threadIdx.x;
+        const int chunk = ((n % 32) / 8) ^ ((n >> 1) & 3);
+        *reinterpret_cast<__nv_bfloat16*>(sId + (n / 32) * (DC * 64) + n * 64 + chunk * 16 + (n % 8) * 2) = __float2bfloat16(1.0f);
+    }
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_qkv_tile);
+            tma_prefetch_desc(&tmap_do_tile);
+            tma_prefetch_desc(&tmap_qkv_chunk);
+            for (int i = 0; i < 2 * D_STAGES; ++i) mbar_init(&bars[i], 1);
+            mbar_init(&bar_S[0], 1);
+            mbar_init(&bar_S[1], 1);
+            mbar_init(&bar_P[0], D_NSOFT);
+            mbar_init(&bar_P[1], D_NSOFT);
+            mbar_init(bar_O, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, D_TMEM_COLS);
+        tmem_relinquish();
+    }
+    // generic-proxy writes of the identity tile must be visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ control: TMA + MMA issue ================================
+        if (lane == 0 && (int)blockIdx.x < items) {
+            constexpr uint32_t idesc_x = umma_idesc_bf16(QT, DC, 0, 0);
+            constexpr uint32_t idesc_g = umma_idesc_bf16(QT, DC, 0, 0);
+            const uint32_t ring_a = smem_u32(smem), sId_a = smem_u32(sId);
+            // flattened (item, slice) stream for the loads
+            int l_item = blockIdx.x, l_sp, l_h, l_t, l_c, l_s, l_send, l_n = 0;
+            decode(l_item, l_sp, l_h, l_t, l_c);
+            l_s = s_begin(l_sp); l_send = s_begin(l_sp + 1);
+            auto load_next = [&]() {                              // returns false when the stream is exhausted
+                while (l_s >= l_send) {
+                    l_item += gridDim.x;
+                    if (l_item >= items) return false;
+                    decode(l_item, l_sp, l_h, l_t, l_c);
+                    l_s = s_begin(l_sp); l_send = s_begin(l_sp + 1);
+                }
+                const int st = l_n % D_STAGES;
+                if (l_n >= D_STAGES) mbar_wait(&empty[st], ((uint32_t)(l_n / D_STAGES) & 1u) ^ 1u);
+                uint8_t* sb = smem + st * D_STAGE_BYTES;
+                mbar_expect_tx(&full[st], D_STAGE_BYTES);
+                tma_load_2d(sb, &tmap_qkv_tile, &full[st], l_h * 32, l_s * TL + l_t * QT);
+                tma_load_2d(sb + Q_BYTES, &tmap_do_tile, &full[st], l_h * 32, l_s * TL + l_t * QT);
+                tma_load_2d(sb + 2 * Q_BYTES, &tmap_qkv_chunk, &full[st], inner + l_h * 32, l_s * TL + l_c * DC);
+                tma_load_2d(sb + 2 * Q_BYTES + DC * 64, &tmap_qkv_chunk, &full[st], 2 * inner + l_h * 32, l_s * TL + l_c * DC);
+                ++l_s; ++l_n;
+                return true;
+            };
+            for (int i = 0; i < D_STAGES - 1; ++i) load_next();
+            // X(n): both logit products of consumed pair n into X buffer n & 1
+            auto issue_x = [&](int n) {
+                const int st = n % D_STAGES;
+                mbar_wait(&full[st], (uint32_t)(n / D_STAGES) & 1u);
+                tc_fence_after();
+                const uint32_t sb = ring_a + st * D_STAGE_BYTES;
+                const uint32_t xb = tmem_base + (uint32_t)(n & 1) * D_XBUF;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    tc_mma_f16(xb + D_COL_X1, umma_desc(sb + k * 32, 16, 512, SW64),
+                               umma_desc(sb + 2 * Q_BYTES + k * 32, 16, 512, SW64), idesc_x, k);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    tc_mma_f16(xb + D_COL_X2, umma_desc(sb + Q_BYTES + k * 32, 16, 512, SW64),
+                               umma_desc(sb + 2 * Q_BYTES + DC * 64 + k * 32, 16, 512, SW64), idesc_x, k);
+                tc_commit(&bar_S[n & 1]);
+                tc_commit(&empty[st]);
+            };
+            // total number of (item, slice) pairs of this CTA
+            int total = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                int sp, h, t, c;
+                decode(item, sp, h, t, c);
+                total += s_begin(sp + 1) - s_begin(sp);
+            }
+            uint32_t p_par = 0;
+            int n = 0;                                            // consumed (item, slice) pairs
+            if (total > 0) issue_x(0);
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                int sp, h, t, c;
+                decode(item, sp, h, t, c);
+                const int s0 = s_begin(sp), s1 = s_begin(sp + 1);
+                for (int s = s0; s < s1; ++s, ++n) {
+                    load_next();                                  // D_STAGES - 1 pairs ahead
+                    // the next pair's logits go to the other X buffer while the softmax warps work on this one
+                    // (its previous content, dS of pair n-1, was consumed by the G product issued before)
+                    if (n + 1 < total) issue_x(n + 1);
+                    mbar_wait(&bar_P[n & 1], (p_par >> (n & 1)) & 1u);
+                    p_par ^= 1u << (n & 1);
+                    tc_fence_after();
+                    const uint32_t xb = tmem_base + (uint32_t)(n & 1) * D_XBUF;
+#pragma unroll
+                    for (int k = 0; k < DC / 16; ++k)               // G += dS * I (the 16 keys of warp group k at columns 16 k)
+                        tc_mma_f16_ts(tmem_base + D_COL_G, xb + D_COL_X2 + k * 16,
+                                      umma_desc(sId_a + (k >> 1) * (DC * 64) + (k & 1) * 32, 16, 512, SW64), idesc_g,
+                                      (s > s0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(bar_O);
+            }
+        }
+    } else {
+        // ================================ softmax warps ================================
+        const int sw = warp - 1;
+        const int quarter = warp & 3;
+        const int hsel = sw >> 2;                                  // which 16 keys of the chunk
+        const int row = quarter * 32 + lane;
+        const int st_id = threadIdx.x - 32;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t sTab_a = smem_u32(sTab), sAcc_a = smem_u32(sAcc);
+        uint32_t s_par = 0, o_par = 0;
+        int cur_head = -1, n = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int sp, h, t, c;
+            decode(item, sp, h, t, c);
+            const int s0 = s_begin(sp), s1 = s_begin(sp + 1);
+            dsoft_sync();                                          // previous item's flush is done
+            if (h != cur_head) {
+                cur_head = h;
+                const float* tg = table + (long long)h * TNOFF;
+                for (int i = st_id; i < TNOFF; i += 32 * D_NSOFT) sTab[(i / TWW) * TPW + i % TWW] = __ldg(tg + i) * LOG2E;
+            }
+            for (int i = st_id; i < TWW * TPW; i += 32 * D_NSOFT) sAcc[i] = 0.f;
+            dsoft_sync();
+            const int i = t * QT + row;
+            const bool active = t * QT + quarter * 32 < TL;
+            const int kbase = c * DC + hsel * 16;                  // first key of this warp's 16
+            const int phase = kbase % TGW;                         // 0, 8 or 16
+            // address of bias(i, key at the start of kbase's grid row)
+            const uint32_t rel = (uint32_t)(TOFF + (i / TGW) * TPW + (i % TGW) - (kbase / TGW) * TPW);
+            const uint32_t bias_addr = sTab_a + 4u * rel;
+            const long long stat_off = ((long long)s0 * heads + h) * TL + (active ? i : 0);
+            const long long stat_step = (long long)heads * TL;
+            float lse_n = 0.f, dl_n = 0.f;
+            if (active && s0 < s1) { lse_n = __ldg(lse + stat_off); dl_n = __ldg(delta + stat_off); }
+            for (int s = s0; s < s1; ++s, ++n) {
+                const uint32_t t_x1 = t_lane + (uint32_t)(n & 1) * D_XBUF + D_COL_X1 + hsel * 16, t_x2 = t_x1 + (D_COL_X2 - D_COL_X1);
+                const float lse2 = lse_n * LOG2E, dlt = dl_n;
+                if (active && s + 1 < s1) {                        // next slice's row statistics, ahead of the wait
+                    lse_n = __ldg(lse + stat_off + (s + 1 - s0) * stat_step);
+                    dl_n = __ldg(delta + stat_off + (s + 1 - s0) * stat_step);
+                }
+                mbar_wait(&bar_S[n & 1], (s_par >> (n & 1)) & 1u);
+                s_par ^= 1u << (n & 1);
+                tc_fence_after();
+                if (active) {
+                    if (phase == 0) dbias_chunk<0>(t_x1, t_x2, bias_addr, lse2, dlt);
+                    else if (phase == 8) dbias_chunk<8>(t_x1, t_x2, bias_addr, lse2, dlt);
+                    else dbias_chunk<16>(t_x1, t_x2, bias_addr, lse2, dlt);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_P[n & 1]);
+            }
+            mbar_wait(bar_O, o_par);
+            o_par ^= 1;
+            tc_fence_after();
+            if (active) {
+                uint32_t g[16];
+                tc_ld_32x32_x16(t_lane + D_COL_G + hsel * 16, g);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int j = phase + e;
+                    const uint32_t a = sAcc_a + 4u * (rel - (uint32_t)((j / TGW) * TPW + j % TGW));
+                    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(__uint_as_float(g[e])) : "memory");
+                }
+            }
+            tc_fence_before();
+            dsoft_sync();
+            float* dt = dtable + (long long)h * TNOFF;
+            for (int k = st_id; k < TNOFF; k += 32 * D_NSOFT) {
+                const float v = sAcc[(k / TWW) * TPW + k % TWW];
+                if (v != 0.f) atomicAdd(dt + k, v);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, D_TMEM_COLS);
+}
+
 template <bool DKV>
 int launch_bwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, const float* table,
                const float* lse, const float* delta, __nv_bfloat16* dqkv, int nseq, int heads, cudaStream_t stream) {
@@ -332,7 +611,7 @@ int launch_bwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
 
 // dq, dk, dv of the 24x24 spatial stack (delta = rowsum(dO o O) already computed); validated by ctk_attn_bwd.
 int ctk_attn_bwd_tc(const void* qkv, const float* table, const void* dout, const float* lse, const float* delta,
-                    void* dqkv, int nseq, int heads, cudaStream_t stream) {
+                    void* dqkv, float* dtable, int dtable_tc, int nseq, int heads, cudaStream_t stream) {
     const int inner = heads * 32;
     const unsigned long long rows = (unsigned long long)nseq * TL;
     CUtensorMap ta, tb, tc, td;
@@ -348,5 +627,26 @@ int ctk_attn_bwd_tc(const void* qkv, const float* table, const void* dout, const
     if ((rc = ctk_make_tmap(&td, dout, false, 2, dims_do, str_do, box_tile, 2))) return rc;
     auto g = reinterpret_cast<__nv_bfloat16*>(dqkv);
     if ((rc = launch_bwd<false>(ta, tb, tc, td, table, lse, delta, g, nseq, heads, stream))) return rc;
-    return launch_bwd<true>(ta, tb, tc, td, table, lse, delta, g, nseq, heads, stream);
+    if ((rc = launch_bwd<true>(ta, tb, tc, td, table, lse, delta, g, nseq, heads, stream))) return rc;
+    // bias-table gradient: the mma.sync kernel of attention.cu (fp32 dS, 0.62 ms at B=8) unless dtable_tc is set -
+    // the tcgen05 formulation below is correct but latency-bound at 0.65-0.7 ms this round
+    if (!dtable_tc) return CTK_OK;
+    CUtensorMap te;
+    const unsigned int box_chunk[2] = {32, DC};
+    if ((rc = ctk_make_tmap(&te, qkv, false, 2, dims_qkv, str_qkv, box_chunk, 2))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        CTK_CUDA(cudaFuncSetAttribute(attn_dbias_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
+        configured = true;
+    }
+    // one CTA per SM (512 TMEM columns); split the slices so that there are ~5 items per CTA
+    const int blocks = heads * NQT * NDC;
+    int nsplit = (5 * ctk_num_sms() + blocks - 1) / blocks;
+    if (nsplit > nseq) nsplit = nseq;
+    if (nsplit < 1) nsplit = 1;
+    long long grid = ctk_num_sms();
+    if (grid > (long long)blocks * nsplit) grid = (long long)blocks * nsplit;
+    attn_dbias_tc_kernel<<<(unsigned)grid, D_NTHR, D_SMEM_BYTES, stream>>>(tb, td, te, table, lse, delta, dtable, nseq, heads, nsplit);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
 }

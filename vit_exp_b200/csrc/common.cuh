@@ -22,9 +22,9 @@ int ctk_make_tmap(CUtensorMap* m, const void* ptr, bool f32, int rank, const uns
 
 // tcgen05/TMEM spatial attention (attention_tc.cu); 24x24-token slices, head dim 32, bias table required
 int ctk_attn_fwd_tc(const void* qkv, const float* table, void* out, float* lse, int nseq, int heads, cudaStream_t stream);
-// dq / dk / dv of the same (attention_tc_bwd.cu); delta = rowsum(dO o O) must already be in `delta`
+// dq / dk / dv / dtable of the same (attention_tc_bwd.cu); delta = rowsum(dO o O) must already be in `delta`
 int ctk_attn_bwd_tc(const void* qkv, const float* table, const void* dout, const float* lse, const float* delta,
-                    void* dqkv, int nseq, int heads, cudaStream_t stream);
+                    void* dqkv, float* dtable, int dtable_tc, int nseq, int heads, cudaStream_t stream);
 
 // temporal stack (24-token sequences, no bias): TMA ring + warp-level MMA (attention_seq24.cu)
 bool ctk_attn_seq24_supported(int L, int heads);
