@@ -34,10 +34,11 @@ def case(nseq, heads, qmul=8.0, seed=0, bwd=True):
                 f" dv {rel(dqkv[:, 2*inner:], gq[:, 2*inner:]):.2e} dtable {rel(dtable, td.grad):.2e}")
     print(msg, flush=True)
 
-for a in ((1, 1), (2, 8), (9, 8), (20, 4), (3, 8, 40.0)):
+BENCH_ONLY = os.environ.get('BENCH_ONLY') == '1'
+for a in () if BENCH_ONLY else ((1, 1), (2, 8), (9, 8), (20, 4), (3, 8, 40.0)):
     case(*a)
 
-def timeit(fn, iters=20, warm=3):
+def timeit(fn, iters=2 if os.environ.get('BENCH_ONLY') == '1' else 20, warm=1 if os.environ.get('BENCH_ONLY') == '1' else 3):
     for _ in range(warm): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
