@@ -173,7 +173,7 @@ def run_ours(args):
     model = clip
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], find_unused_parameters=True,
-                                                          gradient_as_bucket_view=True)
+                                                          gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb)
     params = [p for p in clip.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1.25e-6, betas=(0.9, 0.99), fused=True)      # optimizer.py:14,23-24
     acc = TorchDistAccelerator()
@@ -243,9 +243,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    n0 = lib.ctk_launch_count()
+    n0 = lib.ctk_launch_count() + ops.GRAPH_LAUNCHES
     ms_dev, _ = timed(lambda k: [step(i % 2) for i in range(k)], args.steps)
-    launches = (lib.ctk_launch_count() - n0)
+    launches = (lib.ctk_launch_count() + ops.GRAPH_LAUNCHES - n0)      # direct launches + launches replayed from CUDA graphs
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host inputs, H2D of step i+1 overlapped with step i, loss read back every step -----
@@ -301,7 +301,9 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (1.77 GB of volumes per step); two alternating batches",
                    "e2e_pipeline": "host batch (pinned) -> H2D on a side stream into one of 3 device slots while the "
                                    "previous step computes; loss read back (.item()) every step",
-                   "text_tower": "stock PyTorch BertModel under bf16 autocast"},
+                   "text_tower": "stock PyTorch BertModel under bf16 autocast",
+                   "launch": "encoder forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
+                             else "eager launches"},
         "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s",
                 "h2d_bytes_per_step": int(host_vid[0].numel() * 4 + host_ids[0].numel() * 8), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -412,6 +414,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (MB)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -172,3 +172,36 @@ torch.save({"dtable": dtable.cpu(), "dqkv": dqkv.float().cpu()}, sys.argv[1])
     assert torch.isfinite(b).all()
     assert ((a - b).norm() / a.norm()).item() < 1e-2        # bf16 dS in the tcgen05 variant, fp32 dS in the default
     assert torch.equal(res["0"]["dqkv"], res["1"]["dqkv"])
+
+
+def test_cuda_graph_replay_matches_eager(cuda_dev):
+    """After two eager steps the encoder forward/backward are replayed from CUDA graphs; tokens, loss-side gradient
+    flow and parameter gradients must match the eager launches step for step (same kernels, same order)."""
+    from vit_exp_b200.transformer_maskgit import CTViT
+    res = {}
+    for graphs in (False, True):
+        torch.manual_seed(0)
+        vit = CTViT(dim=128, codebook_size=256, image_size=80, patch_size=20, temporal_patch_size=10, spatial_depth=1,
+                    temporal_depth=1, dim_head=32, heads=4).to(cuda_dev).eval()      # eval: the codebook stays fixed
+        vit.cuda_graphs = graphs
+        vids = [torch.rand(2, 1, 30, 80, 80, generator=_g(10 + i)).to(cuda_dev) for i in range(2)]
+        w = torch.randn(2, 3, 4, 4, 128, generator=_g(20)).to(cuda_dev)
+        outs = []
+        for step in range(5):
+            for q in vit.parameters():
+                q.grad = None
+            tokens = vit(vids[step % 2], return_encoded_tokens=True)
+            (tokens * w).sum().backward()
+            outs.append((tokens.detach().clone(), {n: q.grad.detach().clone() for n, q in vit.named_parameters()
+                                                    if q.grad is not None}))
+        res[graphs] = outs
+        if graphs:
+            assert any(eg.fwd is not None and eg.bwd for eg in vit._graphs.values()), "graphs were never captured"
+    for step in range(5):
+        t0, g0 = res[False][step]
+        t1, g1 = res[True][step]
+        assert torch.equal(t0, t1), f"tokens differ at step {step}"
+        assert g0.keys() == g1.keys()
+        for n in g0:
+            d = (g1[n].double() - g0[n].double()).norm() / g0[n].double().norm().clamp_min(1e-30)
+            assert d.item() < 1e-4, (step, n)                                 # atomics order only

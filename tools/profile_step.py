@@ -9,6 +9,14 @@ from vit_exp_b200.ct_clip import TorchDistAccelerator
 B = int(os.environ.get("B", "8"))
 dev = torch.device("cuda:0")
 clip = bench.build_model(dev).train()
+if os.environ.get("TEXT_STUB") == "1":            # isolate the image path: replace BERT by an embedding table
+    class _Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(30522, 768)
+        def forward(self, input_ids, attention_mask=None):
+            return (self.emb(input_ids),)
+    clip.text_transformer = _Stub().to(dev)
 bert = clip.text_transformer
 orig = bert.forward
 def fwd(*a, **k):
@@ -40,7 +48,7 @@ for e in prof.key_averages():
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
 print(f"total device time {tot/1e3:.2f} ms over {sum(r[1] for r in rows)} kernels")
-for t, c, k in rows[:45]:
+for t, c, k in rows[:int(os.environ.get('TOPN', '45'))]:
     print(f"{t/1e3:9.3f} ms {100*t/tot:5.1f}% x{c:<5d} {k[:110]}")
 
 # ---- host-side cost per phase (no sync inside; CPU launch time only)

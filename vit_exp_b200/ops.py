@@ -32,6 +32,9 @@ def _chk(t: torch.Tensor, dtype, name: str):
 
 # --------------------------------------------------------------------------- GEMM
 GEMM_PROFILE = None     # bench.py sets this to a list: (start_event, end_event, tag) per GEMM launch
+# libctk kernels launched by CUDA-graph replays (the C-side counter only sees direct launches); bench.py adds this
+# to ctk_launch_count() for its `gpu_launches` line
+GRAPH_LAUNCHES = 0
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, c: torch.Tensor, *, M: int, N: int, K: int,
@@ -167,17 +170,22 @@ def fill_(t: torch.Tensor, v: float):
 
 
 # --------------------------------------------------------------------------- encoder ops
-def patch_norm_fwd(video: torch.Tensor, pt: int, p1: int, p2: int, eps: float = 1e-5):
-    """video fp32 [B,1,D,H,W] -> (xhat bf16 [B*T*Hp*Wp, ld], mean, rstd); ld = K rounded up to 8."""
+def patch_norm_fwd(video: torch.Tensor, pt: int, p1: int, p2: int, eps: float = 1e-5, out=None):
+    """video fp32 [B,1,D,H,W] -> (xhat bf16 [B*T*Hp*Wp, ld], mean, rstd); ld = K rounded up to 8.
+    `out` = (xhat, mean, rstd) writes into existing buffers (CUDA-graph replays keep their addresses)."""
     _chk(video, torch.float32, "video")
     B, Cc, D, H, W = video.shape
     assert Cc == 1, "CT volumes are single channel"
     K = pt * p1 * p2
     ld = (K + 7) // 8 * 8
     rows = B * (D // pt) * (H // p1) * (W // p2)
-    xhat = torch.empty(rows, ld, dtype=torch.bfloat16, device=video.device)
-    mean = torch.empty(rows, dtype=torch.float32, device=video.device)
-    rstd = torch.empty(rows, dtype=torch.float32, device=video.device)
+    if out is not None:
+        xhat, mean, rstd = out
+        assert xhat.shape == (rows, ld) and xhat.dtype == torch.bfloat16
+    else:
+        xhat = torch.empty(rows, ld, dtype=torch.bfloat16, device=video.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=video.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=video.device)
     check(_lib.load().ctk_patch_norm_fwd(_p(video), _p(xhat), ld, _p(mean), _p(rstd), B, D, H, W, pt, p1, p2, eps,
                                          _stream()), "ctk_patch_norm_fwd")
     return xhat, mean, rstd

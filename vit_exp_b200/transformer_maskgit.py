@@ -11,6 +11,8 @@ written backward of the whole encoder.  There is no CPU or torch fallback.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple
@@ -293,7 +295,10 @@ def _transformer_bwd(dy, dy_bcast, lps, norm_gamma, cfg: _Cfg, table, dtable, ns
     return g, (g_bf if want_bf16_out else None)
 
 
-def _encode_forward(vit: "CTViT", video: torch.Tensor, params: List[torch.Tensor], save: bool, training: bool):
+def _encode_forward(vit: "CTViT", video: torch.Tensor, params: List[torch.Tensor], save: bool, training: bool,
+                    xhat: Optional[torch.Tensor] = None):
+    """`xhat` (normalised patches from ops.patch_norm_fwd) may be supplied by the caller: the CUDA-graph path runs
+    that one kernel outside the graph because it is the only one that reads the (per-step) volume pointer."""
     cfg = _Cfg(vit, video)
     dim, M = cfg.dim, cfg.M
     it = iter(params)
@@ -305,7 +310,8 @@ def _encode_forward(vit: "CTViT", video: torch.Tensor, params: List[torch.Tensor
     tp_norm = next(it)
 
     # ---- patch embedding (ctvit.py:170-175); LayerNorm(K) affine folded into the projection
-    xhat, pmean, prstd = ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2)
+    if xhat is None:
+        xhat, _, _ = ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2)
     wp_eff = ops.cast_bf16(wp, ld=cfg.Kp, col_scale=g1)
     bias_eff = torch.addmv(bp, wp, b1)                    # parameter folding: b + W beta (dim x K mat-vec)
     y0 = torch.empty(M, dim, dtype=torch.float32, device=video.device)
@@ -335,10 +341,11 @@ def _encode_forward(vit: "CTViT", video: torch.Tensor, params: List[torch.Tensor
     return out, ind.view(cfg.B, cfg.t, cfg.h, cfg.w), xt, ctx
 
 
-def _encode_backward(vit: "CTViT", params: List[torch.Tensor], ctx, dtokens: torch.Tensor):
+def _encode_backward(vit: "CTViT", params: List[torch.Tensor], ctx, dtokens: torch.Tensor, dy_in=None):
+    """`dy_in` = (dy fp32 [rows, dim], bcast) replaces the unpacking of `dtokens` (CUDA-graph path: static buffer)."""
     cfg: _Cfg = ctx["cfg"]
     dim, M = cfg.dim, cfg.M
-    dev = dtokens.device
+    dev = dtokens.device if dy_in is None else dy_in[0].device
     it = iter(params)
     cpb = [next(it) for _ in range(6)]
     g1, b1, wp, bp, g3, b3 = (next(it) for _ in range(6))
@@ -351,12 +358,10 @@ def _encode_backward(vit: "CTViT", params: List[torch.Tensor], ctx, dtokens: tor
 
     # straight-through VQ (quantize = x + (quantize - x).detach()): d enc = d tokens.
     # A mean-pool gradient arrives as a stride-0 expand of [B, dim]: keep it un-materialised.
-    bcast = None
-    if dtokens.dim() == 5 and dtokens.stride()[1:4] == (0, 0, 0) and dtokens.stride(4) == 1:
-        dy = dtokens[:, 0, 0, 0, :].contiguous().float()
-        bcast = (n_tok, 1.0)
+    if dy_in is not None:
+        dy, bcast = dy_in
     else:
-        dy = dtokens.reshape(M, dim).contiguous().float()
+        dy, bcast = _unpack_dtokens(dtokens, cfg)
 
     sp_g: List[Optional[torch.Tensor]] = [None] * (cfg.sd * N_PER_LAYER + 1)
     tp_g: List[Optional[torch.Tensor]] = [None] * (cfg.td * N_PER_LAYER + 1)
@@ -378,23 +383,121 @@ def _encode_backward(vit: "CTViT", params: List[torch.Tensor], ctx, dtokens: tor
     return cpb_g + [dg1, db1, dwp, dbp, dg3, db3] + sp_g + tp_g
 
 
+def _unpack_dtokens(dtokens: torch.Tensor, cfg: "_Cfg"):
+    """(dy fp32 [rows, dim], bcast): a mean-pool gradient arrives as a stride-0 expand of [B, dim]."""
+    n_tok = cfg.t * cfg.h * cfg.w
+    if dtokens.dim() == 5 and dtokens.stride()[1:4] == (0, 0, 0) and dtokens.stride(4) == 1:
+        return dtokens[:, 0, 0, 0, :].contiguous().float(), (n_tok, 1.0)
+    return dtokens.reshape(cfg.M, cfg.dim).contiguous().float(), None
+
+
+class _EncoderGraph:
+    """CUDA graphs of one training-shape encoder forward and backward.
+
+    The encoder is ~260 (forward) + ~330 (backward) kernel launches with static shapes; enqueued from
+    Python they cost ~17 ms of host time per step, more than the forward takes on the GPU, and they delay
+    the text tower's launches.  After `WARMUP` eager calls with the same key (shapes, parameter
+    addresses, mode) the bodies of `_encode_forward` / `_encode_backward` are captured once and replayed.
+    Only two kernels stay outside: the patch gather (it reads the caller's volume, whose address changes
+    from step to step) writes into a static buffer, and the incoming token gradient is copied into a
+    static buffer.  Saved activations live in the graphs' private pool and are reused every step.
+    """
+    WARMUP = 2
+
+    def __init__(self):
+        self.calls = 0
+        self.fwd = None
+        self.bwd = {}            # keyed by the layout of the incoming gradient (broadcast or dense)
+        self.pool = None
+        self.failed = False
+
+
+def _graph_key(video, training, params, embed):
+    return (tuple(video.shape), bool(training), tuple(p.data_ptr() for p in params), embed.data_ptr())
+
+
+def _capture(fn, pool):
+    """capture fn() into a CUDA graph (nothing executes during capture); returns (graph, outputs, launches)"""
+    from . import _lib
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    n0 = lib.ctk_launch_count()
+    # thread_local: NCCL's watchdog / other streams' threads keep issuing CUDA calls while we capture
+    with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+        out = fn()
+    return g, out, int(lib.ctk_launch_count() - n0)
+
+
 class _CTViTEncode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vit, video, training, *params):
-        need = any(p.requires_grad for p in params) and torch.is_grad_enabled()
-        out, ind, pre_vq, saved = _encode_forward(vit, video, list(params), save=True, training=training)
-        ctx.vit = vit
-        ctx.saved = saved
-        ctx.params = params
+        params = list(params)
+        ctx.vit, ctx.params, ctx.graph = vit, params, None
+        eg = None
+        if vit.cuda_graphs and ops.GEMM_PROFILE is None and not torch.cuda.is_current_stream_capturing():
+            key = _graph_key(video, training, params, vit.vq._codebook.embed)
+            eg = vit._graphs.get(key)
+            if eg is None:
+                if len(vit._graphs) >= 4:                       # shapes keep changing: stay eager
+                    vit._graphs.clear()
+                eg = vit._graphs[key] = _EncoderGraph()
+            eg.calls += 1
+            if eg.failed or eg.calls <= _EncoderGraph.WARMUP:
+                eg = None
+        if eg is None:
+            out, ind, pre_vq, saved = _encode_forward(vit, video, params, save=True, training=training)
+            ctx.saved = saved
+            ctx.mark_non_differentiable(ind)
+            return out, ind, pre_vq.detach()
+        cfg = _Cfg(vit, video)
+        if eg.fwd is None:
+            try:
+                eg.pool = torch.cuda.graph_pool_handle()
+                st_x = ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2)            # static patch buffers
+                g, outs, n = _capture(lambda: _encode_forward(vit, video, params, save=True, training=training,
+                                                              xhat=st_x[0]), eg.pool)
+                eg.fwd = dict(graph=g, outs=outs, launches=n, xbuf=st_x)
+            except Exception as e:                                                  # pragma: no cover
+                import warnings
+                warnings.warn(f"CTViT: CUDA-graph capture failed ({e}); staying on eager launches")
+                eg.failed = True
+                torch.cuda.synchronize()
+                out, ind, pre_vq, saved = _encode_forward(vit, video, params, save=True, training=training)
+                ctx.saved = saved
+                ctx.mark_non_differentiable(ind)
+                return out, ind, pre_vq.detach()
+        f = eg.fwd
+        ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2, out=f["xbuf"])
+        f["graph"].replay()
+        ops.GRAPH_LAUNCHES += f["launches"]
+        out, ind, pre_vq, saved = f["outs"]
+        ctx.saved, ctx.graph = saved, eg
+        out, ind, pre_vq = out.detach(), ind.detach(), pre_vq.detach()
         ctx.mark_non_differentiable(ind)
-        return out, ind, pre_vq.detach()
+        return out, ind, pre_vq
 
     @staticmethod
     def backward(ctx, dtokens, _dind, dpre):
         assert dtokens is not None
-        grads = _encode_backward(ctx.vit, list(ctx.params), ctx.saved, dtokens)
-        ctx.saved = None
-        return (None, None, None, *grads)
+        eg = ctx.graph
+        if eg is None or ops.GEMM_PROFILE is not None:
+            grads = _encode_backward(ctx.vit, ctx.params, ctx.saved, dtokens)
+            ctx.saved = None
+            return (None, None, None, *grads)
+        cfg = ctx.saved["cfg"]
+        dy, bcast = _unpack_dtokens(dtokens, cfg)
+        bkey = (bcast, tuple(dy.shape))
+        b = eg.bwd.get(bkey)
+        if b is None:
+            dy_static = dy.clone()
+            g, grads, n = _capture(lambda: _encode_backward(ctx.vit, ctx.params, ctx.saved, None, dy_in=(dy_static, bcast)),
+                                   eg.pool)
+            b = eg.bwd[bkey] = dict(graph=g, grads=grads, launches=n, dy=dy_static)
+        b["dy"].copy_(dy)
+        b["graph"].replay()
+        ops.GRAPH_LAUNCHES += b["launches"]
+        return (None, None, None, *b["grads"])
 
 
 class CTViT(nn.Module):
@@ -430,6 +533,10 @@ class CTViT(nn.Module):
         self.vq = VectorQuantize(dim=dim, codebook_size=codebook_size, use_cosine_sim=True)
         self.to_pixels_first_frame = nn.Sequential(nn.Linear(dim, pdim_ff), nn.Identity())
         self.to_pixels = nn.Sequential(nn.Linear(dim, pdim), nn.Identity())
+        # training-shape forward / backward are replayed from CUDA graphs after two eager steps (see _EncoderGraph);
+        # set to False to keep every step on eager launches
+        self.cuda_graphs = os.environ.get("CTK_CUDA_GRAPHS", "1") != "0"
+        self._graphs = {}
 
     # -- reference helpers kept for callers --------------------------------------------------------
     @property
