@@ -2,6 +2,8 @@
 // LayerNorm forward/backward (with the spatial<->temporal token transposition folded into the
 // row index), PEG depthwise 3x3x3 conv forward/backward, row l2norm, VQ gather / EMA update.
 #include "common.cuh"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -614,6 +616,145 @@ peg_pair_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PEG forward / input gradient, plane-scatter form.  The gather form above reads 9 shared-memory
+// values per output (3 planes x 3 rows, window along axis 2) and is bound by the shared-memory
+// crossbar.  Here every input plane is read ONCE per thread (3 rows x (q + 2) columns for q output
+// positions) and scattered into the partial sums of the three output planes it contributes to,
+// which live in registers (3 x q float2) and rotate at compile time (the plane loop is unrolled by
+// 3): 3 shared-memory reads feed 27 packed FMAs.  Planes are consumed once, so the ring only holds
+// the current plane and the prefetched ones, and no out-of-range planes are ever loaded.
+// MODE 0: y = conv(x) + b + x   (plane p feeds outputs p, p+1, p+2)
+// MODE 1: dx = conv^T(dy) + dy  (plane p feeds outputs p, p-1, p-2; two outputs are flushed at the end)
+// ---------------------------------------------------------------------------------------------
+constexpr int PEGS_RING = 4;
+
+template <int MODE, int QL, int R>
+__device__ __forceinline__ void peg_scatter_plane(const float* pl, int W2, int ncol, const float2 (&wk)[27], float2 (&acc)[3][QL],
+                                                  int p, int n0) {
+    // output plane of tap k0 and its register slot: MODE 0: p + 2 - k0 -> (R + 2 - k0) % 3; MODE 1: p - k0 -> (R + 3 - k0) % 3
+    bool use[3];
+#pragma unroll
+    for (int k0 = 0; k0 < 3; ++k0) use[k0] = MODE == 0 ? (p + 2 - k0 < n0) : (p - k0 >= 0);
+#pragma unroll
+    for (int j = 0; j < QL + 2; ++j) {
+        if (j < ncol) {
+            float2 col[3];
+#pragma unroll
+            for (int k1 = 0; k1 < 3; ++k1) col[k1] = *reinterpret_cast<const float2*>(pl + (k1 * W2 + j) * PEG_CS);
+            if (j >= 1 && j - 1 < QL) {                         // + residual: the un-shifted input goes to output plane p
+                acc[R][j - 1].x += col[1].x;
+                acc[R][j - 1].y += col[1].y;
+            }
+#pragma unroll
+            for (int k0 = 0; k0 < 3; ++k0) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int slot = MODE == 0 ? (R + 2 - k0) % 3 : (R + 3 - k0) % 3;
+                if (use[k0]) {
+#pragma unroll
+                    for (int k1 = 0; k1 < 3; ++k1)
+#pragma unroll
+                        for (int k2 = 0; k2 < 3; ++k2)
+                            if (j - k2 >= 0 && j - k2 < QL) acc[slot][j - k2] = ffma2(wk[(k0 * 3 + k1) * 3 + k2], col[k1], acc[slot][j - k2]);
+                }
+            }
+        }
+    }
+}
+
+template <int MODE, int QL>
+__global__ void __launch_bounds__(256, 2)
+peg_scatter_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, const float* __restrict__ b,
+                   float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16, int B, int n0, int n1, int n2, int dim) {
+    extern __shared__ __align__(128) float psm[];
+    __shared__ __align__(8) uint64_t full_bar[PEGS_RING];
+    __shared__ __align__(8) float2 swt[27][16];                  // weights of the slab, [tap][channel pair]
+    const int W2 = n2 + 2;
+    const int plane_floats = (PEG_T1 + 2) * W2 * PEG_CS;
+    const uint32_t plane_bytes = (uint32_t)plane_floats * 4u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
+    const int bb = blockIdx.y / tiles1;
+    const int r_lo = (blockIdx.y % tiles1) * PEG_T1;
+    const int c0 = blockIdx.x * PEG_CS;
+    const int cp = lane & 15;
+    const int lrow = 2 * (warp & 1) + (lane >> 4);               // row of the 4-row tile
+    const int a1 = r_lo + lrow;
+    const int qlen = (n2 + 3) / 4;                               // <= QL
+    const int p_lo = (warp >> 1) * qlen, p_hi = min(n2, p_lo + qlen);
+    const bool work = a1 < n1 && p_lo < p_hi;
+    const int ncol = p_hi - p_lo + 2;
+    constexpr bool REV = MODE == 1;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < PEGS_RING; ++i) mbar_init(&full_bar[i], 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 27 * 16; i += 256) {
+        const int t = i / 16, q = i % 16;
+        const int tt = REV ? 26 - t : t;
+        swt[t][q] = make_float2(__ldg(w + (long long)(c0 + 2 * q) * 27 + tt), __ldg(w + (long long)(c0 + 2 * q + 1) * 27 + tt));
+    }
+    float2 bias = make_float2(0.f, 0.f);
+    if (MODE == 0 && b) bias = make_float2(__ldg(b + c0 + 2 * cp), __ldg(b + c0 + 2 * cp + 1));
+    __syncthreads();
+    float2 wk[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) wk[t] = swt[t][cp];
+    auto issue = [&](int n) {                                     // plane n -> slot n % PEGS_RING (thread 0 only)
+        const int sl = n % PEGS_RING;
+        mbar_expect_tx(&full_bar[sl], plane_bytes);
+        tma_load_5d(psm + sl * plane_floats, &tmap, &full_bar[sl], c0, -1, r_lo - 1, n, bb);
+    };
+    if (tid == 0)
+        for (int n = 0; n < PEGS_RING - 1 && n < n0; ++n) issue(n);
+    float2 acc[3][QL];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int q = 0; q < QL; ++q) acc[s][q] = bias;
+    auto store = [&](int o, float2 (&a)[QL]) {                    // finished output plane o; the slot restarts from the bias
+        const long long obase = ((((long long)bb * n0 + o) * n1 + a1) * n2 + p_lo) * dim + c0 + 2 * cp;
+#pragma unroll
+        for (int q = 0; q < QL; ++q) {
+            if (p_lo + q < p_hi) {
+                *reinterpret_cast<float2*>(y + obase + (long long)q * dim) = a[q];
+                if (y_bf16) *reinterpret_cast<uint32_t*>(y_bf16 + obase + (long long)q * dim) = pack_bf16x2(a[q].x, a[q].y);
+            }
+            a[q] = bias;
+        }
+    };
+    auto step = [&](int p, auto rtag) {
+        constexpr int R = decltype(rtag)::value;
+        mbar_wait(&full_bar[p % PEGS_RING], (p / PEGS_RING) & 1);
+        __syncthreads();                                          // every warp finished plane p-1: its slot can be refilled
+        if (tid == 0 && p + PEGS_RING - 1 < n0) issue(p + PEGS_RING - 1);
+        if (!work) return;
+        const float* pl = psm + (p % PEGS_RING) * plane_floats + (lrow * W2 + p_lo) * PEG_CS + 2 * cp;
+        peg_scatter_plane<MODE, QL, R>(pl, W2, ncol, wk, acc, p, n0);
+        if (MODE == 0) store(p, acc[R]);
+        else if (p >= 2) store(p - 2, acc[(R + 1) % 3]);
+    };
+    for (int p = 0; p < n0; p += 3) {
+        step(p, std::integral_constant<int, 0>{});
+        if (p + 1 < n0) step(p + 1, std::integral_constant<int, 1>{});
+        if (p + 2 < n0) step(p + 2, std::integral_constant<int, 2>{});
+    }
+    if (MODE == 1 && work) {                                      // outputs n0-2 and n0-1 received their last plane
+        const int r_last = (n0 - 1) % 3;
+        auto flush = [&](int o) {
+            if (o < 0) return;
+            if (o % 3 == 0) store(o, acc[0]);
+            else if (o % 3 == 1) store(o, acc[1]);
+            else store(o, acc[2]);
+        };
+        (void)r_last;
+        flush(n0 - 2);
+        flush(n0 - 1);
+    }
+}
+
 // =============================================================================================
 // VQ helpers
 // =============================================================================================
@@ -820,6 +961,15 @@ static int peg_launch(const float* staged, const float* w, const float* b, const
     if (rc) return rc;
     const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
     if constexpr (MODE != 2) {
+        static const bool gather = [] { const char* e = getenv("CTK_PEG_GATHER"); return e && e[0] == '1'; }();
+        if (n2 <= 24 && !gather) {                                   // plane-scatter form, 6 positions per thread
+            const size_t sm_s = (size_t)PEGS_RING * (PEG_T1 + 2) * (n2 + 2) * PEG_CS * 4;
+            CTK_CUDA(cudaFuncSetAttribute(peg_scatter_kernel<MODE, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s));
+            peg_scatter_kernel<MODE, 6><<<dim3(dim / PEG_CS, B * tiles1), 256, sm_s, s>>>(
+                tm, w, b, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), B, n0, n1, n2, dim);
+            CTK_LAUNCH_CHECK();
+            return CTK_OK;
+        }
         if (n2 <= 4 * PEG_QMAX) {
             CTK_CUDA(cudaFuncSetAttribute(peg_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             peg_pair_kernel<MODE><<<dim3(dim / PEG_CS, B * tiles1), 256, sm, s>>>(
