@@ -755,6 +755,131 @@ peg_scatter_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PEG weight / bias gradient, plane-scatter form on channel pairs: dw[k0][k1][k2] += dy[o] x[o-2+k0]
+// with x plane p staged in shared memory (read once per thread) and the three dy rows it meets
+// (output planes p, p+1, p+2: rows of 6 positions, 8-byte coalesced global loads) held in
+// registers and rotated at compile time.  27 float2 accumulators per thread, reduced over the
+// CTA's warps through shared memory, one atomic per (channel, tap) per CTA.
+// ---------------------------------------------------------------------------------------------
+template <int QL, int R>
+__device__ __forceinline__ void peg_wgrad_plane(const float* pl, int W2, int ncol, float2 (&acc)[27], const float2 (&g)[3][QL],
+                                                int p, int n0) {
+    // tap k0 pairs x plane p with output plane p + 2 - k0, whose gradient row sits in slot (R + 2 - k0) % 3
+    bool use[3];
+#pragma unroll
+    for (int k0 = 0; k0 < 3; ++k0) use[k0] = p + 2 - k0 < n0;
+#pragma unroll
+    for (int j = 0; j < QL + 2; ++j) {
+        if (j < ncol) {
+            float2 col[3];
+#pragma unroll
+            for (int k1 = 0; k1 < 3; ++k1) col[k1] = *reinterpret_cast<const float2*>(pl + (k1 * W2 + j) * PEG_CS);
+#pragma unroll
+            for (int k0 = 0; k0 < 3; ++k0) {
+                const int slot = (R + 2 - k0) % 3;
+                if (use[k0]) {
+#pragma unroll
+                    for (int k1 = 0; k1 < 3; ++k1)
+#pragma unroll
+                        for (int k2 = 0; k2 < 3; ++k2)
+                            if (j - k2 >= 0 && j - k2 < QL)
+                                acc[(k0 * 3 + k1) * 3 + k2] = ffma2(g[slot][j - k2], col[k1], acc[(k0 * 3 + k1) * 3 + k2]);
+                }
+            }
+        }
+    }
+}
+
+template <int QL>
+__global__ void __launch_bounds__(256, 2)
+peg_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ dy, float* __restrict__ dw,
+                 float* __restrict__ db, int B, int n0, int n1, int n2, int dim) {
+    extern __shared__ __align__(128) float psm[];
+    __shared__ __align__(8) uint64_t full_bar[PEGS_RING];
+    const int W2 = n2 + 2;
+    const int plane_floats = (PEG_T1 + 2) * W2 * PEG_CS;
+    const uint32_t plane_bytes = (uint32_t)plane_floats * 4u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles1 = (n1 + PEG_T1 - 1) / PEG_T1;
+    const int bb = blockIdx.y / tiles1;
+    const int r_lo = (blockIdx.y % tiles1) * PEG_T1;
+    const int c0 = blockIdx.x * PEG_CS;
+    const int cp = lane & 15;
+    const int lrow = 2 * (warp & 1) + (lane >> 4);
+    const int a1 = r_lo + lrow;
+    const int qlen = (n2 + 3) / 4;
+    const int p_lo = (warp >> 1) * qlen, p_hi = min(n2, p_lo + qlen);
+    const bool work = a1 < n1 && p_lo < p_hi;
+    const int ncol = p_hi - p_lo + 2;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < PEGS_RING; ++i) mbar_init(&full_bar[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int n) {
+        const int sl = n % PEGS_RING;
+        mbar_expect_tx(&full_bar[sl], plane_bytes);
+        tma_load_5d(psm + sl * plane_floats, &tmap, &full_bar[sl], c0, -1, r_lo - 1, n, bb);
+    };
+    if (tid == 0)
+        for (int n = 0; n < PEGS_RING - 1 && n < n0; ++n) issue(n);
+    float2 acc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc[t] = make_float2(0.f, 0.f);
+    float2 accb = make_float2(0.f, 0.f);
+    float2 g[3][QL];
+    auto load_g = [&](int o, float2 (&row)[QL]) {                 // gradient row of output plane o (zeros past the end)
+        const long long gbase = ((((long long)bb * n0 + o) * n1 + a1) * n2 + p_lo) * dim + c0 + 2 * cp;
+#pragma unroll
+        for (int q = 0; q < QL; ++q) {
+            row[q] = make_float2(0.f, 0.f);
+            if (work && o < n0 && p_lo + q < p_hi) row[q] = *reinterpret_cast<const float2*>(dy + gbase + (long long)q * dim);
+            accb.x += row[q].x;
+            accb.y += row[q].y;
+        }
+    };
+    // before plane p: slots (p % 3, (p+1) % 3) hold output planes p, p+1; plane p+2 is fetched into the third slot
+    load_g(0, g[0]);
+    load_g(1, g[1]);
+    auto step = [&](int p, auto rtag) {
+        constexpr int R = decltype(rtag)::value;
+        load_g(p + 2, g[(R + 2) % 3]);                            // issued before the wait: in flight while the plane lands
+        mbar_wait(&full_bar[p % PEGS_RING], (p / PEGS_RING) & 1);
+        __syncthreads();
+        if (tid == 0 && p + PEGS_RING - 1 < n0) issue(p + PEGS_RING - 1);
+        if (!work) return;
+        const float* pl = psm + (p % PEGS_RING) * plane_floats + (lrow * W2 + p_lo) * PEG_CS + 2 * cp;
+        peg_wgrad_plane<QL, R>(pl, W2, ncol, acc, g, p, n0);
+    };
+    for (int p = 0; p < n0; p += 3) {
+        step(p, std::integral_constant<int, 0>{});
+        if (p + 1 < n0) step(p + 1, std::integral_constant<int, 1>{});
+        if (p + 2 < n0) step(p + 2, std::integral_constant<int, 2>{});
+    }
+    // reduce over the CTA (16 threads share a channel pair): [16 half-warps][28][32 channels] in the ring's memory
+    __syncthreads();
+    float* red = psm;
+    const int hw = warp * 2 + (lane >> 4);
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        red[(hw * 28 + t) * 32 + 2 * cp] = work ? acc[t].x : 0.f;
+        red[(hw * 28 + t) * 32 + 2 * cp + 1] = work ? acc[t].y : 0.f;
+    }
+    red[(hw * 28 + 27) * 32 + 2 * cp] = work ? accb.x : 0.f;
+    red[(hw * 28 + 27) * 32 + 2 * cp + 1] = work ? accb.y : 0.f;
+    __syncthreads();
+    for (int i = tid; i < 28 * 32; i += 256) {
+        const int t = i / 32, l = i % 32;
+        float sacc = 0.f;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) sacc += red[(h * 28 + t) * 32 + l];
+        if (t < 27) atomicAdd(dw + (long long)(c0 + l) * 27 + t, sacc);
+        else atomicAdd(db + c0 + l, sacc);
+    }
+}
+
 // =============================================================================================
 // VQ helpers
 // =============================================================================================
@@ -974,6 +1099,16 @@ static int peg_launch(const float* staged, const float* w, const float* b, const
             CTK_CUDA(cudaFuncSetAttribute(peg_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             peg_pair_kernel<MODE><<<dim3(dim / PEG_CS, B * tiles1), 256, sm, s>>>(
                 tm, w, b, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), B, n0, n1, n2, dim);
+            CTK_LAUNCH_CHECK();
+            return CTK_OK;
+        }
+    }
+    if constexpr (MODE == 2) {
+        static const bool gather = [] { const char* e = getenv("CTK_PEG_GATHER"); return e && e[0] == '1'; }();
+        const size_t sm_s = (size_t)PEGS_RING * (PEG_T1 + 2) * (n2 + 2) * PEG_CS * 4;
+        if (n2 <= 24 && !gather && sm_s >= (size_t)16 * 28 * 32 * 4) {
+            CTK_CUDA(cudaFuncSetAttribute(peg_wgrad_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s));
+            peg_wgrad_kernel<6><<<dim3(dim / PEG_CS, B * tiles1), 256, sm_s, s>>>(tm, dy, dw, db, B, n0, n1, n2, dim);
             CTK_LAUNCH_CHECK();
             return CTK_OK;
         }
