@@ -329,7 +329,8 @@ constexpr int NDC = TL / DC;                // 9
 constexpr int D_STAGES = 5;
 constexpr int D_NSOFT = 16;                // softmax warps: 4 per TMEM lane quarter, 16 keys of the chunk each
 constexpr int D_NTHR = 32 * (1 + D_NSOFT);
-constexpr int D_STAGE_BYTES = 2 * Q_BYTES + 2 * DC * 64;
+constexpr int D_STAT_OFF = 2 * Q_BYTES + 2 * DC * 64;          // lse[128] | delta[128] of the tile's rows for this slice
+constexpr int D_STAGE_BYTES = D_STAT_OFF + 2 * QT * 4;
 constexpr int D_OFF_ID = D_STAGES * D_STAGE_BYTES;
 constexpr int D_OFF_TAB = D_OFF_ID + 2 * DC * 64;
 constexpr int D_OFF_ACC = D_OFF_TAB + TWW * TPW * 4;
@@ -450,7 +451,11 @@ attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __
                 const int st = l_n % D_STAGES;
                 if (l_n >= D_STAGES) mbar_wait(&empty[st], ((uint32_t)(l_n / D_STAGES) & 1u) ^ 1u);
                 uint8_t* sb = smem + st * D_STAGE_BYTES;
-                mbar_expect_tx(&full[st], D_STAGE_BYTES);
+                const uint32_t stat_bytes = (uint32_t)min(QT, TL - l_t * QT) * 4u;       // the last tile holds 64 rows
+                mbar_expect_tx(&full[st], D_STAT_OFF + 2 * stat_bytes);
+                const long long so = ((long long)l_s * heads + l_h) * TL + l_t * QT;
+                bulk_load_1d(sb + D_STAT_OFF, lse + so, stat_bytes, &full[st]);
+                bulk_load_1d(sb + D_STAT_OFF + QT * 4, delta + so, stat_bytes, &full[st]);
                 tma_load_2d(sb, &tmap_qkv_tile, &full[st], l_h * 32, l_s * TL + l_t * QT);
                 tma_load_2d(sb + Q_BYTES, &tmap_do_tile, &full[st], l_h * 32, l_s * TL + l_t * QT);
                 tma_load_2d(sb + 2 * Q_BYTES, &tmap_qkv_chunk, &full[st], inner + l_h * 32, l_s * TL + l_c * DC);
@@ -539,21 +544,17 @@ attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __
             // address of bias(i, key at the start of kbase's grid row)
             const uint32_t rel = (uint32_t)(TOFF + (i / TGW) * TPW + (i % TGW) - (kbase / TGW) * TPW);
             const uint32_t bias_addr = sTab_a + 4u * rel;
-            const long long stat_off = ((long long)s0 * heads + h) * TL + (active ? i : 0);
-            const long long stat_step = (long long)heads * TL;
-            float lse_n = 0.f, dl_n = 0.f;
-            if (active && s0 < s1) { lse_n = __ldg(lse + stat_off); dl_n = __ldg(delta + stat_off); }
             for (int s = s0; s < s1; ++s, ++n) {
                 const uint32_t t_x1 = t_lane + (uint32_t)(n & 1) * D_XBUF + D_COL_X1 + hsel * 16, t_x2 = t_x1 + (D_COL_X2 - D_COL_X1);
-                const float lse2 = lse_n * LOG2E, dlt = dl_n;
-                if (active && s + 1 < s1) {                        // next slice's row statistics, ahead of the wait
-                    lse_n = __ldg(lse + stat_off + (s + 1 - s0) * stat_step);
-                    dl_n = __ldg(delta + stat_off + (s + 1 - s0) * stat_step);
-                }
                 mbar_wait(&bar_S[n & 1], (s_par >> (n & 1)) & 1u);
                 s_par ^= 1u << (n & 1);
                 tc_fence_after();
                 if (active) {
+                    // row statistics of this slice came with the stage (acquire its bulk copies through the stage's own
+                    // barrier; it completed before the X products that signalled bar_S were even issued)
+                    mbar_wait(&full[n % D_STAGES], (uint32_t)(n / D_STAGES) & 1u);
+                    const float* stats = reinterpret_cast<const float*>(smem + (n % D_STAGES) * D_STAGE_BYTES + D_STAT_OFF);
+                    const float lse2 = stats[row] * LOG2E, dlt = stats[QT + row];
                     if (phase == 0) dbias_chunk<0>(t_x1, t_x2, bias_addr, lse2, dlt);
                     else if (phase == 8) dbias_chunk<8>(t_x1, t_x2, bias_addr, lse2, dlt);
                     else dbias_chunk<16>(t_x1, t_x2, bias_addr, lse2, dlt);
