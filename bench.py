@@ -175,7 +175,11 @@ def run_ours(args):
         model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], find_unused_parameters=True,
                                                           gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb)
     params = [p for p in clip.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1.25e-6, betas=(0.9, 0.99), fused=True)      # optimizer.py:14,23-24
+    if args.optimizer == "fused":        # clip_grad_norm_(0.5) + Adam in two libctk launches (vit_exp_b200/optim.py)
+        from vit_exp_b200.optim import FusedClipAdam
+        opt = FusedClipAdam(params, lr=1.25e-6, betas=(0.9, 0.99), max_grad_norm=0.5)   # optimizer.py:14,23-24
+    else:
+        opt = torch.optim.Adam(params, lr=1.25e-6, betas=(0.9, 0.99), fused=True)
     acc = TorchDistAccelerator()
 
     # synthetic CT-RATE-shaped host batch in pinned memory (two buffers -> consecutive steps differ)
@@ -208,7 +212,8 @@ def run_ours(args):
                  "text": SimpleNamespace(input_ids=dev_ids[slot], attention_mask=mask), "image": dev_vid[slot]}
         loss, ld = model(batch, device=dev, accelerator=acc, return_loss=True, return_loss_dict=True)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 0.5)                            # CTCLIPTrainer.py:711-712
+        if args.optimizer != "fused":
+            torch.nn.utils.clip_grad_norm_(params, 0.5)                        # CTCLIPTrainer.py:711-712
         opt.step()
         opt.zero_grad(set_to_none=True)
         return ld["cl_loss"]                                                     # float: D2H read of the loss
@@ -415,6 +420,8 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (MB)")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: libctk clip+Adam (2 launches); torch: clip_grad_norm_ + torch.optim.Adam(fused=True)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -163,6 +163,11 @@ int ctk_cpb_bwd(const float* dtable, const float* w0, const float* w1, const flo
  * CTK_EPI_QKV: bf16 [nseq*L, 3*heads*32], q pre-scaled.  softmax(q.k^T + bias) v, no mask,
  * dim_head 32.  out bf16 [nseq*L, heads*32]; lse fp32 [nseq, heads, L] (natural log).
  * table == NULL -> no bias (temporal stack).  L == gh*gw when a table is given.
+ * Dispatch (same results, different kernels): 24x24-token slices with a table -> tcgen05/TMEM kernels
+ * (attention_tc.cu, attention_tc_bwd.cu); 24-token sequences without a table, 2/4/8 heads -> TMA ring +
+ * warp MMA (attention_seq24.cu); anything else -> mma.sync / SIMT kernels (attention.cu).
+ * Environment switches read once per process: CTK_ATTN_LEGACY=1 forces the last group, CTK_DBIAS_TC=1
+ * selects the tcgen05 bias-table-gradient kernel.
  * ------------------------------------------------------------------------------------------ */
 int ctk_attn_fwd(const void* qkv, const float* table, void* out, float* lse, int nseq, int L,
                  int heads, int gh, int gw, void* stream);
@@ -232,6 +237,24 @@ int ctk_patch_affine_bwd(const float* P, const float* W, const float* gamma, con
 /* db fp32 [cols] += column sums of dy (bf16 or fp32) [rows, cols]. */
 int ctk_colsum(const void* dy_bf16, const float* dy_f32, float* out, long long rows, int cols,
                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer tail: torch.nn.utils.clip_grad_norm_(params, max_norm)
+ * (CTCLIPTrainer.py:711-712) + torch.optim.Adam / AdamW (optimizer.py:14-24) over a device table of
+ * tensors.  rows: int64 [ntensors][6] = {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel,
+ * index of the tensor's first chunk}; a chunk is ctk_opt_chunk_elems() elements, nchunks their total.
+ * ctk_multi_sqnorm overwrites *out_sq with the sum of squares of all gradients; ctk_multi_adam scales
+ * the gradients by min(1, max_norm / (sqrt(*sq) + 1e-6)) (max_norm <= 0: no clipping) and applies
+ * step number `step` (>= 1) of Adam (adamw = 0: weight decay added to the gradient) or AdamW.
+ * ------------------------------------------------------------------------------------------ */
+int ctk_opt_chunk_elems(void);
+/* dst (device) <- src (pinned, device-accessible host memory) by kernel loads, not by a DMA copy: the
+ * table upload must not queue behind the input batch's H2D transfer.  bytes % 16 == 0. */
+int ctk_copy_from_pinned(void* dst, const void* src_pinned, long long bytes, void* stream);
+int ctk_multi_sqnorm(const void* rows, int ntensors, long long nchunks, float* out_sq, void* stream);
+int ctk_multi_adam(const void* rows, int ntensors, long long nchunks, const float* sq, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int adamw, long long step, float max_norm,
+                   int write_clipped_grad, void* stream);
 
 #ifdef __cplusplus
 }

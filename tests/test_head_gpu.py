@@ -74,3 +74,35 @@ def test_pair_logits(cuda_dev):
     lt = torch.tensor([1.0], device=cuda_dev)
     out = ops.pair_logits(t, i[0].contiguous(), lt)
     assert (out - (t @ i[0]) * lt.exp()).abs().max().item() < 1e-5
+
+
+# ----------------------------------------------------------------------------- optimizer tail
+@pytest.mark.gpu
+@pytest.mark.parametrize("wd,max_norm", [(0.0, 0.5), (0.0, None), (0.01, 1e-3)])
+def test_fused_clip_adam_matches_torch(cuda_dev, wd, max_norm):
+    """FusedClipAdam == clip_grad_norm_ + torch.optim.Adam / AdamW (optimizer.py:14-24, CTCLIPTrainer.py:711-715)
+    over tensors of awkward sizes (unaligned tails, > 1 chunk, a parameter without gradient), 3 steps."""
+    import torch
+    from vit_exp_b200.optim import FusedClipAdam
+    g = torch.Generator().manual_seed(11)
+    shapes = [(3,), (1,), (257, 129), (70001,), (64, 1024), (5, 7, 11)]
+    ref_p = [torch.nn.Parameter(torch.randn(*s, generator=g).to(cuda_dev)) for s in shapes] + \
+            [torch.nn.Parameter(torch.randn(9, generator=g).to(cuda_dev))]                     # never gets a gradient
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref_opt = (torch.optim.AdamW if wd > 0 else torch.optim.Adam)(ref_p, lr=1e-2, betas=(0.9, 0.99), weight_decay=wd)
+    our_opt = FusedClipAdam(our_p, lr=1e-2, betas=(0.9, 0.99), weight_decay=wd, max_grad_norm=max_norm)
+    for step in range(3):
+        grads = [torch.randn(*s, generator=g).to(cuda_dev) * (10.0 if step == 1 else 0.01) for s in shapes]
+        for p, q, gr in zip(ref_p, our_p, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        norm_ref = None
+        if max_norm is not None:
+            norm_ref = torch.nn.utils.clip_grad_norm_([p for p in ref_p if p.grad is not None], max_norm)
+        ref_opt.step()
+        norm = our_opt.step()
+        if max_norm is not None:
+            assert abs(norm.item() - norm_ref.item()) <= 1e-5 * norm_ref.item()
+        for p, q in zip(ref_p, our_p):
+            assert torch.allclose(p, q, rtol=2e-5, atol=1e-7), (step, tuple(p.shape), (p - q).abs().max().item())
+    assert torch.equal(ref_p[-1], our_p[-1])

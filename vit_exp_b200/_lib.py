@@ -47,6 +47,10 @@ SIGNATURES = {
     "ctk_peg_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ctk_cpb_fwd": (_i, [_vp] * 9 + [_i, _i, _i, _i, _vp]),
     "ctk_cpb_bwd": (_i, [_vp] * 13 + [_i, _i, _i, _i, _vp]),
+    "ctk_opt_chunk_elems": (_i, []),
+    "ctk_copy_from_pinned": (_i, [_vp, _vp, _ll, _vp]),
+    "ctk_multi_sqnorm": (_i, [_vp, _i, _ll, _vp, _vp]),
+    "ctk_multi_adam": (_i, [_vp, _i, _ll, _vp, _f, _f, _f, _f, _f, _i, _ll, _f, _i, _vp]),
     "ctk_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ctk_attn_bwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _i, _vp]),
     "ctk_qknorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _ll, _i, _vp]),
