@@ -49,6 +49,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner on
+# fd 1 when the first communicator is created), so file descriptor 1 is pointed at stderr for the whole run and
+# the result line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def gemm_traffic_sample():
     """Per-launch DRAM bytes of the tcgen05 GEMM family from the committed `ncu --set full` captures
     (profiles/r1_ncu_gemm_b8_*.csv: 16 launches of one B=8 train step, forward and backward ranges)."""
@@ -326,7 +346,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_train_step_baseline(max_steps=1)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -408,7 +428,7 @@ def run_reference(args):
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -423,6 +443,7 @@ def main():
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: libctk clip+Adam (2 launches); torch: clip_grad_norm_ + torch.optim.Adam(fused=True)")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
