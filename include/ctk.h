@@ -166,8 +166,8 @@ int ctk_cpb_bwd(const float* dtable, const float* w0, const float* w1, const flo
  * Dispatch (same results, different kernels): 24x24-token slices with a table -> tcgen05/TMEM kernels
  * (attention_tc.cu, attention_tc_bwd.cu); 24-token sequences without a table, 2/4/8 heads -> TMA ring +
  * warp MMA (attention_seq24.cu); anything else -> mma.sync / SIMT kernels (attention.cu).
- * Environment switches read once per process: CTK_ATTN_LEGACY=1 forces the last group, CTK_DBIAS_TC=1
- * selects the tcgen05 bias-table-gradient kernel.
+ * Environment switches read once per process: CTK_ATTN_LEGACY=1 forces the last group, CTK_DBIAS_TC=0
+ * selects the mma.sync bias-table-gradient kernel instead of the tcgen05 one.
  * ------------------------------------------------------------------------------------------ */
 int ctk_attn_fwd(const void* qkv, const float* table, void* out, float* lse, int nseq, int L,
                  int heads, int gh, int gw, void* stream);

@@ -137,8 +137,8 @@ def test_ctvit_batch_independence(cuda_dev):
 
 
 def test_bias_table_gradient_tcgen05_variant(cuda_dev):
-    """The opt-in tcgen05 bias-gradient kernel (CTK_DBIAS_TC=1: dS summed over slices by an identity MMA into
-    TMEM) agrees with the default mma.sync kernel; the switch is read once per process, hence the subprocess."""
+    """The tcgen05 bias-gradient kernel (default; dS summed over slices by an identity MMA into TMEM) agrees with
+    the mma.sync kernel (CTK_DBIAS_TC=0); the switch is read once per process, hence the subprocess."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = r'''

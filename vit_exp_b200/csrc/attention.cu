@@ -839,7 +839,7 @@ extern "C" int ctk_attn_bwd(const void* qkv, const float* table, const void* out
     const bool hb = table != nullptr;
     const bool tc_path = hb && L == 576 && gh == 24 && gw == 24 && !attn_legacy();
     static int dbias_tc = -1;
-    if (dbias_tc < 0) { const char* e = getenv("CTK_DBIAS_TC"); dbias_tc = (e && e[0] == '1') ? 1 : 0; }
+    if (dbias_tc < 0) { const char* e = getenv("CTK_DBIAS_TC"); dbias_tc = (e && e[0] == '0') ? 0 : 1; }
     if (tc_path) {
         if ((rc = ctk_attn_bwd_tc(qkv, table, dout, lse, delta, dqkv, dtable, dbias_tc, nseq, heads, s))) return rc;
         if (dbias_tc) return CTK_OK;

@@ -12,8 +12,7 @@
 //   DKV = false : T1 = Q_t, T2 = dO_t, R1 = K, R2 = V;   acc0 += dS R1_c
 //   DKV = true  : T1 = K_t, T2 = V_t,  R1 = Q, R2 = dO;  acc0 += dS^T R1_c (dK), acc1 += P^T R2_c (dV)
 // TMEM columns: X1 [0,96)  X2 [96,192)  acc0 [192,224)  acc1 [224,256); two CTAs per SM.
-// The bias-table gradient has a tcgen05 formulation too (attn_dbias_tc_kernel below, opt-in: CTK_DBIAS_TC=1); the
-// default is attn_bwd_dbias_kernel of attention.cu.
+// The bias-table gradient is attn_dbias_tc_kernel below (CTK_DBIAS_TC=0 selects attn_bwd_dbias_kernel of attention.cu).
 #include "attention_tc.cuh"
 
 using namespace attn_tc;
@@ -319,15 +318,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_box, const __gri
 // itself - G += dS * I_64 (tcgen05.mma TS against an identity tile in shared memory, fp32
 // accumulation in TMEM) - so the softmax warps spend no instruction on the reduction.  After the
 // last slice G is scattered once into a shared-memory copy of the table and flushed with one
-// atomic per touched entry.  Operands of the next four slices are in flight in a 5-stage TMA ring and
-// the logit products are double-buffered in TMEM, so the tensor core works on slice n+1 while the
-// softmax warps turn slice n into dS.  One CTA per SM (512 TMEM columns):
-// X buffer b: X1 = Q K^T [128 b, +64), X2 = dO V^T [128 b + 64, +64);  G [256, 320).
+// atomic per touched entry.  Operands (and the rows' lse / delta) of the next two slices are in flight in
+// a 3-stage TMA ring.  Two CTAs per SM; TMEM columns: X1 = Q K^T [0,64)  X2 = dO V^T [64,128)  G [128,192).
 // ---------------------------------------------------------------------------------------------
 constexpr int DC = 64;                      // keys per block
 constexpr int NDC = TL / DC;                // 9
-constexpr int D_STAGES = 5;
-constexpr int D_NSOFT = 16;                // softmax warps: 4 per TMEM lane quarter, 16 keys of the chunk each
+constexpr int D_STAGES = 3;
+constexpr int D_NSOFT = 8;                 // softmax warps: 2 per TMEM lane quarter, 32 keys of the chunk each
 constexpr int D_NTHR = 32 * (1 + D_NSOFT);
 constexpr int D_STAT_OFF = 2 * Q_BYTES + 2 * DC * 64;          // lse[128] | delta[128] of the tile's rows for this slice
 constexpr int D_STAGE_BYTES = D_STAT_OFF + 2 * QT * 4;
@@ -335,10 +332,10 @@ constexpr int D_OFF_ID = D_STAGES * D_STAGE_BYTES;
 constexpr int D_OFF_TAB = D_OFF_ID + 2 * DC * 64;
 constexpr int D_OFF_ACC = D_OFF_TAB + TWW * TPW * 4;
 constexpr int D_OFF_BAR = D_OFF_ACC + TWW * TPW * 4;
-constexpr int D_NBAR = 2 * D_STAGES + 5;
+constexpr int D_NBAR = 2 * D_STAGES + 3;
 constexpr int D_OFF_SLOT = D_OFF_BAR + D_NBAR * 8;
 constexpr int D_SMEM_BYTES = D_OFF_SLOT + 16 + 1024;
-constexpr uint32_t D_COL_X1 = 0, D_COL_X2 = 64, D_COL_G = 256, D_XBUF = 128, D_TMEM_COLS = 512;   // X buffer b at columns 128 b
+constexpr uint32_t D_COL_X1 = 0, D_COL_X2 = 64, D_COL_G = 128, D_TMEM_COLS = 256;
 
 // 16 columns (keys base + J0 .. base + J0 + 15, base = PHASE mod 24 inside its grid row) -> bf16 pairs of dS
 __device__ __forceinline__ void dsoft_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * D_NSOFT) : "memory"); }
@@ -366,11 +363,16 @@ __device__ __forceinline__ void dbias_chunk(uint32_t t_x1, uint32_t t_x2, uint32
     tc_ld_32x32_x16(t_x2, x2);
     tc_wait_ld();
     dbias_block<PHASE, 0>(x1, x2, ds, bias_addr, lse2, delta);
+    tc_ld_32x32_x16(t_x1 + 16, x1);
+    tc_ld_32x32_x16(t_x2 + 16, x2);
+    tc_wait_ld();
     tc_st_32x32_x8(t_x2, ds);
+    dbias_block<PHASE, 16>(x1, x2, ds, bias_addr, lse2, delta);
+    tc_st_32x32_x8(t_x2 + 8, ds);
     tc_wait_st();
 }
 
-__global__ void __launch_bounds__(D_NTHR, 1)
+__global__ void __launch_bounds__(D_NTHR, 2)
 attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __grid_constant__ CUtensorMap tmap_do_tile,
                      const __grid_constant__ CUtensorMap tmap_qkv_chunk, const float* __restrict__ table,
                      const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dtable, int nseq,
@@ -383,9 +385,9 @@ attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + D_OFF_BAR);
     uint64_t* full = bars;                       // [3] TMA -> MMA
     uint64_t* empty = bars + D_STAGES;           // [3] MMA -> TMA (X products of the stage have retired)
-    uint64_t* bar_S = bars + 2 * D_STAGES;       // [2] MMA -> softmax: X buffer b is ready
-    uint64_t* bar_P = bar_S + 2;                 // [2] softmax -> MMA: dS is in X buffer b
-    uint64_t* bar_O = bar_S + 4;                 // MMA -> softmax: G of the item is complete
+    uint64_t* bar_S = bars + 2 * D_STAGES;       // MMA -> softmax: the logit products of a slice are in TMEM
+    uint64_t* bar_P = bar_S + 1;                 // softmax -> MMA: dS of the slice is in TMEM
+    uint64_t* bar_O = bar_S + 2;                 // MMA -> softmax: G of the item is complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D_OFF_SLOT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -413,10 +415,8 @@ attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __
             tma_prefetch_desc(&tmap_do_tile);
             tma_prefetch_desc(&tmap_qkv_chunk);
             for (int i = 0; i < 2 * D_STAGES; ++i) mbar_init(&bars[i], 1);
-            mbar_init(&bar_S[0], 1);
-            mbar_init(&bar_S[1], 1);
-            mbar_init(&bar_P[0], D_NSOFT);
-            mbar_init(&bar_P[1], D_NSOFT);
+            mbar_init(bar_S, 1);
+            mbar_init(bar_P, D_NSOFT);
             mbar_init(bar_O, 1);
             mbar_fence_init();
         }
@@ -464,50 +464,34 @@ attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __
                 return true;
             };
             for (int i = 0; i < D_STAGES - 1; ++i) load_next();
-            // X(n): both logit products of consumed pair n into X buffer n & 1
-            auto issue_x = [&](int n) {
-                const int st = n % D_STAGES;
-                mbar_wait(&full[st], (uint32_t)(n / D_STAGES) & 1u);
-                tc_fence_after();
-                const uint32_t sb = ring_a + st * D_STAGE_BYTES;
-                const uint32_t xb = tmem_base + (uint32_t)(n & 1) * D_XBUF;
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    tc_mma_f16(xb + D_COL_X1, umma_desc(sb + k * 32, 16, 512, SW64),
-                               umma_desc(sb + 2 * Q_BYTES + k * 32, 16, 512, SW64), idesc_x, k);
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    tc_mma_f16(xb + D_COL_X2, umma_desc(sb + Q_BYTES + k * 32, 16, 512, SW64),
-                               umma_desc(sb + 2 * Q_BYTES + DC * 64 + k * 32, 16, 512, SW64), idesc_x, k);
-                tc_commit(&bar_S[n & 1]);
-                tc_commit(&empty[st]);
-            };
-            // total number of (item, slice) pairs of this CTA
-            int total = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                int sp, h, t, c;
-                decode(item, sp, h, t, c);
-                total += s_begin(sp + 1) - s_begin(sp);
-            }
             uint32_t p_par = 0;
             int n = 0;                                            // consumed (item, slice) pairs
-            if (total > 0) issue_x(0);
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 int sp, h, t, c;
                 decode(item, sp, h, t, c);
                 const int s0 = s_begin(sp), s1 = s_begin(sp + 1);
                 for (int s = s0; s < s1; ++s, ++n) {
                     load_next();                                  // D_STAGES - 1 pairs ahead
-                    // the next pair's logits go to the other X buffer while the softmax warps work on this one
-                    // (its previous content, dS of pair n-1, was consumed by the G product issued before)
-                    if (n + 1 < total) issue_x(n + 1);
-                    mbar_wait(&bar_P[n & 1], (p_par >> (n & 1)) & 1u);
-                    p_par ^= 1u << (n & 1);
+                    const int st = n % D_STAGES;
+                    mbar_wait(&full[st], (uint32_t)(n / D_STAGES) & 1u);
                     tc_fence_after();
-                    const uint32_t xb = tmem_base + (uint32_t)(n & 1) * D_XBUF;
+                    const uint32_t sb = ring_a + st * D_STAGE_BYTES;
 #pragma unroll
-                    for (int k = 0; k < DC / 16; ++k)               // G += dS * I (the 16 keys of warp group k at columns 16 k)
-                        tc_mma_f16_ts(tmem_base + D_COL_G, xb + D_COL_X2 + k * 16,
+                    for (int k = 0; k < 2; ++k)
+                        tc_mma_f16(tmem_base + D_COL_X1, umma_desc(sb + k * 32, 16, 512, SW64),
+                                   umma_desc(sb + 2 * Q_BYTES + k * 32, 16, 512, SW64), idesc_x, k);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        tc_mma_f16(tmem_base + D_COL_X2, umma_desc(sb + Q_BYTES + k * 32, 16, 512, SW64),
+                                   umma_desc(sb + 2 * Q_BYTES + DC * 64 + k * 32, 16, 512, SW64), idesc_x, k);
+                    tc_commit(bar_S);
+                    tc_commit(&empty[st]);
+                    mbar_wait(bar_P, p_par);
+                    p_par ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < DC / 16; ++k)               // G += dS * I (keys of warp half k/2 at columns 32 (k/2))
+                        tc_mma_f16_ts(tmem_base + D_COL_G, tmem_base + D_COL_X2 + (k >> 1) * 32 + (k & 1) * 8,
                                       umma_desc(sId_a + (k >> 1) * (DC * 64) + (k & 1) * 32, 16, 512, SW64), idesc_g,
                                       (s > s0 || k > 0) ? 1u : 0u);
                 }
@@ -518,7 +502,7 @@ attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __
         // ================================ softmax warps ================================
         const int sw = warp - 1;
         const int quarter = warp & 3;
-        const int hsel = sw >> 2;                                  // which 16 keys of the chunk
+        const int hsel = sw >> 2;                                  // which 32 keys of the chunk
         const int row = quarter * 32 + lane;
         const int st_id = threadIdx.x - 32;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -539,15 +523,15 @@ attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __
             dsoft_sync();
             const int i = t * QT + row;
             const bool active = t * QT + quarter * 32 < TL;
-            const int kbase = c * DC + hsel * 16;                  // first key of this warp's 16
+            const int kbase = c * DC + hsel * 32;                  // first key of this warp's 32
             const int phase = kbase % TGW;                         // 0, 8 or 16
             // address of bias(i, key at the start of kbase's grid row)
             const uint32_t rel = (uint32_t)(TOFF + (i / TGW) * TPW + (i % TGW) - (kbase / TGW) * TPW);
             const uint32_t bias_addr = sTab_a + 4u * rel;
             for (int s = s0; s < s1; ++s, ++n) {
-                const uint32_t t_x1 = t_lane + (uint32_t)(n & 1) * D_XBUF + D_COL_X1 + hsel * 16, t_x2 = t_x1 + (D_COL_X2 - D_COL_X1);
-                mbar_wait(&bar_S[n & 1], (s_par >> (n & 1)) & 1u);
-                s_par ^= 1u << (n & 1);
+                const uint32_t t_x1 = t_lane + D_COL_X1 + hsel * 32, t_x2 = t_lane + D_COL_X2 + hsel * 32;
+                mbar_wait(bar_S, s_par);
+                s_par ^= 1;
                 tc_fence_after();
                 if (active) {
                     // row statistics of this slice came with the stage (acquire its bulk copies through the stage's own
@@ -561,17 +545,17 @@ attn_dbias_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_tile, const __
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_P[n & 1]);
+                if (lane == 0) mbar_arrive(bar_P);
             }
             mbar_wait(bar_O, o_par);
             o_par ^= 1;
             tc_fence_after();
             if (active) {
-                uint32_t g[16];
-                tc_ld_32x32_x16(t_lane + D_COL_G + hsel * 16, g);
+                uint32_t g[32];
+                tc_ld_32x32(t_lane + D_COL_G + hsel * 32, g);
                 tc_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
+                for (int e = 0; e < 32; ++e) {
                     const int j = phase + e;
                     const uint32_t a = sAcc_a + 4u * (rel - (uint32_t)((j / TGW) * TPW + j % TGW));
                     asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(__uint_as_float(g[e])) : "memory");
@@ -629,8 +613,8 @@ int ctk_attn_bwd_tc(const void* qkv, const float* table, const void* dout, const
     auto g = reinterpret_cast<__nv_bfloat16*>(dqkv);
     if ((rc = launch_bwd<false>(ta, tb, tc, td, table, lse, delta, g, nseq, heads, stream))) return rc;
     if ((rc = launch_bwd<true>(ta, tb, tc, td, table, lse, delta, g, nseq, heads, stream))) return rc;
-    // bias-table gradient: the mma.sync kernel of attention.cu (fp32 dS, 0.62 ms at B=8) unless dtable_tc is set -
-    // the tcgen05 formulation below is correct but latency-bound at 0.65-0.7 ms this round
+    // bias-table gradient: tcgen05 formulation below (0.50 ms at B=8) unless dtable_tc == 0, in which case the caller
+    // runs the mma.sync kernel of attention.cu (fp32 dS, 0.62 ms)
     if (!dtable_tc) return CTK_OK;
     CUtensorMap te;
     const unsigned int box_chunk[2] = {32, DC};
@@ -640,12 +624,13 @@ int ctk_attn_bwd_tc(const void* qkv, const float* table, const void* dout, const
         CTK_CUDA(cudaFuncSetAttribute(attn_dbias_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
         configured = true;
     }
-    // one CTA per SM (512 TMEM columns); split the slices so that there are ~5 items per CTA
+    // two CTAs per SM (256 TMEM columns each): one CTA's control / MMA round trip is covered by the other's
+    // softmax; split the slices so that there are ~5 items per CTA
     const int blocks = heads * NQT * NDC;
-    int nsplit = (5 * ctk_num_sms() + blocks - 1) / blocks;
+    int nsplit = (10 * ctk_num_sms() + blocks - 1) / blocks;
     if (nsplit > nseq) nsplit = nseq;
     if (nsplit < 1) nsplit = 1;
-    long long grid = ctk_num_sms();
+    long long grid = 2LL * ctk_num_sms();
     if (grid > (long long)blocks * nsplit) grid = (long long)blocks * nsplit;
     attn_dbias_tc_kernel<<<(unsigned)grid, D_NTHR, D_SMEM_BYTES, stream>>>(tb, td, te, table, lse, delta, dtable, nseq, heads, nsplit);
     CTK_LAUNCH_CHECK();
