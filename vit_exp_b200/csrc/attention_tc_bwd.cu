@@ -61,7 +61,9 @@ __device__ __forceinline__ void bwd_block(const uint32_t (&x1)[16], const uint32
             const int j = J0 + e + u;
             const uint32_t pos = 4u * (uint32_t)((j / TGW) * TPW + j % TGW);
             const float b = lds_f32(DKV ? bias_addr + pos : bias_addr - pos);
-            p[u] = fast_exp2(fmaf(__uint_as_float(x1[e + u]), LOG2E, b) - (DKV ? ls[e + u] : lse2));
+            // DKV: ls = natural-log lse of the column's query (staged raw by the bulk copy); else lse2 = lse * log2e
+            p[u] = DKV ? fast_exp2(fmaf(__uint_as_float(x1[e + u]) - ls[e + u], LOG2E, b))
+                       : fast_exp2(fmaf(__uint_as_float(x1[e + u]), LOG2E, b) - lse2);
             d[u] = p[u] * (__uint_as_float(x2[e + u]) - (DKV ? dl[e + u] : delta));
         }
         if (DKV) pp[e >> 1] = pack_bf16x2(p[0], p[1]);
@@ -127,7 +129,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_box, const __gri
             auto load_r = [&](int item) {
                 const int s = item % nseq, h = item / nseq;
                 for (int c = 0; c < NCH; ++c) {
-                    mbar_expect_tx(&bar_R[c], 2 * CH_BYTES);
+                    mbar_expect_tx(&bar_R[c], 2 * CH_BYTES + ((DKV && c == 0) ? 2 * TL * 4 : 0));
+                    if (DKV && c == 0) {          // lse / delta of the item's 576 queries travel with the first box
+                        const long long so = ((long long)s * heads + h) * TL;
+                        bulk_load_1d(sL, lse + so, TL * 4, &bar_R[0]);
+                        bulk_load_1d(sL + TL, delta + so, TL * 4, &bar_R[0]);
+                    }
                     if (DKV) {
                         tma_load_2d(sR1 + c * CH_BYTES, &tmap_qkv_box, &bar_R[c], h * 32, s * TL + c * CH);
                         tma_load_2d(sR2 + c * CH_BYTES, &tmap_do_box, &bar_R[c], h * 32, s * TL + c * CH);
@@ -140,7 +147,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_box, const __gri
             auto load_t = [&](int g) {
                 const int item = g / NQT, t = g % NQT;
                 const int s = item % nseq, h = item / nseq;
-                mbar_expect_tx(bar_T, 2 * Q_BYTES);
+                const uint32_t stat_bytes = DKV ? 0u : (uint32_t)min(QT, TL - t * QT) * 4u;
+                mbar_expect_tx(bar_T, 2 * Q_BYTES + 2 * stat_bytes);
+                if (!DKV) {                       // lse / delta of the tile's query rows travel with the tile
+                    const long long so = ((long long)s * heads + h) * TL + t * QT;
+                    bulk_load_1d(sL, lse + so, stat_bytes, bar_T);
+                    bulk_load_1d(sL + TL, delta + so, stat_bytes, bar_T);
+                }
                 if (DKV) {
                     tma_load_2d(sT1, &tmap_qkv_tile, bar_T, inner + h * 32, s * TL + t * QT);
                     tma_load_2d(sT2, &tmap_qkv_tile, bar_T, 2 * inner + h * 32, s * TL + t * QT);
@@ -208,26 +221,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_box, const __gri
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const uint32_t sTab_a = smem_u32(sTab), sL_a = smem_u32(sL);
         uint32_t s_par = 0, o_par = 0;
-        int cur_item = -1, cur_head = -1;
-        for (int g = g0; g < g1; ++g) {
+        int cur_item = -1, cur_head = -1, n = 0;
+        for (int g = g0; g < g1; ++g, ++n) {
             const int item = g / NQT, t = g % NQT;
             const int s = item % nseq, h = item / nseq;
-            const long long stat_off = ((long long)s * heads + h) * TL;
             if (item != cur_item) {
                 cur_item = item;
-                if (DKV || h != cur_head) soft_sync();          // everyone is done with the previous item's tables
-                if (h != cur_head) {
+                if (h != cur_head) {                             // rare: items are head-major
+                    soft_sync();                                 // everyone is done with the previous head's table
                     cur_head = h;
                     const float* tg = table + (long long)h * TNOFF;
                     for (int i = st; i < TNOFF; i += 32 * NSOFT) sTab[(i / TWW) * TPW + i % TWW] = __ldg(tg + i) * LOG2E;
+                    soft_sync();
                 }
-                if (DKV) {
-                    for (int i = st; i < TL; i += 32 * NSOFT) {
-                        sL[i] = __ldg(lse + stat_off + i) * LOG2E;
-                        sL[TL + i] = __ldg(delta + stat_off + i);
-                    }
-                }
-                soft_sync();
+                // DKV: the item's lse / delta arrive with the first resident box (bulk copies, no global loads here)
+                if (DKV) mbar_wait(&bar_R[0], (uint32_t)(item - g0 / NQT) & 1u);
             }
             const int i = t * QT + row;                            // query (dQ) or key (dK/dV) of this thread
             const bool active = t * QT + quarter * 32 < TL;        // warp-uniform
@@ -239,8 +247,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv_box, const __gri
                     bias_row = sTab_a + 4u * (uint32_t)(TOFF - pos);
                 } else {
                     bias_row = sTab_a + 4u * (uint32_t)(TOFF + pos);
-                    lse2 = __ldg(lse + stat_off + i) * LOG2E;
-                    dlt = __ldg(delta + stat_off + i);
+                    mbar_wait(bar_T, (uint32_t)n & 1u);          // the tile's statistics came with its operands
+                    lse2 = sL[row] * LOG2E;
+                    dlt = sL[TL + row];
                 }
             }
 #pragma unroll 1
