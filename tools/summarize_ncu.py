@@ -24,7 +24,7 @@ if os.path.exists(lc) and len(sys.argv) <= 2:
         cnt[k] += 1
     T = sum(tot.values())
     with open(os.path.join(out_dir, f"{tag}_launches_summary.md"), "w") as f:
-        f.write(f"# ncu launch list, one train step (B=8/GPU): {sum(cnt.values())} launches, {T/1e6:.2f} ms serialised\n\n")
+        f.write(f"# ncu launch list, a window of {sum(cnt.values())} consecutive launches (about 1.5 train steps, B=8/GPU) inside the timed region: {T/1e6:.2f} ms serialised\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` on `python bench.py --steps 2 --warmup 3 "
                 "--no-cpu-baseline`; cold-cache, serialised - compare shares, not absolutes.\n\n| ms | share | launches | kernel |\n|---|---|---|---|\n")
         for k, v in sorted(tot.items(), key=lambda x: -x[1])[:45]:

@@ -40,3 +40,15 @@ t = timeit(lambda: ops.layernorm_bwd(dyb, x, g, mean, rstd, dg, dbt, dx=dxo, acc
 print(f"ln bwd (dy bf16, accum dx f32, dx bf16) {t*1e3:7.1f} us  {(0.5 + 1 + 1 + 1 + 0.5) * MB / t / 1e3:6.2f} TB/s")
 t = timeit(lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dg, dbt, dx=dxo, accum=False))
 print(f"ln bwd (dy f32, dx f32) {t*1e3:7.1f} us  {(3) * MB / t / 1e3:6.2f} TB/s")
+# qknorm backward (in place on dqkv)
+heads = 8
+qkv = torch.randn(M, 768, device=dev).bfloat16()
+dqkv = torch.randn(M, 768, device=dev).bfloat16()
+rn = torch.rand(M, 2 * heads, device=dev) + 0.5
+qs = torch.ones(32, device=dev); ks = torch.ones(32, device=dev)
+dqs = torch.zeros(32, device=dev); dks = torch.zeros(32, device=dev)
+from vit_exp_b200 import _lib
+lib = _lib.load()
+t = timeit(lambda: lib.ctk_qknorm_bwd(dqkv.data_ptr(), qkv.data_ptr(), rn.data_ptr(), qs.data_ptr(), ks.data_ptr(), 8.0,
+                                      dqs.data_ptr(), dks.data_ptr(), M, heads, torch.cuda.current_stream().cuda_stream))
+print(f"qknorm bwd {t*1e3:7.1f} us  {(3 * M * 512 * 2) / 1e6 / t / 1e3:6.2f} TB/s (q,k of qkv + dqkv read, dqkv write)")
