@@ -197,6 +197,37 @@ def test_cuda_graph_replay_matches_eager(cuda_dev):
         res[graphs] = outs
         if graphs:
             assert any(eg.fwd is not None and eg.bwd for eg in vit._graphs.values()), "graphs were never captured"
+    # two forwards in flight (micro-batches) before any backward: the second one must not clobber the first one's
+    # saved activations (it falls back to eager launches)
+    torch.manual_seed(0)
+    vit = CTViT(dim=128, codebook_size=256, image_size=80, patch_size=20, temporal_patch_size=10, spatial_depth=1,
+                temporal_depth=1, dim_head=32, heads=4).to(cuda_dev).eval()
+    vids = [torch.rand(2, 1, 30, 80, 80, generator=_g(10 + i)).to(cuda_dev) for i in range(2)]
+    w = torch.randn(2, 3, 4, 4, 128, generator=_g(20)).to(cuda_dev)
+    for _ in range(4):                                        # reach the replay regime
+        for q in vit.parameters():
+            q.grad = None
+        (vit(vids[0], return_encoded_tokens=True) * w).sum().backward()
+    ref = {}
+    for k in range(2):
+        for q in vit.parameters():
+            q.grad = None
+        (vit(vids[k], return_encoded_tokens=True) * w).sum().backward()
+        ref[k] = {n: q.grad.detach().clone() for n, q in vit.named_parameters() if q.grad is not None}
+    for q in vit.parameters():
+        q.grad = None
+    la = (vit(vids[0], return_encoded_tokens=True) * w).sum()
+    lb = (vit(vids[1], return_encoded_tokens=True) * w).sum()
+    la.backward()
+    ga = {n: q.grad.detach().clone() for n, q in vit.named_parameters() if q.grad is not None}
+    for q in vit.parameters():
+        q.grad = None
+    lb.backward()
+    gb = {n: q.grad.detach().clone() for n, q in vit.named_parameters() if q.grad is not None}
+    for got, want in ((ga, ref[0]), (gb, ref[1])):
+        for n in want:
+            d = (got[n].double() - want[n].double()).norm() / want[n].double().norm().clamp_min(1e-30)
+            assert d.item() < 1e-4, n
     for step in range(5):
         t0, g0 = res[False][step]
         t1, g1 = res[True][step]

@@ -12,6 +12,7 @@ written backward of the whole encoder.  There is no CPU or torch fallback.
 from __future__ import annotations
 
 import os
+import weakref
 
 import math
 from pathlib import Path
@@ -410,6 +411,15 @@ class _EncoderGraph:
         self.bwd = {}            # keyed by the layout of the incoming gradient (broadcast or dense)
         self.pool = None
         self.failed = False
+        self.owner = None        # weakref to the token of the forward whose activations sit in the static buffers
+
+
+class _Token:
+    """Lives on the autograd ctx of a graphed forward; `done` once its backward has consumed the static activations."""
+    __slots__ = ("done", "__weakref__")
+
+    def __init__(self):
+        self.done = False
 
 
 def _graph_key(video, training, params, embed):
@@ -443,7 +453,12 @@ class _CTViTEncode(torch.autograd.Function):
                     vit._graphs.clear()
                 eg = vit._graphs[key] = _EncoderGraph()
             eg.calls += 1
+            prev = eg.owner() if eg.owner is not None else None
             if eg.failed or eg.calls <= _EncoderGraph.WARMUP:
+                eg = None
+            elif prev is not None and not prev.done:
+                # a previous graphed forward is still waiting for its backward (e.g. two micro-batches before one
+                # backward): replaying would overwrite its saved activations, so this call runs eagerly
                 eg = None
         if eg is None:
             out, ind, pre_vq, saved = _encode_forward(vit, video, params, save=True, training=training)
@@ -473,7 +488,10 @@ class _CTViTEncode(torch.autograd.Function):
         ops.GRAPH_LAUNCHES += f["launches"]
         out, ind, pre_vq, saved = f["outs"]
         ctx.saved, ctx.graph = saved, eg
-        out, ind, pre_vq = out.detach(), ind.detach(), pre_vq.detach()
+        ctx.token = _Token()
+        eg.owner = weakref.ref(ctx.token)
+        # the caller gets private copies (3 small stream-ordered copies): the static buffers are rewritten by the next replay
+        out, ind, pre_vq = out.clone(), ind.clone(), pre_vq.clone()
         ctx.mark_non_differentiable(ind)
         return out, ind, pre_vq
 
@@ -497,6 +515,7 @@ class _CTViTEncode(torch.autograd.Function):
         b["dy"].copy_(dy)
         b["graph"].replay()
         ops.GRAPH_LAUNCHES += b["launches"]
+        ctx.token.done = True
         return (None, None, None, *b["grads"])
 
 
