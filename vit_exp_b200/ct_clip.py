@@ -174,10 +174,20 @@ class CTCLIP(nn.Module):
             prio = -1 if os.environ.get("CTK_TEXT_STREAM_PRIORITY", "1") != "0" else 0
             self._side_stream = torch.cuda.Stream(device=image.device, priority=prio)
         side = self._side_stream
-        side.wait_stream(cur)
+        # If the encoder forward can be replayed from its CUDA graph it is enqueued FIRST (one launch), so the GPU
+        # works on it while the host spends ~9 ms enqueueing the text tower; its autograd node is still created
+        # AFTER the tower's nodes (vt(..., _launched=handle) below), so the encoder's backward is launched first too.
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        vt = self.visual_transformer
+        handle = vt.encode_begin(image) if hasattr(vt, "encode_begin") else None
+        side.wait_event(ready)
         with torch.cuda.stream(side):
             enc_text = self._encode_text(text)
-        enc_image = self.visual_transformer(image, return_encoded_tokens=True)
+        if handle is not None:
+            enc_image = vt(image, return_encoded_tokens=True, _launched=handle)
+        else:
+            enc_image = vt(image, return_encoded_tokens=True)
         cur.wait_stream(side)
         enc_text.record_stream(cur)
         return enc_text, enc_image

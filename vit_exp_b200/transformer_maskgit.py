@@ -439,59 +439,70 @@ def _capture(fn, pool):
     return g, out, int(lib.ctk_launch_count() - n0)
 
 
+_EAGER = object()       # "the launch decision was taken: this call runs on eager launches"
+
+
+def _graph_launch(vit: "CTViT", video: torch.Tensor, training: bool, params: List[torch.Tensor]):
+    """Decide how this forward runs and, on the graph path, LAUNCH it now (patch gather + replay).
+    Returns `_EAGER` or a dict(eg, out, ind, pre_vq, saved, token) that `_CTViTEncode.forward` binds to an autograd
+    node later.  Splitting launch from binding lets CTCLIP enqueue the encoder before the text tower's ~350 small
+    launches (9 ms of host time during which the GPU would otherwise idle) while the encoder's autograd node is still
+    created last, so that its backward is launched first."""
+    if not (vit.cuda_graphs and ops.GEMM_PROFILE is None and not torch.cuda.is_current_stream_capturing()):
+        return _EAGER
+    key = _graph_key(video, training, params, vit.vq._codebook.embed)
+    eg = vit._graphs.get(key)
+    if eg is None:
+        if len(vit._graphs) >= 4:                       # shapes keep changing: stay eager
+            vit._graphs.clear()
+        eg = vit._graphs[key] = _EncoderGraph()
+    eg.calls += 1
+    prev = eg.owner() if eg.owner is not None else None
+    if eg.failed or eg.calls <= _EncoderGraph.WARMUP:
+        return _EAGER
+    if prev is not None and not prev.done:
+        # a previous graphed forward is still waiting for its backward (e.g. two micro-batches before one
+        # backward): replaying would overwrite its saved activations, so this call runs eagerly
+        return _EAGER
+    cfg = _Cfg(vit, video)
+    if eg.fwd is None:
+        try:
+            eg.pool = torch.cuda.graph_pool_handle()
+            st_x = ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2)            # static patch buffers
+            g, outs, n = _capture(lambda: _encode_forward(vit, video, params, save=True, training=training,
+                                                          xhat=st_x[0]), eg.pool)
+            eg.fwd = dict(graph=g, outs=outs, launches=n, xbuf=st_x)
+        except Exception as e:                                                  # pragma: no cover
+            import warnings
+            warnings.warn(f"CTViT: CUDA-graph capture failed ({e}); staying on eager launches")
+            eg.failed = True
+            torch.cuda.synchronize()
+            return _EAGER
+    f = eg.fwd
+    ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2, out=f["xbuf"])
+    f["graph"].replay()
+    ops.GRAPH_LAUNCHES += f["launches"]
+    out, ind, pre_vq, saved = f["outs"]
+    token = _Token()
+    eg.owner = weakref.ref(token)
+    # the caller gets private copies (3 small stream-ordered copies): the static buffers are rewritten by the next replay
+    return dict(eg=eg, out=out.clone(), ind=ind.clone(), pre_vq=pre_vq.clone(), saved=saved, token=token)
+
+
 class _CTViTEncode(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, vit, video, training, *params):
+    def forward(ctx, vit, video, training, launched, *params):
         params = list(params)
         ctx.vit, ctx.params, ctx.graph = vit, params, None
-        eg = None
-        if vit.cuda_graphs and ops.GEMM_PROFILE is None and not torch.cuda.is_current_stream_capturing():
-            key = _graph_key(video, training, params, vit.vq._codebook.embed)
-            eg = vit._graphs.get(key)
-            if eg is None:
-                if len(vit._graphs) >= 4:                       # shapes keep changing: stay eager
-                    vit._graphs.clear()
-                eg = vit._graphs[key] = _EncoderGraph()
-            eg.calls += 1
-            prev = eg.owner() if eg.owner is not None else None
-            if eg.failed or eg.calls <= _EncoderGraph.WARMUP:
-                eg = None
-            elif prev is not None and not prev.done:
-                # a previous graphed forward is still waiting for its backward (e.g. two micro-batches before one
-                # backward): replaying would overwrite its saved activations, so this call runs eagerly
-                eg = None
-        if eg is None:
+        if launched is None:
+            launched = _graph_launch(vit, video, training, params)
+        if launched is _EAGER:
             out, ind, pre_vq, saved = _encode_forward(vit, video, params, save=True, training=training)
             ctx.saved = saved
             ctx.mark_non_differentiable(ind)
             return out, ind, pre_vq.detach()
-        cfg = _Cfg(vit, video)
-        if eg.fwd is None:
-            try:
-                eg.pool = torch.cuda.graph_pool_handle()
-                st_x = ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2)            # static patch buffers
-                g, outs, n = _capture(lambda: _encode_forward(vit, video, params, save=True, training=training,
-                                                              xhat=st_x[0]), eg.pool)
-                eg.fwd = dict(graph=g, outs=outs, launches=n, xbuf=st_x)
-            except Exception as e:                                                  # pragma: no cover
-                import warnings
-                warnings.warn(f"CTViT: CUDA-graph capture failed ({e}); staying on eager launches")
-                eg.failed = True
-                torch.cuda.synchronize()
-                out, ind, pre_vq, saved = _encode_forward(vit, video, params, save=True, training=training)
-                ctx.saved = saved
-                ctx.mark_non_differentiable(ind)
-                return out, ind, pre_vq.detach()
-        f = eg.fwd
-        ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2, out=f["xbuf"])
-        f["graph"].replay()
-        ops.GRAPH_LAUNCHES += f["launches"]
-        out, ind, pre_vq, saved = f["outs"]
-        ctx.saved, ctx.graph = saved, eg
-        ctx.token = _Token()
-        eg.owner = weakref.ref(ctx.token)
-        # the caller gets private copies (3 small stream-ordered copies): the static buffers are rewritten by the next replay
-        out, ind, pre_vq = out.clone(), ind.clone(), pre_vq.clone()
+        ctx.saved, ctx.graph, ctx.token = launched["saved"], launched["eg"], launched["token"]
+        out, ind, pre_vq = launched["out"], launched["ind"], launched["pre_vq"]
         ctx.mark_non_differentiable(ind)
         return out, ind, pre_vq
 
@@ -502,7 +513,7 @@ class _CTViTEncode(torch.autograd.Function):
         if eg is None or ops.GEMM_PROFILE is not None:
             grads = _encode_backward(ctx.vit, ctx.params, ctx.saved, dtokens)
             ctx.saved = None
-            return (None, None, None, *grads)
+            return (None, None, None, None, *grads)
         cfg = ctx.saved["cfg"]
         dy, bcast = _unpack_dtokens(dtokens, cfg)
         bkey = (bcast, tuple(dy.shape))
@@ -516,7 +527,7 @@ class _CTViTEncode(torch.autograd.Function):
         b["graph"].replay()
         ops.GRAPH_LAUNCHES += b["launches"]
         ctx.token.done = True
-        return (None, None, None, *b["grads"])
+        return (None, None, None, None, *b["grads"])
 
 
 class CTViT(nn.Module):
@@ -580,18 +591,33 @@ class CTViT(nn.Module):
         p += _layer_params(self.enc_temporal_transformer)
         return p
 
-    def encode_with_aux(self, video: torch.Tensor):
+    def encode_begin(self, video: torch.Tensor):
+        """Optional early launch (used by CTCLIP): if this training-shape forward can be replayed from its CUDA graph,
+        enqueue it NOW on the current stream and return a handle for `forward(..., _launched=handle)`, which only
+        binds the autograd node.  Returns None when there is nothing to gain (no-grad call)."""
+        assert video.is_cuda, "CTViT runs on sm_100a only: move the module and its input to a CUDA device"
+        params = self._flat_params()
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in params)):
+            return None
+        video = video.contiguous().float()
+        with torch.no_grad():
+            return (_graph_launch(self, video, self.training, params), video)
+
+    def encode_with_aux(self, video: torch.Tensor, _launched=None):
         """returns (tokens after VQ, code indices, tokens before VQ)"""
         assert video.is_cuda, "CTViT runs on sm_100a only: move the module and its input to a CUDA device"
-        video = video.contiguous().float()
         params = self._flat_params()
+        if _launched is not None:
+            launched, video = _launched
+            return _CTViTEncode.apply(self, video, self.training, launched, *params)
+        video = video.contiguous().float()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _CTViTEncode.apply(self, video, self.training, *params)
+            return _CTViTEncode.apply(self, video, self.training, None, *params)
         out, ind, pre, _ = _encode_forward(self, video, params, save=False, training=self.training)
         return out, ind, pre
 
     def forward(self, video, mask=None, return_recons=False, return_recons_only=False, return_discr_loss=False,
-                apply_grad_penalty=True, return_only_codebook_ids=False, return_encoded_tokens=False):
+                apply_grad_penalty=True, return_only_codebook_ids=False, return_encoded_tokens=False, _launched=None):
         assert video.ndim in {4, 5}
         if video.ndim == 4:
             video = video[:, :, None]
@@ -599,7 +625,7 @@ class CTViT(nn.Module):
         b, c, f, *image_dims = video.shape
         assert tuple(image_dims) == self.image_size
         assert mask is None, "frame masks are not used on the CT-CLIP path"
-        tokens, indices, _ = self.encode_with_aux(video)
+        tokens, indices, _ = self.encode_with_aux(video, _launched=_launched)
         if return_only_codebook_ids:
             return indices.reshape(b, -1)
         if return_encoded_tokens:
