@@ -648,8 +648,6 @@ __device__ __forceinline__ void peg_scatter_plane(const float* pl, int W2, int n
             }
 #pragma unroll
             for (int k0 = 0; k0 < 3; ++k0) {
-                constexpr int dummy = 0;
-                (void)dummy;
                 const int slot = MODE == 0 ? (R + 2 - k0) % 3 : (R + 3 - k0) % 3;
                 if (use[k0]) {
 #pragma unroll
