@@ -143,7 +143,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_model(dev, seed=0):
+def build_model(dev, seed=0, config=None):
     import torch
     from transformers import BertConfig, BertModel
     from vit_exp_b200.ct_clip import CTCLIP
@@ -152,7 +152,7 @@ def build_model(dev, seed=0):
     vit = CTViT(dim=512, codebook_size=8192, image_size=480, patch_size=20, temporal_patch_size=10,
                 spatial_depth=4, temporal_depth=4, dim_head=32, heads=8)          # run_train.py:56-66
     bert = BertModel(BertConfig(vocab_size=30522, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
-    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=512, dim_latent=512, config={})
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=512, dim_latent=512, config=dict(config or {}))
     return clip.to(dev)
 
 
@@ -187,7 +187,7 @@ def run_ours(args):
     lib = _lib.load()
     B = args.batch_per_gpu
 
-    clip = build_model(dev, seed=0)
+    clip = build_model(dev, seed=0, config={} if args.sync_loss_read else {"defer_loss_read": True})
     clip.train()
     bert = clip.text_transformer
     model = clip
@@ -237,7 +237,7 @@ def run_ours(args):
             torch.nn.utils.clip_grad_norm_(params, 0.5)                        # CTCLIPTrainer.py:711-712
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return ld["cl_loss"]                                                     # float: D2H read of the loss
+        return float(ld["cl_loss"])                   # D2H read of the loss, every step (deferred: after the step is enqueued)
 
     def barrier():
         if world > 1:
@@ -359,6 +359,8 @@ def run_ours(args):
                    "e2e_pipeline": "host batch (pinned) -> H2D on a side stream into one of 3 device slots while the "
                                    "previous step computes; loss read back (.item()) every step",
                    "text_tower": "stock PyTorch BertModel under bf16 autocast",
+                   "loss_read": "loss.item() inside forward" if args.sync_loss_read else
+                                "config['defer_loss_read']: async D2H copy, read every step after the step is enqueued",
                    "launch": "encoder forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
                              else "eager launches"},
         "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s",
@@ -476,6 +478,9 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (MB)")
+    ap.add_argument("--sync-loss-read", action="store_true",
+                    help="CTCLIP returns cl_loss via loss.item() inside forward (reference behaviour: a host sync between "
+                         "forward and backward); default: config['defer_loss_read'], the same value read back at the end of the step")
     ap.add_argument("--half-host", action="store_true", help="also time the e2e pipeline with fp16 host volumes (informational)")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: libctk clip+Adam (2 launches); torch: clip_grad_norm_ + torch.optim.Adam(fused=True)")

@@ -101,6 +101,15 @@ def test_tiny_ctclip_loss_and_grads_match_reference(cuda_dev, gold):
     loss, ld = clip(batch, device=cuda_dev, accelerator=TorchDistAccelerator())
     assert abs(loss.item() - g["loss"].item()) / abs(g["loss"].item()) < 1e-3
     assert abs(ld["cl_loss"] - g["cl_loss"]) / abs(g["cl_loss"]) < 1e-3
+    # opt-in deferred read-back of the same scalar (config["defer_loss_read"]): a float-like that synchronises on use
+    clip.config["defer_loss_read"] = True
+    vit.eval()                                   # keep the codebook fixed for the second forward
+    _, ld2 = clip(batch, device=cuda_dev, accelerator=TorchDistAccelerator())
+    _, ld3 = clip(batch, device=cuda_dev, accelerator=TorchDistAccelerator())
+    assert not isinstance(ld2["cl_loss"], float) and float(ld2["cl_loss"]) == float(ld3["cl_loss"])
+    assert f"{ld2['cl_loss']:.4f}" == f"{float(ld3['cl_loss']):.4f}" and ld2["cl_loss"] + 0.0 == float(ld2["cl_loss"])
+    clip.config["defer_loss_read"] = False
+    vit.train()
     loss.backward()
     assert rel_l2(clip.to_text_latent.weight.grad, g["grad_to_text_latent"]) < 2e-2
     assert rel_l2(clip.to_visual_latent.weight.grad, g["grad_to_visual_latent"]) < 2e-2

@@ -100,6 +100,55 @@ class _ClipHead(torch.autograd.Function):
         return dcls, dtok, dwt, dwv, dtemp, None
 
 
+class DeferredFloat:
+    """A scalar that is on its way from the device: float(x), format(x), comparisons and arithmetic synchronise on
+    first use.  Returned in the loss dict instead of `loss.item()` when `config["defer_loss_read"]` is set."""
+
+    __slots__ = ("_host", "_event", "_value")
+
+    def __init__(self, t: torch.Tensor):
+        self._host = torch.empty((), dtype=torch.float32, pin_memory=True)
+        self._host.copy_(t.detach().float(), non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        self._value = None
+
+    def __float__(self):
+        if self._value is None:
+            self._event.synchronize()
+            self._value = float(self._host)
+            self._host = None
+        return self._value
+
+    def item(self):
+        return float(self)
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def __repr__(self):
+        return repr(float(self))
+
+    __str__ = __repr__
+
+    def __add__(self, o): return float(self) + float(o)
+    __radd__ = __add__
+    def __sub__(self, o): return float(self) - float(o)
+    def __rsub__(self, o): return float(o) - float(self)
+    def __mul__(self, o): return float(self) * float(o)
+    __rmul__ = __mul__
+    def __truediv__(self, o): return float(self) / float(o)
+    def __rtruediv__(self, o): return float(o) / float(self)
+    def __neg__(self): return -float(self)
+    def __abs__(self): return abs(float(self))
+    def __lt__(self, o): return float(self) < float(o)
+    def __le__(self, o): return float(self) <= float(o)
+    def __gt__(self, o): return float(self) > float(o)
+    def __ge__(self, o): return float(self) >= float(o)
+    def __eq__(self, o): return float(self) == float(o)
+    def __hash__(self): return hash(float(self))
+
+
 class CTCLIP(nn.Module):
     """Reference constructor: ct_clip.py:467-660 (only the arguments reachable from the launchers
     are honoured; the x-clip default encoders, MLM / visual-SSL branches and segmentation heads are
@@ -205,6 +254,10 @@ class CTCLIP(nn.Module):
         enc_text, enc_image = self._encode_both(text, image)                        # (B, L, dt), (B, t, h, w, C)
         loss, _, _ = _ClipHead.apply(enc_text[:, 0, :], enc_image, self.to_text_latent.weight,
                                      self.to_visual_latent.weight, self.temperature, accelerator)
+        if self.config.get("defer_loss_read", False):
+            # opt-in: same value, read back lazily (async copy to pinned memory now, synchronise on first use), so the
+            # host can enqueue the backward pass while the forward still runs
+            return loss, {"cl_loss": DeferredFloat(loss)}
         return loss, {"cl_loss": loss.item()}      # the reference also syncs here (ct_clip.py:1384)
 
     @torch.no_grad()
