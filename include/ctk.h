@@ -62,7 +62,10 @@ typedef enum {
                               aux0 = fp32 [M, ld_aux0] reciprocal norms at head index (col+i1)/32.
                               attention.py:145-160 (q from LayerNorm(x), k/v from raw x) */
     CTK_EPI_ATOMIC_F32 = 6,/* C fp32 += alpha * acc via atomics (split-K); row_map permutes output rows */
-    CTK_EPI_ARGMAX = 7     /* C = uint64 [M]: atomicMax of (orderable(acc)<<32 | ~col)  (VQ code search)   */
+    CTK_EPI_ARGMAX = 7,    /* C = uint64 [M]: atomicMax of (orderable(acc)<<32 | ~col)  (VQ code search)   */
+    CTK_EPI_GELU = 8,      /* text tower (HF BertIntermediate, ct_clip.py:1271): C = U bf16 [M,N] = acc + bias
+                              (pre-activations, kept for the backward pass), aux0 = bf16 [M,N] = gelu(U), erf form */
+    CTK_EPI_GELU_BWD = 9   /* acc = dG; aux0 = U bf16 [M,N]; C = dU bf16 = dG * gelu'(U)                      */
 } ctk_epilogue;
 
 typedef struct {

@@ -13,7 +13,8 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libctk.so"
 
 CTK_OK = 0
-EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_GEGLU, EPI_GEGLU_BWD, EPI_QKV, EPI_ATOMIC_F32, EPI_ARGMAX = range(8)
+(EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_GEGLU, EPI_GEGLU_BWD, EPI_QKV, EPI_ATOMIC_F32, EPI_ARGMAX, EPI_GELU,
+ EPI_GELU_BWD) = range(10)
 
 _vp = C.c_void_p
 _ll = C.c_longlong

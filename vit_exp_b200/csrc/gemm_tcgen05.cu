@@ -312,6 +312,72 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
                 sg.commit();
             }
         }
+    } else if constexpr (EPI == CTK_EPI_GELU) {
+        // U (mc0) = acc + bias, kept in bf16 for the backward pass; G (mc1) = gelu(U), exact erf form
+        // (HF BertIntermediate, hidden_act "gelu").  Block h2 of a pass uses slots 2*h2 (U) and 2*h2+1 (G).
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 64) {
+            sg.begin();
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int c = hf * 128 + cc + h2 * 32;
+                const int col = n0 + c;
+                if (col >= N) break;                     // warp-uniform
+                float v[32];
+                ld_acc(t_row + c, v);
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+                }
+                uint8_t* su = sg.base + (2 * h2) * SLOT_BYTES;
+                slot_write_bf16(su, lane, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float cdf, pdf;
+                    normal_cdf_pdf(v[i], cdf, pdf);
+                    v[i] *= cdf;
+                }
+                slot_write_bf16(su + SLOT_BYTES, lane, v);
+                sg.fence();
+                sg.store(mc0, 2 * h2, col, row0);
+                sg.store(mc1, 2 * h2 + 1, col, row0);
+            }
+            sg.commit();
+        }
+    } else if constexpr (EPI == CTK_EPI_GELU_BWD) {
+        // accumulator = dG; mc1 = U (bf16 pre-activations); mc0 = dU = dG * gelu'(U).  Chunk i (32 columns)
+        // lives in slot 2*(i&1); the U block of chunk i+1 is prefetched while chunk i is processed.
+        const int cbase = n0 + hf * 128;
+        int nvalid = (N - cbase + 31) / 32;
+        nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
+        if (nvalid > 0) {
+            sg.begin();
+            sg.issue_load(0, mc1, 0, cbase, 0, 0, row0, SLOT_BYTES, 1);
+#pragma unroll 1
+            for (int i = 0; i < nvalid; ++i) {
+                const int par = i & 1;
+                const int col = cbase + i * 32;
+                if (i + 1 < nvalid) {
+                    if (i >= 1) sg.begin();                 // chunk i-1's store has left the other buffer
+                    sg.issue_load(par ^ 1, mc1, (par ^ 1) * 2, col + 32, 0, 0, row0, SLOT_BYTES, 1);
+                }
+                float dg[32], u[32];
+                ld_acc(t_row + hf * 128 + i * 32, dg);
+                sg.wait_load(par);
+                uint8_t* slot = sg.base + (par * 2) * SLOT_BYTES;
+                slot_read_bf16(slot, lane, u);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    float cdf, pdf;
+                    normal_cdf_pdf(u[q], cdf, pdf);
+                    dg[q] *= fmaf(u[q], pdf, cdf);           // gelu'(u) = Phi(u) + u phi(u)
+                }
+                slot_write_bf16(slot, lane, dg);
+                sg.fence();
+                sg.store(mc0, par * 2, col, row0);
+                sg.commit();
+            }
+        }
     } else if constexpr (EPI == CTK_EPI_ATOMIC_F32) {
         float* C = reinterpret_cast<float*>(p.C);
         const long long orow = row_ok ? (p.row_map ? (long long)p.row_map[row] : row) : -1;
@@ -697,8 +763,11 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
         splits = (kb_total + per - 1) / per;
     }
     if (epilogue == CTK_EPI_BF16 || epilogue == CTK_EPI_F32 || epilogue == CTK_EPI_RESID_F32 ||
-        epilogue == CTK_EPI_QKV || epilogue == CTK_EPI_GEGLU_BWD)
+        epilogue == CTK_EPI_QKV || epilogue == CTK_EPI_GEGLU_BWD || epilogue == CTK_EPI_GELU ||
+        epilogue == CTK_EPI_GELU_BWD)
         CTK_REQUIRE(N % 32 == 0, CTK_ERR_SHAPE, "gemm: N %% 32 != 0 for a block epilogue");
+    if (epilogue == CTK_EPI_GELU || epilogue == CTK_EPI_GELU_BWD)
+        CTK_REQUIRE(e->aux0 && !a_mn_major, CTK_ERR_SHAPE, "gemm: GELU epilogues need the aux0 buffer and K-major operands");
     if (epilogue == CTK_EPI_GEGLU)
         CTK_REQUIRE(N % BN == 0 && e->aux0, CTK_ERR_SHAPE, "gemm: GEGLU needs N %% 256 == 0 and an H buffer");
     if (epilogue == CTK_EPI_GEGLU_BWD)
@@ -753,6 +822,11 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
             rc = make_block_tmap(&tc0, e->C, false, 2LL * N, M, e->ldc);
             if (!rc) rc = make_block_tmap(&tc1, e->aux0, false, 2LL * N, M, e->ld_aux0);
             break;
+        case CTK_EPI_GELU:
+        case CTK_EPI_GELU_BWD:
+            rc = make_block_tmap(&tc0, e->C, false, N, M, e->ldc);
+            if (!rc) rc = make_block_tmap(&tc1, e->aux0, false, N, M, e->ld_aux0);
+            break;
         default:
             break;
     }
@@ -765,7 +839,13 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
                               : launch<E, false, false, true>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream); \
         return a_mn_major ? launch<E, true, true, false>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream)      \
                           : launch<E, false, false, false>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream);
+#define CTK_GEMM_CASE_KMAJOR(E)                                                                            \
+    case E:                                                                                                \
+        if (pair) return launch<E, false, false, true>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream);     \
+        return launch<E, false, false, false>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream);
     switch (epilogue) {
+        CTK_GEMM_CASE_KMAJOR(CTK_EPI_GELU)
+        CTK_GEMM_CASE_KMAJOR(CTK_EPI_GELU_BWD)
         CTK_GEMM_CASE(CTK_EPI_BF16)
         CTK_GEMM_CASE(CTK_EPI_F32)
         CTK_GEMM_CASE(CTK_EPI_RESID_F32)
@@ -778,6 +858,7 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
             break;
     }
 #undef CTK_GEMM_CASE
+#undef CTK_GEMM_CASE_KMAJOR
     ctk_set_error("gemm: unknown epilogue %d", epilogue);
     return CTK_ERR_SHAPE;
 }
