@@ -43,6 +43,9 @@ GF_VQ = 116.0
 GF_GEMM_FWD = GF_PATCH + 8 * GF_LAYER_GEMM + GF_VQ
 GF_GEMM_BWD = GF_PATCH + 2 * 8 * GF_LAYER_GEMM             # patch: wgrad only; layers: dgrad + wgrad
 GF_GEMM_STEP = GF_GEMM_FWD + GF_GEMM_BWD
+# --text-tower ctk: BERT-base at 512 tokens, per report and layer: QKV 1.812 + out 0.604 + intermediate 2.416 + output 2.416
+# GF forward (attention core excluded), dgrad + wgrad in the backward pass
+GF_TEXT_GEMM_STEP = 3 * 12 * (1.812 + 0.604 + 2.416 + 2.416)
 
 
 def log(*a):
@@ -187,7 +190,10 @@ def run_ours(args):
     lib = _lib.load()
     B = args.batch_per_gpu
 
-    clip = build_model(dev, seed=0, config={} if args.sync_loss_read else {"defer_loss_read": True})
+    cfg = {} if args.sync_loss_read else {"defer_loss_read": True}
+    if args.text_tower == "ctk":
+        cfg["ctk_text_tower"] = True
+    clip = build_model(dev, seed=0, config=cfg)
     clip.train()
     bert = clip.text_transformer
     model = clip
@@ -339,7 +345,8 @@ def run_ours(args):
     for a, b, tag in prof:
         by_epi[tag] = by_epi.get(tag, 0.0) + a.elapsed_time(b)
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    achieved_tf = GF_GEMM_STEP * B / gemm_ms                                   # GFLOP / ms == TFLOP/s
+    gf_step = GF_GEMM_STEP + (GF_TEXT_GEMM_STEP if args.text_tower == "ctk" else 0.0)
+    achieved_tf = gf_step * B / gemm_ms                                        # GFLOP / ms == TFLOP/s
     traffic, traffic_n = gemm_traffic_sample()
 
     if rank != 0:
@@ -358,7 +365,9 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (1.77 GB of volumes per step); two alternating batches",
                    "e2e_pipeline": "host batch (pinned) -> H2D on a side stream into one of 3 device slots while the "
                                    "previous step computes; loss read back (.item()) every step",
-                   "text_tower": "stock PyTorch BertModel under bf16 autocast",
+                   "text_tower": ("BertModel parameters through libctk (vit_exp_b200/text_tower.py), dropout 0"
+                                  if args.text_tower == "ctk" else
+                                  "stock PyTorch BertModel under bf16 autocast, dropout 0 (both arms)"),
                    "loss_read": "loss.item() inside forward" if args.sync_loss_read else
                                 "config['defer_loss_read']: async D2H copy, read every step after the step is enqueued",
                    "launch": "encoder forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
@@ -379,7 +388,7 @@ def run_ours(args):
                                      "(ncu --set full, profiles/r1_ncu_gemm_b8_*.csv)",
                      "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": len(prof),
                      "gemm_share_of_step": gemm_ms / (ms_dev / args.steps),
-                     "algorithmic_gflop_per_volume": GF_GEMM_STEP, "ms_by_epilogue": by_epi},
+                     "algorithmic_gflop_per_volume": gf_step, "ms_by_epilogue": by_epi},
         "loss": loss_val,
     }
     if not args.no_cpu_baseline and world == 1:
@@ -484,6 +493,9 @@ def main():
     ap.add_argument("--half-host", action="store_true", help="also time the e2e pipeline with fp16 host volumes (informational)")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: libctk clip+Adam (2 launches); torch: clip_grad_norm_ + torch.optim.Adam(fused=True)")
+    ap.add_argument("--text-tower", default="hf", choices=["hf", "ctk"],
+                    help="hf: the BertModel runs as passed (stock PyTorch, bf16 autocast); ctk: its forward/backward run "
+                         "through libctk (vit_exp_b200/text_tower.py; opt-in until validated on hardware)")
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":
