@@ -121,3 +121,325 @@ def colsum_(dy, out):
     CALLS.append(("colsum", None))
     out.add_(dy.float().sum(0))
     return out
+
+
+# ================================================================================================
+# image encoder + contrastive head (contracts: include/ctk.h; callers: vit_exp_b200/transformer_maskgit.py,
+# vit_exp_b200/ct_clip.py).  `gemm_full` extends `gemm` with the epilogues / operand views those callers use.
+# ================================================================================================
+import torch.nn.functional as F  # noqa: E402
+
+from vit_exp_b200._lib import EPI_ARGMAX, EPI_GEGLU, EPI_GEGLU_BWD, EPI_QKV  # noqa: E402
+
+GRAPH_LAUNCHES = 0
+GEMM_PROFILE = None
+
+
+def gemm_full(a, b, epilogue, c, *, M, N, K, mn_major=False, lda=None, ldb=None, ldc=None, bias=None, resid=None,
+              ldr=None, aux0=None, ld_aux0=0, vec0=None, vec1=None, row_map=None, alpha=1.0, split_k=0, i0=0, i1=0):
+    """all epilogues; operands may be column-sliced views (their strides play the role of lda / ldb)."""
+    CALLS.append(("gemm", epilogue))
+    if mn_major:
+        acc = a[:K, :M].float().t() @ b[:K, :N].float()
+    else:
+        acc = a[:M, :K].float() @ b[:N, :K].float().t()
+    if bias is not None:
+        acc = acc + bias
+    if epilogue == EPI_BF16:
+        c[:M, :N] = (acc * alpha).to(c.dtype)
+    elif epilogue == EPI_F32:
+        c[:M, :N] = acc
+    elif epilogue == EPI_RESID_F32:
+        c[:M, :N] = acc + resid[:M, :N]
+    elif epilogue == EPI_GEGLU:                     # U interleaved per 128 hidden units: 128 value | 128 gate
+        u = acc.view(M, N // 256, 2, 128)
+        c[:M, :N] = acc.to(c.dtype)
+        aux0[:M, : N // 2] = (_gelu(u[:, :, 1]) * u[:, :, 0]).reshape(M, N // 2).to(aux0.dtype)
+    elif epilogue == EPI_GEGLU_BWD:                 # acc = dH [M, N]; aux0 = U [M, 2N]; c = dU [M, 2N]
+        u = aux0[:M, : 2 * N].float().view(M, N // 128, 2, 128)
+        dh = acc.view(M, N // 128, 128)
+        val, gate = u[:, :, 0], u[:, :, 1]
+        du = torch.stack([dh * _gelu(gate), dh * val * _gelu_grad(gate)], dim=2)
+        c[:M, : 2 * N] = du.reshape(M, 2 * N).to(c.dtype)
+    elif epilogue == EPI_QKV:
+        out = acc.clone()
+        nh = i0 // 32
+        if nh:
+            hd = acc[:, :i0].view(M, nh, 32)
+            rn = 1.0 / hd.norm(dim=-1).clamp_min(1e-12)
+            out[:, :i0] = (hd * rn[..., None] * vec0 * alpha).reshape(M, i0)
+            aux0[:M, i1 // 32: i1 // 32 + nh] = rn
+        c[:M, i1: i1 + N] = out.to(c.dtype)
+    elif epilogue == EPI_ATOMIC_F32:
+        upd = alpha * acc
+        if row_map is None:
+            c[:M, :N] += upd
+        else:
+            keep = row_map[:M] >= 0
+            c.index_add_(0, row_map[:M][keep].long(), upd[keep])
+    elif epilogue == EPI_ARGMAX:                    # the double stores the winning column itself (first maximum)
+        c[:M] = acc.argmax(dim=1)
+    else:
+        raise AssertionError(f"epilogue {epilogue} not emulated")
+    return c
+
+
+def cast_bf16_full(src, ld=None, col_scale=None, out=None):
+    rows, cols = src.shape
+    ld = ld or cols
+    v = src if col_scale is None else src * col_scale
+    res = torch.zeros(rows, ld, dtype=OPERAND) if out is None else out
+    res[:, :cols] = v.to(OPERAND)
+    return res
+
+
+def transpose_cast_bf16_full(src, ld=None, out=None):
+    rows, cols = src.shape
+    ld = ld or rows
+    res = torch.zeros(cols, ld, dtype=OPERAND) if out is None else out
+    res[:, :rows] = src.t().to(OPERAND)
+    return res
+
+
+def pack_ff_w1(w1, inner, inner_pad, want_t=True):
+    dim = w1.shape[1]
+    dst = torch.zeros(2 * inner_pad, dim, dtype=OPERAND)
+    row_map = torch.full((2 * inner_pad,), -1, dtype=torch.int32)
+    for blk in range(inner_pad // 128):
+        j0 = blk * 128
+        n = max(0, min(128, inner - j0))
+        if n:
+            dst[blk * 256: blk * 256 + n] = w1[j0: j0 + n].to(OPERAND)                          # value rows
+            dst[blk * 256 + 128: blk * 256 + 128 + n] = w1[inner + j0: inner + j0 + n].to(OPERAND)  # gate rows
+            row_map[blk * 256: blk * 256 + n] = torch.arange(j0, j0 + n, dtype=torch.int32)
+            row_map[blk * 256 + 128: blk * 256 + 128 + n] = torch.arange(inner + j0, inner + j0 + n, dtype=torch.int32)
+    return dst, (dst.t().contiguous() if want_t else None), row_map
+
+
+def patch_norm_fwd(video, pt, p1, p2, eps=1e-5, out=None):
+    B, c, D, H, W = video.shape
+    t, h, w = D // pt, H // p1, W // p2
+    x = video.reshape(B, c, t, pt, h, p1, w, p2).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B * t * h * w, -1)
+    K = x.shape[1]
+    ld = (K + 7) // 8 * 8
+    mean = x.mean(1)
+    rstd = torch.rsqrt(x.var(1, unbiased=False) + eps)
+    xhat = torch.zeros(x.shape[0], ld, dtype=OPERAND)
+    xhat[:, :K] = ((x - mean[:, None]) * rstd[:, None]).to(OPERAND)
+    if out is not None:
+        for dst, src in zip(out, (xhat, mean, rstd)):
+            dst.copy_(src)
+        return out
+    return xhat, mean, rstd
+
+
+def _perm_index(rows, perm_outer, perm_inner):
+    """output row of input row r: (g*outer + o)*inner + i -> (g*inner + i)*outer + o"""
+    r = torch.arange(rows)
+    if perm_inner == 0:
+        return r
+    g, rem = r // (perm_outer * perm_inner), r % (perm_outer * perm_inner)
+    o, i = rem // perm_inner, rem % perm_inner
+    return (g * perm_inner + i) * perm_outer + o
+
+
+def layernorm_fwd_full(x, gamma, beta=None, *, want_bf16=True, want_f32=False, want_raw=False, eps=1e-5,
+                       perm_outer=0, perm_inner=0, save_stats=True):
+    CALLS.append(("layernorm_fwd", None))
+    mean = x.mean(1)
+    rstd = torch.rsqrt(x.var(1, unbiased=False) + eps)
+    y = (x - mean[:, None]) * rstd[:, None] * gamma
+    if beta is not None:
+        y = y + beta
+    dst = _perm_index(x.shape[0], perm_outer, perm_inner)
+    yp = torch.empty_like(y)
+    yp[dst] = y
+    return (yp.to(OPERAND) if want_bf16 else None, yp if want_f32 else None, x.to(OPERAND) if want_raw else None,
+            mean if save_stats else None, rstd if save_stats else None)
+
+
+def layernorm_bwd_full(dy, x, gamma, mean, rstd, dgamma, dbeta=None, *, dx=None, accum=False, perm_outer=0,
+                       perm_inner=0, bcast_rows=0, dy_scale=1.0, dx_bf16=None):
+    CALLS.append(("layernorm_bwd", None))
+    rows = x.shape[0]
+    if bcast_rows:
+        dyf = dy.float().repeat_interleave(bcast_rows, dim=0) * dy_scale
+    else:
+        dyf = dy.float()[_perm_index(rows, perm_outer, perm_inner)] * dy_scale
+    xhat = (x - mean[:, None]) * rstd[:, None]
+    dgamma.add_((dyf * xhat).sum(0))
+    if dbeta is not None:
+        dbeta.add_(dyf.sum(0))
+    wdy = dyf * gamma
+    res = rstd[:, None] * (wdy - wdy.mean(1, keepdim=True) - xhat * (wdy * xhat).mean(1, keepdim=True))
+    if dx is None:
+        dx = res
+    elif accum:
+        dx.add_(res)
+    else:
+        dx.copy_(res)
+    if dx_bf16 is not None:
+        dx_bf16.copy_(dx.to(dx_bf16.dtype))
+    return dx
+
+
+def _peg_conv(x, w, b, shape):
+    B, n0, n1, n2 = shape
+    dim = x.shape[-1]
+    v = x.reshape(B, n0, n1, n2, dim).permute(0, 4, 1, 2, 3)
+    v = F.conv3d(F.pad(v, (1, 1, 1, 1, 2, 0)), w.reshape(dim, 1, 3, 3, 3), b, groups=dim)
+    return v.permute(0, 2, 3, 4, 1).reshape(x.shape)
+
+
+def peg_fwd(x, w, b, shape):
+    return _peg_conv(x, w, b, shape) + x
+
+
+def peg_bwd(dy, x, w, shape, dw, db, dx_bf16=None):
+    with torch.enable_grad():
+        xx, ww, bb = x.detach().clone().requires_grad_(), w.detach().clone().requires_grad_(), torch.zeros_like(db).requires_grad_()
+        y = _peg_conv(xx, ww, bb, shape) + xx
+        gx, gw, gb = torch.autograd.grad(y, (xx, ww, bb), dy)
+    dw.add_(gw)
+    db.add_(gb)
+    if dx_bf16 is not None:
+        dx_bf16.copy_(gx.to(dx_bf16.dtype))
+    return gx
+
+
+def _cpb_table(w0, b0, w1, b1, w2, b2, gh, gw):
+    dy, dx = torch.meshgrid(torch.arange(-(gh - 1), gh), torch.arange(-(gw - 1), gw), indexing="ij")
+    rel = torch.stack([dy, dx], dim=-1).reshape(-1, 2).float()
+    rel = torch.sign(rel) * torch.log(rel.abs() + 1)
+    h0 = F.leaky_relu(rel @ w0.t() + b0, 0.1)
+    h1 = F.leaky_relu(h0 @ w1.t() + b1, 0.1)
+    return (h1 @ w2.t() + b2).t().reshape(-1, 2 * gh - 1, 2 * gw - 1), h0, h1
+
+
+def cpb_fwd(w0, b0, w1, b1, w2, b2, gh, gw):
+    table, h0, h1 = _cpb_table(w0, b0, w1, b1, w2, b2, gh, gw)
+    return table.contiguous(), h0, h1
+
+
+def cpb_bwd(dtable, w0, w1, w2, h0, h1, gh, gw):
+    """gradients from the saved (post-LeakyReLU) activations, as the kernel computes them"""
+    heads = w2.shape[0]
+    dy, dx = torch.meshgrid(torch.arange(-(gh - 1), gh), torch.arange(-(gw - 1), gw), indexing="ij")
+    rel = torch.stack([dy, dx], dim=-1).reshape(-1, 2).float()
+    rel = torch.sign(rel) * torch.log(rel.abs() + 1)
+    slope = lambda h: torch.where(h > 0, torch.ones_like(h), torch.full_like(h, 0.1))
+    dout = dtable.reshape(heads, -1).t()
+    dz1 = (dout @ w2) * slope(h1)
+    dz0 = (dz1 @ w1) * slope(h0)
+    return [dz0.t() @ rel, dz0.sum(0), dz1.t() @ h0, dz1.sum(0), dout.t() @ h1, dout.sum(0)]
+
+
+def _bias_from_table(table, gh, gw):
+    ys, xs = torch.meshgrid(torch.arange(gh), torch.arange(gw), indexing="ij")
+    ys, xs = ys.reshape(-1), xs.reshape(-1)
+    iy = ys[:, None] - ys[None, :] + gh - 1
+    ix = xs[:, None] - xs[None, :] + gw - 1
+    return table[:, iy, ix]                                     # [heads, L, L]
+
+
+def _attn_core(qkv, table, nseq, L, heads, gh, gw):
+    inner = heads * 32
+    q, k, v = (qkv[:, i * inner:(i + 1) * inner].float().reshape(nseq, L, heads, 32).permute(0, 2, 1, 3) for i in range(3))
+    sim = q @ k.transpose(-1, -2)
+    if table is not None:
+        sim = sim + _bias_from_table(table, gh, gw)
+    lse = torch.logsumexp(sim, dim=-1)
+    out = (sim.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(nseq * L, inner)
+    return out, lse
+
+
+def attn_fwd(qkv, table, nseq, L, heads, gh=0, gw=0):
+    out, lse = _attn_core(qkv, table, nseq, L, heads, gh, gw)
+    return out.to(OPERAND), lse
+
+
+def attn_bwd(qkv, table, out, dout, lse, dtable, nseq, L, heads, gh=0, gw=0):
+    with torch.enable_grad():
+        qq = qkv.detach().float().clone().requires_grad_()
+        tt = table.detach().clone().requires_grad_() if table is not None else None
+        o, _ = _attn_core(qq, tt, nseq, L, heads, gh, gw)
+        gs = torch.autograd.grad(o, (qq, tt) if tt is not None else (qq,), dout.float())
+    if tt is not None:
+        dtable.add_(gs[1])
+    return gs[0].to(OPERAND)
+
+
+def qknorm_bwd_(dqkv, qkv, rnorm, q_scale, k_scale, alpha, dq_scale, dk_scale, heads):
+    inner = heads * 32
+    rows = qkv.shape[0]
+    for off, scale, a, dscale, hcol in ((0, q_scale, alpha, dq_scale, 0), (inner, k_scale, 1.0, dk_scale, heads)):
+        g = dqkv[:, off: off + inner].float().reshape(rows, heads, 32)
+        y = qkv[:, off: off + inner].float().reshape(rows, heads, 32)           # = raw * rn * scale * a
+        xhat = y / (scale * a)
+        dscale.add_((g * xhat * a).sum((0, 1)))
+        gx = g * scale * a
+        rn = rnorm[:, hcol: hcol + heads]
+        draw = rn[..., None] * (gx - xhat * (gx * xhat).sum(-1, keepdim=True))
+        dqkv[:, off: off + inner] = draw.reshape(rows, inner).to(dqkv.dtype)
+    return dqkv
+
+
+def l2norm_rows(x, want_f32=False):
+    xn = x / x.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    return xn.to(OPERAND), (xn if want_f32 else None)
+
+
+def vq_gather(best, embed):
+    ind = best.long()
+    return ind, embed[ind].float()
+
+
+def vq_ema_update_(xn_f32, ind, cluster_size, embed, decay=0.8):
+    C = embed.shape[0]
+    bins = torch.bincount(ind, minlength=C).float()
+    cluster_size.mul_(decay).add_(bins * (1 - decay))
+    esum = torch.zeros_like(embed).index_add_(0, ind, xn_f32)
+    hit = bins > 0
+    mean = esum[hit] / bins[hit][:, None]
+    en = embed / embed.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    en[hit] = mean / mean.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    embed.mul_(decay).add_(en * (1 - decay))
+
+
+def patch_affine_bwd(P, W, gamma, beta, db):
+    return gamma * P + beta * db[:, None], (W * P).sum(0), (W * db[:, None]).sum(0)
+
+
+def mean_pool(x):
+    return x.mean(1)
+
+
+def latent_fwd(x, W):
+    y = x @ W.t()
+    rn = 1.0 / y.norm(dim=-1).clamp_min(1e-12)
+    return y * rn[:, None], rn
+
+
+def latent_bwd(dlat, lat, rn, x, W, need_dx=True):
+    dy = rn[:, None] * (dlat - lat * (dlat * lat).sum(-1, keepdim=True))
+    return dy.t() @ x, (dy @ W if need_dx else None)
+
+
+def clip_loss_fwd_bwd(T, I, log_temp, b_local, row0, need_grad=True):
+    with torch.enable_grad():
+        t, i, lt = (v.detach().clone().requires_grad_() for v in (T, I, log_temp))
+        S = t @ i.t() * lt.exp()
+        n = S.shape[0]
+        lab = torch.arange(n)
+        loss = (F.cross_entropy(S, lab) + F.cross_entropy(S.t(), lab)) / 2 / b_local
+        gt, gi, glt = torch.autograd.grad(loss, (t, i, lt))
+    sl = slice(row0, row0 + b_local)
+    return torch.stack([loss.detach(), glt.reshape(())]), (torch.stack([gt[sl], gi[sl]]) if need_grad else None)
+
+
+def pair_logits(text_lat, image_lat, log_temp):
+    return (text_lat * image_lat).sum(-1) * log_temp.exp()
+
+
+def fill_(t, v):
+    return t.fill_(v)
