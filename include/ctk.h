@@ -65,7 +65,14 @@ typedef enum {
     CTK_EPI_ARGMAX = 7,    /* C = uint64 [M]: atomicMax of (orderable(acc)<<32 | ~col)  (VQ code search)   */
     CTK_EPI_GELU = 8,      /* text tower (HF BertIntermediate, ct_clip.py:1271): C = U bf16 [M,N] = acc + bias
                               (pre-activations, kept for the backward pass), aux0 = bf16 [M,N] = gelu(U), erf form */
-    CTK_EPI_GELU_BWD = 9   /* acc = dG; aux0 = U bf16 [M,N]; C = dU bf16 = dG * gelu'(U)                      */
+    CTK_EPI_GELU_BWD = 9,  /* acc = dG; aux0 = U bf16 [M,N]; C = dU bf16 = dG * gelu'(U)                      */
+    CTK_EPI_LSE_PART = 10, /* contrastive logits x = exp(*vec1) * acc (ct_clip.py:1347), never stored: C = fp32
+                              [ceil(N/128), M, 3] online softmax statistics (max, sum e^(x-max), sum x e^(x-max)) of
+                              every row over each block of 128 columns; aux0 (fp32 [M], may be NULL) receives the
+                              logit with row + i0 == col (the positives, ct_clip.py:1355-1358)                 */
+    CTK_EPI_CLIP_GRAD = 11 /* dloss/dlogit of the symmetric InfoNCE, scaled for the latent
+                              gradients: g = alpha * exp(*vec1) * (e^(x - vec0[row]) + e^(x - bias[col])
+                              - 2 [row + i0 == col + i1]); C = bf16 hi part [M,N], aux0 = bf16 lo part (g - hi) */
 } ctk_epilogue;
 
 typedef struct {
@@ -77,7 +84,7 @@ typedef struct {
     void* aux0;
     long long ld_aux0;
     const float* vec0;     /* [32] */
-    const float* vec1;     /* [32] */
+    const float* vec1;     /* [32]; LSE_PART / CLIP_GRAD: pointer to the log of the logit scale (device scalar) */
     const int* row_map;    /* [M] or NULL */
     float alpha;
     int i0;                /* QKV: number of leading columns to normalise */

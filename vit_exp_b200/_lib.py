@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libctk.so"
 
 CTK_OK = 0
 (EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_GEGLU, EPI_GEGLU_BWD, EPI_QKV, EPI_ATOMIC_F32, EPI_ARGMAX, EPI_GELU,
- EPI_GELU_BWD) = range(10)
+ EPI_GELU_BWD, EPI_LSE_PART, EPI_CLIP_GRAD) = range(12)
 
 _vp = C.c_void_p
 _ll = C.c_longlong

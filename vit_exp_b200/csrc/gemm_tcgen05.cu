@@ -378,6 +378,88 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
                 sg.commit();
             }
         }
+    } else if constexpr (EPI == CTK_EPI_LSE_PART) {
+        // Contrastive logits x = exp(*vec1) * acc (ct_clip.py:1347).  This warp reduces its 32 rows over its
+        // (up to) 128 columns to the online statistics (max, sum e^(x-max), sum x e^(x-max)) and writes them to
+        // part[(column block, row)][3]; column block = (n0 + hf*128) / 128.  The diagonal logit (row + i0 == col)
+        // goes to aux0[row] when aux0 != NULL.  Nothing else leaves the SM.
+        const int cbase = n0 + hf * 128;
+        if (cbase < N) {
+            const float scale = expf(__ldg(p.vec1));
+            float* diag = reinterpret_cast<float*>(p.aux0);
+            const long long drow = row + p.i0;
+            float m = -INFINITY, l = 0.f, w = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 128; cc += 32) {
+                const int col = cbase + cc;
+                if (col >= N) break;                     // warp-uniform
+                float v[32];
+                ld_acc(t_row + hf * 128 + cc, v);
+                float mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = col + i < N ? v[i] * scale : -INFINITY;
+                    mx = fmaxf(mx, v[i]);
+                }
+                if (mx > m) {                            // rescale the running sums to the new maximum
+                    const float r = expf(m - mx);        // m = -inf on the first chunk: r = 0, l = w = 0
+                    l *= r;
+                    w *= r;
+                    m = mx;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (col + i < N) {
+                        const float e = expf(v[i] - m);
+                        l += e;
+                        w = fmaf(e, v[i], w);
+                        if (diag && row_ok && drow == col + i) diag[row] = v[i];
+                    }
+                }
+            }
+            if (row_ok) {
+                float* dst = reinterpret_cast<float*>(p.C) + ((long long)(cbase / 128) * M + row) * 3;
+                dst[0] = m; dst[1] = l; dst[2] = w;
+            }
+        }
+    } else if constexpr (EPI == CTK_EPI_CLIP_GRAD) {
+        // dloss/dS of the symmetric InfoNCE for x = exp(*vec1) * acc:
+        //   g = alpha * exp(*vec1) * (e^(x - vec0[row]) + e^(x - bias[col]) - 2 [row + i0 == col + i1])
+        // (the logit scale is folded in so that the latent gradients are plain products with g), written as a
+        // bf16 pair hi (mc0) + lo (mc1), hi + lo = g to 16 mantissa bits.
+        const float scale = expf(__ldg(p.vec1));
+        const float la = row_ok ? __ldg(p.vec0 + row) : 0.f;
+        const float gs = p.alpha * scale;
+        const long long drow = row + p.i0;
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 64) {
+            sg.begin();
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int c = hf * 128 + cc + h2 * 32;
+                const int col = n0 + c;
+                if (col >= N) break;                     // warp-uniform
+                float v[32], lo[32];
+                ld_acc(t_row + c, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = v[i] * scale;
+                    float g = expf(x - la) + expf(x - __ldg(p.bias + col + i));
+                    if (drow == (long long)col + i + p.i1) g -= 2.f;
+                    g *= gs;
+                    const float hi = __bfloat162float(__float2bfloat16_rn(g));
+                    v[i] = hi;
+                    lo[i] = g - hi;
+                }
+                uint8_t* sh = sg.base + (2 * h2) * SLOT_BYTES;
+                slot_write_bf16(sh, lane, v);
+                slot_write_bf16(sh + SLOT_BYTES, lane, lo);
+                sg.fence();
+                sg.store(mc0, 2 * h2, col, row0);
+                sg.store(mc1, 2 * h2 + 1, col, row0);
+            }
+            sg.commit();
+        }
     } else if constexpr (EPI == CTK_EPI_ATOMIC_F32) {
         float* C = reinterpret_cast<float*>(p.C);
         const long long orow = row_ok ? (p.row_map ? (long long)p.row_map[row] : row) : -1;
@@ -764,10 +846,15 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     }
     if (epilogue == CTK_EPI_BF16 || epilogue == CTK_EPI_F32 || epilogue == CTK_EPI_RESID_F32 ||
         epilogue == CTK_EPI_QKV || epilogue == CTK_EPI_GEGLU_BWD || epilogue == CTK_EPI_GELU ||
-        epilogue == CTK_EPI_GELU_BWD)
+        epilogue == CTK_EPI_GELU_BWD || epilogue == CTK_EPI_CLIP_GRAD)
         CTK_REQUIRE(N % 32 == 0, CTK_ERR_SHAPE, "gemm: N %% 32 != 0 for a block epilogue");
     if (epilogue == CTK_EPI_GELU || epilogue == CTK_EPI_GELU_BWD)
         CTK_REQUIRE(e->aux0 && !a_mn_major, CTK_ERR_SHAPE, "gemm: GELU epilogues need the aux0 buffer and K-major operands");
+    if (epilogue == CTK_EPI_LSE_PART)
+        CTK_REQUIRE(e->vec1 && !a_mn_major, CTK_ERR_SHAPE, "gemm: LSE_PART needs the log-scale pointer and K-major operands");
+    if (epilogue == CTK_EPI_CLIP_GRAD)
+        CTK_REQUIRE(e->vec0 && e->vec1 && e->bias && e->aux0 && !a_mn_major, CTK_ERR_SHAPE,
+                    "gemm: CLIP_GRAD needs both lse vectors, the log-scale pointer, the lo buffer and K-major operands");
     if (epilogue == CTK_EPI_GEGLU)
         CTK_REQUIRE(N % BN == 0 && e->aux0, CTK_ERR_SHAPE, "gemm: GEGLU needs N %% 256 == 0 and an H buffer");
     if (epilogue == CTK_EPI_GEGLU_BWD)
@@ -824,6 +911,7 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
             break;
         case CTK_EPI_GELU:
         case CTK_EPI_GELU_BWD:
+        case CTK_EPI_CLIP_GRAD:
             rc = make_block_tmap(&tc0, e->C, false, N, M, e->ldc);
             if (!rc) rc = make_block_tmap(&tc1, e->aux0, false, N, M, e->ld_aux0);
             break;
@@ -846,6 +934,8 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     switch (epilogue) {
         CTK_GEMM_CASE_KMAJOR(CTK_EPI_GELU)
         CTK_GEMM_CASE_KMAJOR(CTK_EPI_GELU_BWD)
+        CTK_GEMM_CASE_KMAJOR(CTK_EPI_LSE_PART)
+        CTK_GEMM_CASE_KMAJOR(CTK_EPI_CLIP_GRAD)
         CTK_GEMM_CASE(CTK_EPI_BF16)
         CTK_GEMM_CASE(CTK_EPI_F32)
         CTK_GEMM_CASE(CTK_EPI_RESID_F32)

@@ -7,10 +7,17 @@
 //   pass 2  clip_reduce     : merge tile partials -> row/col log-sum-exp, loss, d(log temp).
 //   pass 3  clip_grad_tiles : recompute logits for the rank's rows / columns only and emit
 //                             G = dloss/dS stripes [b_local, N];  pass 4: dT = s G I, dI = s G^T T.
+// For N >= 1024 an opt-in variant (CTK_CLIP_LOSS_TC=1, clip_loss_tc below) runs the same passes with the
+// contractions on the tcgen05 GEMM (split-bf16 operands, fused LSE / gradient epilogues).
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "sgemm.cuh"
 
 namespace {
+
+constexpr int CLIP_TC_MIN_N = 1024;     // below this the loss is launch-latency bound: fp32 SIMT tiles
+constexpr int CLIP_TC_MAX_D = 512;      // latent width the tensor-core path's workspace is sized for
 
 // ---------------------------------------------------------------- mean pool
 __global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict__ pooled,
@@ -295,6 +302,24 @@ __global__ void pair_logits_kernel(const float* __restrict__ tl, const float* __
     if (lane == 0) out[p] = acc * expf(*log_temp);
 }
 
+// Tensor-core path (N >= 1024): fp32 latents as bf16 pairs x = hi + lo (16 mantissa bits).  The three products a
+// split-precision dot needs are laid side by side along K so that ONE bf16 GEMM with K = 3d evaluates
+// hi.hi + hi.lo + lo.hi:   text rows [hi | hi | lo],  image rows [hi | lo | hi].
+__global__ void clip_split_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ cat, long long n, int d,
+                                  int image_pattern) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * d) return;
+    const long long r = idx / d;
+    const int c = (int)(idx % d);
+    const float x = X[idx];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    __nv_bfloat16* row = cat + r * 3 * d;
+    row[c] = hi;
+    row[d + c] = image_pattern ? lo : hi;
+    row[2 * d + c] = image_pattern ? hi : lo;
+}
+
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 }  // namespace
@@ -359,9 +384,105 @@ extern "C" size_t ctk_clip_loss_ws_bytes(int N, int b_local) {
     size_t bytes = 0;
     bytes += align256(sizeof(float) * nblk * N * 3) * 2;     // row / col partials
     bytes += align256(sizeof(float) * N) * 3;                // diag, row_lse, col_lse
-    bytes += align256(sizeof(float) * (size_t)b_local * N * 2);
+    bytes += align256(sizeof(float) * (size_t)b_local * N * 2);   // G stripes (fp32, or bf16 hi/lo pairs)
+    if (N >= CLIP_TC_MIN_N)
+        bytes += align256((size_t)N * 3 * CLIP_TC_MAX_D * 2) * 2;     // tensor-core path: split latents [N, 3d] bf16 x 2
     return bytes;
 }
+
+namespace {
+
+// 0 = fp32 SIMT tiles (default), 1 = tcgen05 split-bf16 path for N >= 1024 (CTK_CLIP_LOSS_TC=1; opt-in until it has
+// been validated on hardware)
+bool clip_tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CTK_CLIP_LOSS_TC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+// Same four passes as the SIMT path with the three contractions on ctk_gemm_bf16:
+//   pass 1  two GEMMs (rows = texts, rows = images), K = 3d, epilogue LSE_PART: per-row online statistics over
+//           128-column blocks + the diagonal; the logits never leave the SM.
+//   pass 2  clip_reduce_kernel (shared with the SIMT path).
+//   pass 3  two GEMMs [N, b_local] with epilogue CLIP_GRAD: the stripes of s * dloss/dS this rank needs, stored
+//           k-index-major as bf16 hi/lo pairs.
+//   pass 4  dT_local = G0^T I, dI_local = G1^T T: three MN-major split-K products each (hi.hi, hi.lo, lo.hi)
+//           accumulated in fp32 (the weight-gradient form of ctk_gemm_bf16).
+int clip_loss_tc(const float* T, const float* I, const float* log_temp, float* out, float* d_local, uint8_t* p, int N,
+                 int d, int b_local, int row0, cudaStream_t s) {
+    void* stream = reinterpret_cast<void*>(s);
+    const int nblk = (N + 127) / 128;
+    const size_t nblk64 = (size_t)(N + 63) / 64;             // the workspace is carved exactly as ctk_clip_loss_ws_bytes sizes it
+    float* rowpart = reinterpret_cast<float*>(p); p += align256(sizeof(float) * nblk64 * N * 3);
+    float* colpart = reinterpret_cast<float*>(p); p += align256(sizeof(float) * nblk64 * N * 3);
+    float* diag = reinterpret_cast<float*>(p);    p += align256(sizeof(float) * N);
+    float* row_lse = reinterpret_cast<float*>(p); p += align256(sizeof(float) * N);
+    float* col_lse = reinterpret_cast<float*>(p); p += align256(sizeof(float) * N);
+    __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(p); p += align256(sizeof(float) * (size_t)b_local * N * 2);
+    __nv_bfloat16* catT = reinterpret_cast<__nv_bfloat16*>(p); p += align256((size_t)N * 3 * CLIP_TC_MAX_D * 2);
+    __nv_bfloat16* catI = reinterpret_cast<__nv_bfloat16*>(p);
+    const long long stripe = (long long)N * b_local;         // elements of one [N, b_local] bf16 stripe
+    __nv_bfloat16 *g0_hi = G, *g0_lo = G + stripe, *g1_hi = G + 2 * stripe, *g1_lo = G + 3 * stripe;
+
+    const float inv_2nb = 1.0f / (2.0f * (float)N * (float)b_local);
+    CTK_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(float), s));
+    const long long nel = (long long)N * d;
+    clip_split_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(T, catT, N, d, 0);
+    CTK_LAUNCH_CHECK();
+    clip_split_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(I, catI, N, d, 1);
+    CTK_LAUNCH_CHECK();
+
+    ctk_gemm_epilogue_t e;
+    memset(&e, 0, sizeof(e));
+    e.alpha = 1.f;
+    e.vec1 = log_temp;
+    // ---- pass 1
+    e.C = rowpart; e.aux0 = diag;
+    int rc = ctk_gemm_bf16(catT, 3LL * d, 0, catI, 3LL * d, 0, N, N, 3 * d, CTK_EPI_LSE_PART, &e, 0, stream);
+    if (rc) return rc;
+    e.C = colpart; e.aux0 = nullptr;
+    rc = ctk_gemm_bf16(catI, 3LL * d, 0, catT, 3LL * d, 0, N, N, 3 * d, CTK_EPI_LSE_PART, &e, 0, stream);
+    if (rc) return rc;
+    // ---- pass 2
+    clip_reduce_kernel<<<(N + 127) / 128, 128, 0, s>>>(rowpart, colpart, diag, row_lse, col_lse, out, N, nblk, inv_2nb);
+    CTK_LAUNCH_CHECK();
+    if (!d_local) return CTK_OK;
+    // ---- pass 3: G0[c, r] = g(text row0+r, image c);  G1[i, c] = g(text i, image row0+c);  both [N, b_local]
+    e.alpha = inv_2nb;
+    e.i0 = 0; e.i1 = row0;                                   // diagonal: gemm row == gemm col + row0
+    e.ldc = b_local; e.ld_aux0 = b_local;
+    e.C = g0_hi; e.aux0 = g0_lo; e.vec0 = col_lse; e.bias = row_lse + row0;
+    rc = ctk_gemm_bf16(catI, 3LL * d, 0, catT + (long long)row0 * 3 * d, 3LL * d, 0, N, b_local, 3 * d,
+                       CTK_EPI_CLIP_GRAD, &e, 0, stream);
+    if (rc) return rc;
+    e.C = g1_hi; e.aux0 = g1_lo; e.vec0 = row_lse; e.bias = col_lse + row0;
+    rc = ctk_gemm_bf16(catT, 3LL * d, 0, catI + (long long)row0 * 3 * d, 3LL * d, 0, N, b_local, 3 * d,
+                       CTK_EPI_CLIP_GRAD, &e, 0, stream);
+    if (rc) return rc;
+    // ---- pass 4: contraction over the N gathered samples, operands [K = N, rows] (MN-major), fp32 atomics
+    CTK_CUDA(cudaMemsetAsync(d_local, 0, sizeof(float) * 2 * (size_t)b_local * d, s));
+    memset(&e, 0, sizeof(e));
+    e.alpha = 1.f;
+    e.ldc = d;
+    const __nv_bfloat16 *i_hi = catI, *i_lo = catI + d, *t_hi = catT, *t_lo = catT + 2 * d;
+    const __nv_bfloat16* ga[2][2] = {{g0_hi, g0_lo}, {g1_hi, g1_lo}};
+    const __nv_bfloat16* xb[2][2] = {{i_hi, i_lo}, {t_hi, t_lo}};
+    for (int z = 0; z < 2; ++z) {
+        e.C = d_local + (long long)z * b_local * d;
+        const int term[3][2] = {{0, 0}, {0, 1}, {1, 0}};     // (G part, latent part): hi.hi, hi.lo, lo.hi
+        for (int t = 0; t < 3; ++t) {
+            rc = ctk_gemm_bf16(ga[z][term[t][0]], b_local, 1, xb[z][term[t][1]], 3LL * d, 1, b_local, d, N,
+                               CTK_EPI_ATOMIC_F32, &e, 0, stream);
+            if (rc) return rc;
+        }
+    }
+    return CTK_OK;
+}
+
+}  // namespace
 
 extern "C" int ctk_clip_loss_fwd_bwd(const float* T, const float* I, const float* log_temp,
                                      float* out, float* d_local, void* ws, size_t ws_bytes, int N,
@@ -374,6 +495,9 @@ extern "C" int ctk_clip_loss_fwd_bwd(const float* T, const float* I, const float
     CTK_REQUIRE(ws_bytes >= ctk_clip_loss_ws_bytes(N, b_local), CTK_ERR_SHAPE,
                 "clip_loss: workspace too small");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (clip_tc_enabled() && N >= CLIP_TC_MIN_N && N % 128 == 0 && d % 64 == 0 && d <= CLIP_TC_MAX_D && b_local % 32 == 0 &&
+        CTK_ALIGNED(ws, 256))
+        return clip_loss_tc(T, I, log_temp, out, d_local, reinterpret_cast<uint8_t*>(ws), N, d, b_local, row0, s);
     const int nblk = (N + 63) / 64;
     uint8_t* p = reinterpret_cast<uint8_t*>(ws);
     float* rowpart = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)nblk * N * 3);
