@@ -249,6 +249,15 @@ int ctk_colsum(const void* dy_bf16, const float* dy_f32, float* out, long long r
                void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Loader-side volume preparation: scripts/data.py:49-111 npz_to_tensor on the device.
+ * src = the stored array arr_0, (D, H, W) row-major, float32 (src_is_f16 = 0) or float16 (1), in device or
+ * pinned host memory; dst fp32 (Dt, Ht, Wt) = (240, 480, 480) in the reference:
+ *   (clip(x, -1, 1) + 1) / 2 in the stored dtype, centre crop, centre pad with -1.  Bit-exact with the reference.
+ * ------------------------------------------------------------------------------------------ */
+int ctk_volume_prep(const void* src, int src_is_f16, int D, int H, int W, float* dst, int Dt, int Ht, int Wt,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimizer tail: torch.nn.utils.clip_grad_norm_(params, max_norm)
  * (CTCLIPTrainer.py:711-712) + torch.optim.Adam / AdamW (optimizer.py:14-24) over a device table of
  * tensors.  rows: int64 [ntensors][6] = {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel,

@@ -18,6 +18,7 @@ export CTK_TEST_UNVERIFIED=1
 run gelu_epilogues 300 python -m pytest tests/test_text_tower_gpu.py -m gpu -q --no-header -p no:cacheprovider -k "gelu"
 run text_tower 600 python -m pytest tests/test_text_tower_gpu.py -m gpu -q --no-header -p no:cacheprovider -k "not gelu"
 run clip_loss_tc 900 python -m pytest tests/test_clip_loss_tc_gpu.py -m gpu -q --no-header -p no:cacheprovider
+run volume_prep 300 python -m pytest tests/test_volume_prep_gpu.py -m gpu -q --no-header -p no:cacheprovider
 unset CTK_TEST_UNVERIFIED
 
 # 2. the validated suite must still be green with the rebuilt library

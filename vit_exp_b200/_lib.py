@@ -67,6 +67,7 @@ SIGNATURES = {
     "ctk_fill_f32": (_i, [_vp, _f, _ll, _vp]),
     "ctk_patch_affine_bwd": (_i, [_vp] * 8 + [_i, _i, _vp]),
     "ctk_colsum": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "ctk_volume_prep": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
 }
 
 _lib = None

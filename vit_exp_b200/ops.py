@@ -332,3 +332,18 @@ def colsum_(dy, out):
     dyf = dy if dy.dtype == torch.float32 else None
     check(_lib.load().ctk_colsum(_p(dyb), _p(dyf), _p(out), rows, cols, _stream()), "ctk_colsum")
     return out
+
+
+# --------------------------------------------------------------------------- loader-side volume preparation
+def volume_prep(src: torch.Tensor, out: torch.Tensor):
+    """scripts/data.py:49-111 on the device: src = stored array (D, H, W), fp32 or fp16, CUDA or pinned host memory;
+    out fp32 CUDA (..., Dt, Ht, Wt) contiguous (the last three dims are the target volume)."""
+    assert src.dim() == 3 and src.is_contiguous() and src.dtype in (torch.float32, torch.float16)
+    assert src.is_cuda or src.is_pinned(), "volume_prep reads device or pinned host memory"
+    _chk(out, torch.float32, "out")
+    D, H, W = src.shape
+    Dt, Ht, Wt = out.shape[-3:]
+    assert out.numel() == Dt * Ht * Wt
+    check(_lib.load().ctk_volume_prep(src.data_ptr(), int(src.dtype == torch.float16), D, H, W, _p(out), Dt, Ht, Wt,
+                                      _stream()), "ctk_volume_prep")
+    return out
