@@ -334,6 +334,39 @@ def run_ours(args):
         ms_e2e16, _ = timed(e2e16_loop, args.steps)
         del host16, dev16
 
+    # ---- informational: the reference's own STORED format on the host (float16 arr_0 of the *_fp16 datasets, values in
+    # [-1, 1]) -> H2D in that dtype -> ctk_volume_prep on the device (scripts/data.py:49-111, bit-exact) -> train step.
+    # Same result tensor as the loader's, half the PCIe bytes.  Opt-in until the kernel has run on hardware.
+    ms_e2e_st = None
+    if args.stored_host:
+        hosts = [(v[:, 0] * 2 - 1).half().pin_memory() for v in host_vid]          # (B, D, H, W) stored arrays
+        devs = [torch.empty(B, *VOL, dtype=torch.float16, device=dev) for _ in range(NSLOT)]
+        done_st = [None] * NSLOT
+        def h2d_st(slot, src):
+            with torch.cuda.stream(copy_stream):
+                devs[slot].copy_(hosts[src], non_blocking=True)
+                dev_ids[slot].copy_(host_ids[src], non_blocking=True)
+                for b in range(B):
+                    ops.volume_prep(devs[slot][b], dev_vid[slot][b])
+        def e2e_st_loop(k):
+            h2d_st(0, 0)
+            last = None
+            for i in range(k):
+                torch.cuda.current_stream().wait_stream(copy_stream)
+                if i + 1 < k:
+                    nxt = (i + 1) % NSLOT
+                    if done_st[nxt] is not None:
+                        copy_stream.wait_event(done_st[nxt])
+                    h2d_st(nxt, (i + 1) % 2)
+                last = step(i % NSLOT)
+                ev = torch.cuda.Event()
+                ev.record()
+                done_st[i % NSLOT] = ev
+            return last
+        e2e_st_loop(2)
+        ms_e2e_st, _ = timed(e2e_st_loop, args.steps)
+        del hosts, devs
+
     # ---- roofline: instrument every tcgen05 GEMM launch of one more step --------------------------
     ops.GEMM_PROFILE = []
     step(0)
@@ -379,6 +412,11 @@ def run_ours(args):
             "value": vols / (ms_e2e16 / 1e3), "unit": "volumes/s", "ms_per_step": ms_e2e16 / args.steps,
             "h2d_bytes_per_step": int(host_vid[0].numel() * 2 + host_ids[0].numel() * 8),
             "note": "informational: fp16 host volumes widened on the device; the contract number is `e2e` (fp32 host batch)"},
+        "e2e_stored_host": None if ms_e2e_st is None else {
+            "value": vols / (ms_e2e_st / 1e3), "unit": "volumes/s", "ms_per_step": ms_e2e_st / args.steps,
+            "h2d_bytes_per_step": int(host_vid[0].numel() * 2 + host_ids[0].numel() * 8),
+            "note": "informational: float16 stored arrays (the *_fp16 datasets' arr_0) shipped as stored and prepared by "
+                    "ctk_volume_prep (scripts/data.py:49-111 on the device); the contract number is `e2e`"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<EPI, major> (tcgen05 128x256x64, all launches of one step)",
@@ -491,6 +529,8 @@ def main():
                     help="CTCLIP returns cl_loss via loss.item() inside forward (reference behaviour: a host sync between "
                          "forward and backward); default: config['defer_loss_read'], the same value read back at the end of the step")
     ap.add_argument("--half-host", action="store_true", help="also time the e2e pipeline with fp16 host volumes (informational)")
+    ap.add_argument("--stored-host", action="store_true",
+                    help="also time the e2e pipeline from float16 STORED arrays through vit_exp_b200.data / ctk_volume_prep (informational)")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: libctk clip+Adam (2 launches); torch: clip_grad_norm_ + torch.optim.Adam(fused=True)")
     ap.add_argument("--text-tower", default="hf", choices=["hf", "ctk"],

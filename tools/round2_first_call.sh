@@ -25,7 +25,7 @@ unset CTK_TEST_UNVERIFIED
 run suite 1200 python -m pytest tests -m gpu -x -q --no-header -p no:cacheprovider
 
 # 3. measurements: stock vs libctk text tower; loss sweep with and without the tensor-core path
-run bench_hf 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+run bench_hf 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --stored-host --half-host
 grep -h '^{' gpurun_out/r2_bench_hf.log > gpurun_out/r2_bench_hf.json
 run bench_ctk 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --text-tower ctk
 grep -h '^{' gpurun_out/r2_bench_ctk.log > gpurun_out/r2_bench_ctk.json
