@@ -1,0 +1,77 @@
+"""BASELINE config 4: zero-shot 18-pathology scoring of V synthetic CT-RATE-shaped volumes sharded over N GPUs.
+
+    python tools/bench_zero_shot.py --volumes 64                                   # 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+           tools/bench_zero_shot.py --volumes 512                                  # 8 GPUs, replicas + one gather
+
+Each rank scores its contiguous share (vit_exp_b200.zero_shot.ZeroShotScorer.run); the 36 prompt latents come from
+a random-init BERT-base once, outside the timed region (zero_shot.py:480-496 does the same in prepare_infer).
+Prints one JSON line (volumes/s over all GPUs, device-timed, max over ranks).  Inputs are generated on the host in
+pinned memory and copied per volume inside the timed region, like the reference's loader + .cuda() (zero_shot.py:547).
+"""
+import argparse
+import json
+import os
+import sys
+from types import SimpleNamespace
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from bench import build_model
+from vit_exp_b200.zero_shot import ZeroShotScorer, shard_bounds
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--volumes", type=int, default=64)
+    ap.add_argument("--resident", action="store_true", help="volumes already in HBM (no H2D in the timed region)")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    clip = build_model(dev, seed=0).eval()
+    sc = ZeroShotScorer(clip)
+    g = torch.Generator().manual_seed(0)
+    toks = [SimpleNamespace(input_ids=torch.randint(0, 30522, (2, 512), generator=g).to(dev),
+                            attention_mask=torch.ones(2, 512, dtype=torch.int64, device=dev)) for _ in range(18)]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        sc.prepare(text_tokens=toks)
+    lo, hi = shard_bounds(args.volumes, world, rank)
+    g = torch.Generator().manual_seed(100 + rank)
+    host = [torch.rand(1, 1, 240, 480, 480, generator=g).pin_memory() for _ in range(2)]
+    res = [h.to(dev) for h in host] if args.resident else None
+
+    def load(i):
+        return res[i % 2] if args.resident else host[i % 2].to(dev, non_blocking=True)
+
+    sc.run(min(args.volumes, 2 * world), load)                       # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    probs = sc.run(args.volumes, load)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        assert probs.shape == (args.volumes, 18)
+        print(json.dumps({"config": 4, "workload": "zero-shot 18 pathologies x 2 prompts, volumes sharded over GPUs",
+                          "n_gpus": world, "volumes": args.volumes, "ms": ms.item(),
+                          "volumes_per_s": args.volumes / ms.item() * 1e3, "resident_inputs": bool(args.resident),
+                          "scaling": "strong (fixed V)", "mean_prob": float(probs.mean())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

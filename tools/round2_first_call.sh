@@ -19,6 +19,7 @@ run gelu_epilogues 300 python -m pytest tests/test_text_tower_gpu.py -m gpu -q -
 run text_tower 600 python -m pytest tests/test_text_tower_gpu.py -m gpu -q --no-header -p no:cacheprovider -k "not gelu"
 run clip_loss_tc 900 python -m pytest tests/test_clip_loss_tc_gpu.py -m gpu -q --no-header -p no:cacheprovider
 run volume_prep 300 python -m pytest tests/test_volume_prep_gpu.py -m gpu -q --no-header -p no:cacheprovider
+run zero_shot 300 python -m pytest tests/test_zero_shot_gpu.py -m gpu -q --no-header -p no:cacheprovider
 unset CTK_TEST_UNVERIFIED
 
 # 2. the validated suite must still be green with the rebuilt library
@@ -31,3 +32,4 @@ run bench_ctk 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --text-
 grep -h '^{' gpurun_out/r2_bench_ctk.log > gpurun_out/r2_bench_ctk.json
 CTK_CLIP_LOSS_TC=0 run configs_simt 600 python tools/bench_configs.py
 CTK_CLIP_LOSS_TC=1 run configs_tc 600 python tools/bench_configs.py
+run zero_shot_bench 600 python tools/bench_zero_shot.py --volumes 32
