@@ -11,10 +11,8 @@ its backward - runs in libctk.so.  The text encoder is whatever module the calle
 from __future__ import annotations
 
 import copy
-from pathlib import Path
-from typing import Optional
-
 import os
+from pathlib import Path
 
 import torch
 import torch.distributed as dist

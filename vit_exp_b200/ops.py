@@ -11,8 +11,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_ARGMAX, EPI_ATOMIC_F32, EPI_BF16, EPI_F32, EPI_GEGLU, EPI_GEGLU_BWD, EPI_GELU, EPI_GELU_BWD,
-                   EPI_QKV, EPI_RESID_F32, GemmEpilogue, check)
+from ._lib import (EPI_ARGMAX, EPI_ATOMIC_F32, EPI_BF16, EPI_CLIP_GRAD, EPI_F32, EPI_GEGLU, EPI_GEGLU_BWD,  # noqa: F401
+                   EPI_GELU, EPI_GELU_BWD, EPI_LSE_PART, EPI_QKV, EPI_RESID_F32, GemmEpilogue, check)
 
 
 def _stream() -> int:

@@ -6,8 +6,6 @@ The reference trainer does `accelerator.clip_grad_norm_(params, max_grad_norm)` 
 """
 from __future__ import annotations
 
-import ctypes as C
-import math
 from typing import Iterable, Optional
 
 import numpy as np

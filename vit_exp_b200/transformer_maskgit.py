@@ -13,10 +13,8 @@ from __future__ import annotations
 
 import os
 import weakref
-
-import math
 from pathlib import Path
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn.functional as F
