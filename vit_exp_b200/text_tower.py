@@ -6,7 +6,7 @@ The caller's `BertModel` stays the parameter holder (its state-dict keys are the
 only *reads its parameters* and runs the arithmetic of `BertEmbeddings`, `BertLayer` x depth (post-LayerNorm:
 attention -> dense + residual -> LayerNorm -> intermediate dense + erf GELU -> dense + residual -> LayerNorm)
 through the same tcgen05 GEMM (`ctk_gemm_bf16`, epilogues BF16 / RESID_F32 / GELU / GELU_BWD / ATOMIC_F32) and
-LayerNorm kernels the image encoder uses.  The pooler is not evaluated (CTCLIP reads `[0][:, 0, :]` only,
+LayerNorm kernels the image encoder uses (bias gradients are dY^T 1 products on the same GEMM).  The pooler is not evaluated (CTCLIP reads `[0][:, 0, :]` only,
 ct_clip.py:1273,1313), so `pooler.dense.*` receives no gradient, exactly as in the reference.
 
 Data layout: M = B*L token rows, hidden H; fp32 residual stream, bf16 GEMM operands written by the producing
@@ -184,6 +184,15 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
     f32 = dict(dtype=torch.float32, device=dev)
     grads: List[Optional[torch.Tensor]] = [None] * len(params)
     g = dout.reshape(M, H).float().contiguous()                  # d(last_hidden_state)
+    ones = torch.ones(M, 8, dtype=od, device=dev)
+
+    def bias_grad(dyb: torch.Tensor, n: int) -> torch.Tensor:
+        """column sums of dY [M, n] as a token-contraction on the tensor cores, dY^T 1: the MN-major split-K product
+        of the weight gradients with a ones operand streams dY through TMA at full rate (a plain column-sum kernel
+        keeps too few loads in flight for [4096, 3072] matrices)."""
+        out = torch.zeros(n, 8, **f32)
+        ops.gemm(dyb, ones, ops.EPI_ATOMIC_F32, out, M=n, N=8, K=M, mn_major=True, ldc=8)
+        return out[:, 0]
     for li in range(s.depth - 1, -1, -1):
         base = N_EMB + li * N_PER_LAYER
         (wq, bq, wk, bk, wv, bv, wo, bo, g1, b1, wi, bi, wo2, bo2, g2, b2) = params[base: base + N_PER_LAYER]
@@ -193,13 +202,13 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
         dg2, db2 = torch.zeros(H, **f32), torch.zeros(H, **f32)
         dy2b = torch.empty(M, H, dtype=od, device=dev)
         dy2 = ops.layernorm_bwd(g, sv["y2"], g2, sv["mu2"], sv["rs2"], dg2, db2, dx_bf16=dy2b)
-        dbo2 = ops.colsum_(dy2, torch.zeros(H, **f32))
+        dbo2 = bias_grad(dy2b, H)
         dwo2 = torch.zeros(H, I, **f32)
         ops.gemm(dy2b, sv["G"], ops.EPI_ATOMIC_F32, dwo2, M=H, N=I, K=M, mn_major=True, ldc=I)
         # ---- G = gelu(U), U = x1 Wi^T + bi
         dU = torch.empty(M, I, dtype=od, device=dev)
         ops.gemm(dy2b, w["wo2_t"], ops.EPI_GELU_BWD, dU, M=M, N=I, K=H, aux0=sv["U"], ld_aux0=I)
-        dbi = ops.colsum_(dU, torch.zeros(I, **f32))
+        dbi = bias_grad(dU, I)
         dwi = torch.zeros(I, H, **f32)
         ops.gemm(dU, sv["x1b"], ops.EPI_ATOMIC_F32, dwi, M=I, N=H, K=M, mn_major=True, ldc=H)
         dx1 = torch.empty(M, H, **f32)
@@ -208,14 +217,14 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
         dg1, db1 = torch.zeros(H, **f32), torch.zeros(H, **f32)
         dy1b = torch.empty(M, H, dtype=od, device=dev)
         dy1 = ops.layernorm_bwd(dx1, sv["y1"], g1, sv["mu1"], sv["rs1"], dg1, db1, dx_bf16=dy1b)
-        dbo = ops.colsum_(dy1, torch.zeros(H, **f32))
+        dbo = bias_grad(dy1b, H)
         dwo = torch.zeros(H, H, **f32)
         ops.gemm(dy1b, sv["ctxb"], ops.EPI_ATOMIC_F32, dwo, M=H, N=H, K=M, mn_major=True, ldc=H)
         dctx = torch.empty(M, H, dtype=od, device=dev)
         ops.gemm(dy1b, w["wo_t"], ops.EPI_BF16, dctx, M=M, N=H, K=H)
         # ---- attention core and the packed q|k|v projection
         dqkv = _attention_bwd(sv["attn"], dctx, s)
-        dbqkv = ops.colsum_(dqkv, torch.zeros(3 * H, **f32))
+        dbqkv = bias_grad(dqkv, 3 * H)
         dwqkv = torch.zeros(3 * H, H, **f32)
         ops.gemm(dqkv, sv["xb"], ops.EPI_ATOMIC_F32, dwqkv, M=3 * H, N=H, K=M, mn_major=True, ldc=H)
         gx = torch.empty(M, H, **f32)
