@@ -182,6 +182,74 @@ def ctvit_forward(video, p: Params, *, patch: int, tpatch: int, spatial_depth: i
 
 
 # ------------------------------------------------------------------------------------------
+# CTViT3D: joint 3-D transformer, ctvit3d.py:175-520
+# ------------------------------------------------------------------------------------------
+def flash_attention(x, p: Params, pre: str, heads: int):
+    """attention.py:189-284 `FlashAttention` as CTViT3D uses it (no context / mask / causal; `attn_bias` is ignored,
+    attention.py:257): q from LayerNorm(x), k and v from the raw x; learned null key/values are PREPENDED
+    ('h (n r) d -> b h n r d', r = 2: even rows are keys, odd rows values), l2norm + q_scale / k_scale are applied
+    AFTER the concat (so the null keys are normalised too), then F.scaled_dot_product_attention with its default
+    scale 1/sqrt(dim_head) - not the cosine-attention scale 8 of `Attention`."""
+    b, n, _ = x.shape
+    xn = layer_norm(x, p[pre + "norm.gamma"])
+    q = xn @ p[pre + "to_q.weight"].T
+    k, v = (x @ p[pre + "to_kv.weight"].T).chunk(2, dim=-1)
+    q, k, v = (t.reshape(b, n, heads, -1).permute(0, 2, 1, 3) for t in (q, k, v))
+    null = p[pre + "null_kv"]                                            # (heads, 2 * n_null, dh)
+    nk, nv = null.reshape(heads, -1, 2, null.shape[-1]).unbind(dim=-2)
+    k = torch.cat([nk.expand(b, *nk.shape), k], dim=-2)
+    v = torch.cat([nv.expand(b, *nv.shape), v], dim=-2)
+    q = l2norm(q) * p[pre + "q_scale"]
+    k = l2norm(k) * p[pre + "k_scale"]
+    sim = torch.einsum("bhid,bhjd->bhij", q, k) / math.sqrt(q.shape[-1])
+    out = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
+    out = out.permute(0, 2, 1, 3).reshape(b, n, -1)
+    return out @ p[pre + "to_out.weight"].T
+
+
+def sincos_pos_embed_3d(dim: int, grid):
+    """ctvit3d.py:122-173 fixed 3-D sin/cos table (n_t*n_h*n_w, dim), float32 numpy semantics restated in torch
+    float64 then cast.  Reproduces the reference's construction literally: np.meshgrid(t, w, h) in its default 'xy'
+    indexing yields arrays of shape (n_w, n_t, n_h) that are then *reshaped* (not transposed) to (n_t, n_w, n_h)
+    (ctvit3d.py:131-135), so unless n_t == n_w the three coordinate channels are a scrambled - but fixed and
+    deterministic - function of the token index; a third of the channels encodes each of them as [sin | cos] with
+    frequencies 10000^(-i / (dim/6))."""
+    n_t, n_h, n_w = grid
+    assert dim % 6 == 0
+    gt = torch.arange(n_t, dtype=torch.float32)
+    gh = torch.arange(n_h, dtype=torch.float32)
+    gw = torch.arange(n_w, dtype=torch.float32)
+    # numpy 'xy' meshgrid of (t, w, h): out[k][j, i, l] with x = t (index i), y = w (index j), z = h (index l)
+    T = gt[None, :, None].expand(n_w, n_t, n_h)
+    W = gw[:, None, None].expand(n_w, n_t, n_h)
+    H = gh[None, None, :].expand(n_w, n_t, n_h)
+    chans = [c.reshape(-1) for c in (T, W, H)]             # the reshape to (1, n_t, n_w, n_h) keeps memory order
+    d3 = dim // 3
+    omega = torch.arange(d3 // 2, dtype=torch.float32) / (d3 / 2.0)
+    omega = 1.0 / 10000 ** omega
+    parts = []
+    for pos in chans:
+        out = pos[:, None] * omega[None, :]
+        parts += [torch.sin(out), torch.cos(out)]
+    return torch.cat(parts, dim=1)
+
+
+def ctvit3d_forward(video, p: Params, *, patch: int, tpatch: int, blocks: int, heads: int):
+    """ctvit3d.py:455-520 with return_encoded_tokens=True: patch embedding (ctvit3d.py:240-245, same as CTViT),
+    + pos_embed, `blocks` x [x = flash_attn(x) + x; x = ff(x) + x] over ALL t*h*w tokens jointly (no PEG,
+    ctvit3d.py:247-258), final LayerNorm (attention.py:452); no vector quantisation."""
+    tokens = patch_embed(video, p, patch, tpatch)
+    b, t, h, w, d = tokens.shape
+    x = tokens.reshape(b, t * h * w, d) + p["pos_embed"]
+    for l in range(blocks):
+        lp = f"enc_3D.layers.{l}."
+        x = flash_attention(x, p, lp + "1.", heads) + x
+        x = feed_forward(x, p, lp + "3.") + x
+    x = layer_norm(x, p["enc_3D.norm_out.gamma"])
+    return x.reshape(b, t, h, w, d)
+
+
+# ------------------------------------------------------------------------------------------
 # contrastive head
 # ------------------------------------------------------------------------------------------
 def image_latent(enc_image, W):

@@ -19,6 +19,7 @@ run gelu_epilogues 300 python -m pytest tests/test_text_tower_gpu.py -m gpu -q -
 run text_tower 600 python -m pytest tests/test_text_tower_gpu.py -m gpu -q --no-header -p no:cacheprovider -k "not gelu"
 run clip_loss_tc 900 python -m pytest tests/test_clip_loss_tc_gpu.py -m gpu -q --no-header -p no:cacheprovider
 run volume_prep 300 python -m pytest tests/test_volume_prep_gpu.py -m gpu -q --no-header -p no:cacheprovider
+run ctvit3d 600 python -m pytest tests/test_ctvit3d_gpu.py -m gpu -q --no-header -p no:cacheprovider
 run zero_shot 300 python -m pytest tests/test_zero_shot_gpu.py -m gpu -q --no-header -p no:cacheprovider
 unset CTK_TEST_UNVERIFIED
 

@@ -97,14 +97,16 @@ class Transformer(nn.Module):
     """attention.py:386-439: layers[i] = [PEG, Attention, None (no cross-attn), FeedForward]."""
 
     def __init__(self, dim, *, depth, dim_head=64, heads=8, ff_mult=4, peg=False, peg_causal=False,
-                 attn_dropout=0.0, ff_dropout=0.0):
+                 attn_dropout=0.0, ff_dropout=0.0, attn_num_null_kv=0):
         super().__init__()
         assert attn_dropout == 0.0 and ff_dropout == 0.0, "dropout is 0 on the reference path (run_train.py:56-66)"
         self.layers = nn.ModuleList([])
         for _ in range(depth):
             self.layers.append(nn.ModuleList([
                 PEG(dim=dim, causal=peg_causal) if peg else None,
-                Attention(dim=dim, dim_head=dim_head, heads=heads),
+                # attention.py:422 builds `Attention` without null kv; the FlashAttention of CTViT3D (attention.py:413)
+                # gets attn_num_null_kv = 2 learned null key/value pairs
+                Attention(dim=dim, dim_head=dim_head, heads=heads, num_null_kv=attn_num_null_kv),
                 None,
                 FeedForward(dim=dim, mult=ff_mult, dropout=ff_dropout),
             ]))
