@@ -43,6 +43,7 @@ def _build():
                     "layernorm_fwd": E.layernorm_fwd_full, "layernorm_bwd": E.layernorm_bwd_full}
             return full[name] if name in full else getattr(E, name)
 
+    saved = (E.OPERAND, TM.ops, CC.ops, torch.empty, torch.zeros)
     E.OPERAND = torch.float32
     TM.ops = CC.ops = _Ops()
     _empty, _zeros = torch.empty, torch.zeros
@@ -80,14 +81,17 @@ def _build():
     g = torch.Generator().manual_seed(1)
     video = torch.rand(WORLD * B, 1, 4, 8, 8, generator=g)
     ids = torch.randint(0, 40, (WORLD * B, 5), generator=g)
-    return clip.eval(), video, ids, CC            # eval: frozen codebook (the training-mode EMA is not a gradient path)
+    def restore():                               # the checker runs inside the pytest process: undo the patches there
+        E.OPERAND, TM.ops, CC.ops, torch.empty, torch.zeros = saved
+    # eval: frozen codebook (the training-mode EMA is not a gradient path)
+    return clip.eval(), video, ids, CC, restore
 
 
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    clip, video, ids, CC = _build()
+    clip, video, ids, CC, _ = _build()
     model = torch.nn.parallel.DistributedDataParallel(clip, find_unused_parameters=True)
     sl = slice(rank * B, (rank + 1) * B)
     batch = {"data_type": ["imagereport"] * B, "image": video[sl],
@@ -107,7 +111,8 @@ def test_two_rank_ddp_step_matches_global_gradient(tmp_path):
 
     # single-process answer: the oracle on the concatenated batch, loss / bs_single_gpu (ct_clip.py:1379)
     from oracle import ctclip_oracle as O
-    clip, video, ids, _ = _build()
+    clip, video, ids, _, restore = _build()
+    restore()                                    # only the seeded model and inputs are needed here; the oracle computes
     vit = clip.visual_transformer
     p = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in vit.state_dict().items()}
     emb = clip.text_transformer.emb.weight.detach().clone().requires_grad_()
