@@ -8,62 +8,23 @@
 // HBM-bound: every stored voxel is read at most once, every output voxel written once (16-byte stores); the host
 // ships the volume in its stored dtype (2 bytes per voxel for the fp16 datasets) instead of the fp32 result, which
 // is what bounds the end-to-end step over PCIe.  Algorithmic bytes per volume: Dt*Ht*Wt*(src_bytes + 4).
+// The per-voxel code lives in volume_prep_math.cuh so that tests/host_checks.cu can run it on the CPU.
 #include "common.cuh"
-#include <cuda_fp16.h>
+#include "volume_prep_math.cuh"
 
 namespace {
 
-struct AxisPlan { int start, len, pad; };     // source offset, copied length, leading pad (data.py:77-98)
-
-inline AxisPlan plan_axis(int n, int t) {
-    AxisPlan p;
-    p.start = (n - t) / 2 > 0 ? (n - t) / 2 : 0;
-    const int end = p.start + t < n ? p.start + t : n;
-    p.len = end - p.start;
-    p.pad = (t - p.len) / 2;
-    return p;
-}
-
-__device__ __forceinline__ float prep_f32(float x) {
-    if (x != x) return x;                                        // np.clip propagates NaN
-    const float c = fminf(fmaxf(x, -1.f), 1.f);
-    return __fmul_rn(__fadd_rn(c, 1.f), 0.5f);
-}
-// numpy evaluates float16 ufuncs as float32 operations rounded back to float16 after each step
-__device__ __forceinline__ float prep_f16(__half h) {
-    const float x = __half2float(h);
-    if (x != x) return x;
-    const float c = fminf(fmaxf(x, -1.f), 1.f);
-    const __half s = __float2half_rn(__fadd_rn(c, 1.f));
-    const __half r = __float2half_rn(__fmul_rn(__half2float(s), 0.5f));
-    return __half2float(r);
-}
+using volprep::AxisPlan;
 
 template <bool HALF>
 __global__ void __launch_bounds__(256)
-volume_prep_kernel(const void* __restrict__ src_, float* __restrict__ dst, int H, int W, AxisPlan pz, AxisPlan py,
+volume_prep_kernel(const void* __restrict__ src, float* __restrict__ dst, int H, int W, AxisPlan pz, AxisPlan py,
                    AxisPlan px, int Dt, int Ht, int Wt) {
     const long long nvec = (long long)Dt * Ht * (Wt / 4);
-    const int wv = Wt / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
          i += (long long)gridDim.x * blockDim.x) {
-        const int xq = (int)(i % wv);
-        const long long zy = i / wv;
-        const int y = (int)(zy % Ht), z = (int)(zy / Ht);
-        const int sz = z - pz.pad, sy = y - py.pad;
-        float v[4] = {-1.f, -1.f, -1.f, -1.f};                   // pad value (data.py:100)
-        if (sz >= 0 && sz < pz.len && sy >= 0 && sy < py.len) {
-            const long long row = ((long long)(pz.start + sz) * H + (py.start + sy)) * W;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int sx = xq * 4 + j - px.pad;
-                if (sx >= 0 && sx < px.len) {
-                    const long long idx = row + px.start + sx;
-                    if (HALF) v[j] = prep_f16(reinterpret_cast<const __half*>(src_)[idx]);
-                    else v[j] = prep_f32(reinterpret_cast<const float*>(src_)[idx]);
-                }
-            }
-        }
+        float v[4];
+        volprep::prep_vec4<HALF>(i, src, H, W, pz, py, px, Ht, Wt, v);
         reinterpret_cast<float4*>(dst)[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
@@ -78,7 +39,7 @@ extern "C" int ctk_volume_prep(const void* src, int src_is_f16, int D, int H, in
                 "volume_prep: bad arguments");
     CTK_REQUIRE(Wt % 4 == 0 && CTK_ALIGNED(dst, 16), CTK_ERR_ALIGN, "volume_prep: output rows need 16-byte alignment");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    const AxisPlan pz = plan_axis(D, Dt), py = plan_axis(H, Ht), px = plan_axis(W, Wt);
+    const AxisPlan pz = volprep::plan_axis(D, Dt), py = volprep::plan_axis(H, Ht), px = volprep::plan_axis(W, Wt);
     const long long nvec = (long long)Dt * Ht * (Wt / 4);
     long long blocks = (nvec + 255) / 256;
     const long long cap = (long long)ctk_num_sms() * 16;         // grid-stride: a whole number of waves
