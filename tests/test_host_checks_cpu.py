@@ -29,7 +29,7 @@ def lib():
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    deps = [SRC, os.path.join(ROOT, "vit_exp_b200", "csrc", "volume_prep_math.cuh")]
+    deps = [SRC] + [os.path.join(ROOT, "vit_exp_b200", "csrc", h) for h in ("volume_prep_math.cuh", "clip_epilogue_math.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         r = subprocess.run([nvcc, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
                             "-x", "cu", SRC, "-o", OUT], capture_output=True, text=True)
@@ -87,3 +87,79 @@ def test_full_size_digest_of_reference_function(lib, case):
     arr = V.synthetic_volume(tuple(case["shape"]), case["dtype"], case["seed"])
     got = _run(lib, arr, (240, 480, 480))
     assert V.digest(got) == case["sha256"]
+
+
+# ------------------------------------------------------------------------------------------------
+# contrastive-loss GEMM epilogues: the device functions of csrc/clip_epilogue_math.cuh over host accumulators
+# ------------------------------------------------------------------------------------------------
+def _bind_clip(lib):
+    f32p, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.hostcheck_lse_part.restype = None
+    lib.hostcheck_lse_part.argtypes = [f32p, i, i, f, i, f32p, f32p]
+    lib.hostcheck_clip_grad.restype = None
+    lib.hostcheck_clip_grad.argtypes = [f32p, i, i, f, f, f32p, f32p, i, i, f32p, f32p]
+
+
+def _merge(part):
+    """clip_reduce_kernel: (lse, sum(x e^x) / sum(e^x)) per row from the [blocks, M, 3] partials"""
+    m = part[:, :, 0].max(axis=0)
+    sc = np.exp(part[:, :, 0] - m)
+    l = (part[:, :, 1] * sc).sum(axis=0)
+    w = (part[:, :, 2] * sc).sum(axis=0)
+    return m + np.log(l), w / l
+
+
+@pytest.mark.parametrize("N,W,rank,lt", [(256, 1, 0, 1.0), (384, 4, 2, 2.0), (200, 1, 0, 0.5)])
+def test_clip_epilogue_device_functions_vs_oracle(lib, N, W, rank, lt):
+    """the loss pipeline of head.cu `clip_loss_tc` with the REAL epilogue functions (run on the host) and numpy for
+    the matrix products: loss, d(log temperature) and both latent gradients against the fp64 oracle.  N = 200 has a
+    ragged last block (LSE_PART only; the gradient pass needs b_local % 32 == 0 and is skipped there)."""
+    import torch
+    from oracle import ctclip_oracle as orc
+    _bind_clip(lib)
+    d, B, row0 = 64, N // W, rank * (N // W)
+    g = torch.Generator().manual_seed(0)
+    T = torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=-1)
+    I = torch.nn.functional.normalize(torch.randn(N, d, generator=g) + 0.5 * T, dim=-1)
+    ref = orc.clip_loss_and_local_grads(T.double(), I.double(), torch.tensor(lt).double(), B, rank)
+
+    def split(x):
+        hi = x.bfloat16().float()
+        return hi.numpy(), (x - hi).bfloat16().float().numpy()
+    (Th, Tl), (Ih, Il) = split(T), split(I)
+    catT, catI = np.concatenate([Th, Th, Tl], 1), np.concatenate([Ih, Il, Ih], 1)
+    nblk = (N + 127) // 128
+
+    def lse_pass(A, Bm, want_diag):
+        acc = np.ascontiguousarray(A @ Bm.T, dtype=np.float32)
+        part = np.full((nblk, N, 3), np.nan, dtype=np.float32)
+        diag = np.full(N, np.nan, dtype=np.float32)
+        lib.hostcheck_lse_part(acc.ctypes.data, N, N, lt, 0, part.ctypes.data, diag.ctypes.data if want_diag else None)
+        return part, diag
+    rowpart, diag = lse_pass(catT, catI, True)
+    colpart, _ = lse_pass(catI, catT, False)
+    assert np.isfinite(rowpart).all() and np.isfinite(colpart).all() and np.isfinite(diag).all()
+    row_lse, row_mean = _merge(rowpart)
+    col_lse, col_mean = _merge(colpart)
+    inv = 1.0 / (2.0 * N * B)
+    loss = ((row_lse - diag).sum() + (col_lse - diag).sum()) * inv
+    dtemp = ((row_mean - diag).sum() + (col_mean - diag).sum()) * inv
+    assert abs(loss - float(ref["loss"])) <= 2e-6 * abs(float(ref["loss"]))
+    assert abs(dtemp - float(ref["dlog_temp"])) <= 1e-4 * abs(float(ref["dlog_temp"])) + 1e-8
+    if B % 32:
+        return
+
+    def grad_pass(A, Bm, vec0, bias):
+        acc = np.ascontiguousarray(A @ Bm.T, dtype=np.float32)                      # [N, b_local]
+        hi, lo = np.empty_like(acc), np.empty_like(acc)
+        v0, bb = np.ascontiguousarray(vec0, dtype=np.float32), np.ascontiguousarray(bias, dtype=np.float32)
+        lib.hostcheck_clip_grad(acc.ctypes.data, N, B, lt, inv, v0.ctypes.data, bb.ctypes.data, 0, row0,
+                                hi.ctypes.data, lo.ctypes.data)
+        assert np.array_equal(hi, torch.from_numpy(hi).bfloat16().float().numpy())     # representable in bf16
+        return hi, lo
+    g0h, g0l = grad_pass(catI, catT[row0:row0 + B], col_lse, row_lse[row0:row0 + B])
+    g1h, g1l = grad_pass(catT, catI[row0:row0 + B], row_lse, col_lse[row0:row0 + B])
+    dT = g0h.T @ Ih + g0h.T @ Il + g0l.T @ Ih
+    dI = g1h.T @ Th + g1h.T @ Tl + g1l.T @ Th
+    for got, want in ((dT, ref["dT_local"].numpy()), (dI, ref["dI_local"].numpy())):
+        assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max()

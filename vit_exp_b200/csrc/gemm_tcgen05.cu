@@ -24,6 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "clip_epilogue_math.cuh"
 
 namespace {
 
@@ -388,35 +389,16 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
             const float scale = expf(__ldg(p.vec1));
             float* diag = reinterpret_cast<float*>(p.aux0);
             const long long drow = row + p.i0;
-            float m = -INFINITY, l = 0.f, w = 0.f;
+            clipepi::RowStat st = {-INFINITY, 0.f, 0.f};
 #pragma unroll 1
             for (int cc = 0; cc < 128; cc += 32) {
                 const int col = cbase + cc;
                 if (col >= N) break;                     // warp-uniform
                 float v[32];
                 ld_acc(t_row + hf * 128 + cc, v);
-                float mx = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = col + i < N ? v[i] * scale : -INFINITY;
-                    mx = fmaxf(mx, v[i]);
-                }
-                if (mx > m) {                            // rescale the running sums to the new maximum
-                    const float r = expf(m - mx);        // m = -inf on the first chunk: r = 0, l = w = 0
-                    l *= r;
-                    w *= r;
-                    m = mx;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (col + i < N) {
-                        const float e = expf(v[i] - m);
-                        l += e;
-                        w = fmaf(e, v[i], w);
-                        if (diag && row_ok && drow == col + i) diag[row] = v[i];
-                    }
-                }
+                clipepi::lse_chunk(st, v, scale, col, N, drow, (diag && row_ok) ? diag + row : nullptr);
             }
+            const float m = st.m, l = st.l, w = st.w;
             if (row_ok) {
                 float* dst = reinterpret_cast<float*>(p.C) + ((long long)(cbase / 128) * M + row) * 3;
                 dst[0] = m; dst[1] = l; dst[2] = w;
@@ -441,16 +423,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
                 if (col >= N) break;                     // warp-uniform
                 float v[32], lo[32];
                 ld_acc(t_row + c, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = v[i] * scale;
-                    float g = expf(x - la) + expf(x - __ldg(p.bias + col + i));
-                    if (drow == (long long)col + i + p.i1) g -= 2.f;
-                    g *= gs;
-                    const float hi = __bfloat162float(__float2bfloat16_rn(g));
-                    v[i] = hi;
-                    lo[i] = g - hi;
-                }
+                clipepi::clip_grad_chunk(v, lo, scale, gs, la, p.bias + col, drow, col, p.i1);
                 uint8_t* sh = sg.base + (2 * h2) * SLOT_BYTES;
                 slot_write_bf16(sh, lane, v);
                 slot_write_bf16(sh + SLOT_BYTES, lane, lo);
