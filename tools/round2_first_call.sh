@@ -35,3 +35,4 @@ CTK_CLIP_LOSS_TC=0 run configs_simt 600 python tools/bench_configs.py
 CTK_CLIP_LOSS_TC=1 run configs_tc 600 python tools/bench_configs.py
 run zero_shot_bench 600 python tools/bench_zero_shot.py --volumes 32
 run config1 300 python tools/bench_config1.py --gpu
+run h2d_probe 300 python tools/h2d_probe.py
