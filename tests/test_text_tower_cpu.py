@@ -31,6 +31,7 @@ def _tiny_bert(seed=0, layers=2, hidden=128, heads=2, inter=256):
 def _inputs(B=3, L=16, padded=True, seed=1):
     g = torch.Generator().manual_seed(seed)
     ids = torch.randint(0, 97, (B, L), generator=g)
+    ids[1, 3] = 0                                  # the pad token id: nn.Embedding(padding_idx=0) gives its row no gradient
     mask = torch.ones(B, L, dtype=torch.int64)
     if padded:
         mask[0, L - 5:] = 0
@@ -149,16 +150,84 @@ def test_token_type_ids_and_partial_requires_grad(emulated):
 
 def test_unsupported_configurations_are_refused():
     from transformers import BertConfig, BertModel
-    bert = BertModel(BertConfig(vocab_size=50, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
-                                intermediate_size=256))                      # HF default dropout 0.1
-    assert "dropout" in text_tower.unsupported_reason(bert, training=True)
-    assert text_tower.unsupported_reason(bert, training=False) is None
-    with pytest.raises(NotImplementedError):
-        text_tower.encode(bert.train(), torch.zeros(1, 4, dtype=torch.long))
     odd = BertModel(BertConfig(vocab_size=50, hidden_size=96, num_hidden_layers=1, num_attention_heads=2,
                                intermediate_size=256, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
     assert text_tower.unsupported_reason(odd, training=True) is not None
+    with pytest.raises(NotImplementedError):
+        text_tower.encode(odd, torch.zeros(1, 4, dtype=torch.long))
+    relu = BertModel(BertConfig(vocab_size=50, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+                                intermediate_size=256, hidden_act="relu"))
+    assert "hidden_act" in text_tower.unsupported_reason(relu, training=False)
     assert text_tower.unsupported_reason(torch.nn.Linear(2, 2), training=False) == "not a BertModel"
+    stock = BertModel(BertConfig(vocab_size=50, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+                                 intermediate_size=256))                     # HF defaults: dropout 0.1 / 0.1
+    assert text_tower.unsupported_reason(stock, training=True) is None
+
+
+def test_hidden_dropout_matches_hf_with_shared_masks(emulated, monkeypatch):
+    """training mode, hidden_dropout_prob 0.2: with the SAME keep-masks fed to HF's nn.Dropout and to the tower (call
+    order: embeddings, then per layer BertSelfOutput, BertOutput) outputs and every gradient agree - i.e. dropout sits
+    at the reference's three places, scaled by 1 / (1 - p), and the residual branches bypass it."""
+    _set_operand(torch.float32)
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(11)
+    bert = BertModel(BertConfig(vocab_size=97, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                intermediate_size=256, max_position_embeddings=40, hidden_dropout_prob=0.2,
+                                attention_probs_dropout_prob=0.0)).train()
+    calls = {"n": 0}
+
+    def keep_mask(numel, p):
+        calls["n"] += 1
+        return torch.rand(numel, generator=torch.Generator().manual_seed(1000 + calls["n"])) >= p
+
+    def f_dropout(x, p=0.5, training=True, inplace=False):
+        if not training or p == 0:
+            return x
+        return x * keep_mask(x.numel(), p).view(x.shape) / (1 - p)
+
+    def tower_dropout(x, p):
+        m = keep_mask(x.numel(), p).view(x.shape)
+        return x * m / (1 - p), m
+    monkeypatch.setattr(torch.nn.functional, "dropout", f_dropout)
+    monkeypatch.setattr(text_tower, "_dropout", tower_dropout)
+    ids, mask = _inputs(seed=12)
+    calls["n"] = 0
+    ref = bert(ids, attention_mask=mask)[0]
+    assert calls["n"] == 1 + 2 * 2
+    _objective(ref).backward()
+    ref_grads = {n: p.grad.clone() for n, p in bert.named_parameters() if p.grad is not None}
+    bert.zero_grad(set_to_none=True)
+    calls["n"] = 0
+    out = text_tower.encode(bert, ids, mask)
+    assert calls["n"] == 5 and _rel(out, ref.detach()) < 1e-5
+    _objective(out).backward()
+    for n, g in ref_grads.items():
+        if n.endswith("key.bias"):
+            continue
+        assert _rel(dict(bert.named_parameters())[n].grad, g) < 2e-4, n
+    # eval mode: no dropout call at all
+    calls["n"] = 0
+    with torch.no_grad():
+        text_tower.encode(bert.eval(), ids, mask)
+    assert calls["n"] == 0
+
+
+def test_attention_dropout_is_passed_to_the_attention_core(emulated, monkeypatch):
+    _set_operand(torch.float32)
+    from transformers import BertConfig, BertModel
+    bert = BertModel(BertConfig(vocab_size=97, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+                                intermediate_size=256, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.3)).train()
+    seen = []
+    real = torch.nn.functional.scaled_dot_product_attention
+
+    def sdpa(q, k, v, attn_mask=None, dropout_p=0.0, scale=None, **kw):
+        seen.append(dropout_p)
+        return real(q, k, v, attn_mask=attn_mask, dropout_p=0.0, scale=scale, **kw)
+    monkeypatch.setattr(text_tower.F, "scaled_dot_product_attention", sdpa)
+    ids, mask = _inputs()
+    text_tower.encode(bert, ids, mask)
+    text_tower.encode(bert.eval(), ids, mask)
+    assert seen == [0.3, 0.0]
 
 
 def test_product_path_has_no_cpu_fallback():

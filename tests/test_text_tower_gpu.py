@@ -105,6 +105,28 @@ def test_text_tower_matches_hf(cuda_dev, hidden, heads, layers, inter, B, L, pad
         assert _rel(got, gr) < 5e-2, (n, _rel(got, gr))
 
 
+def test_text_tower_training_mode_dropout(cuda_dev):
+    """CXR-BERT's dropout (0.1 / 0.1) in training mode: runs, finite, and is stochastic; eval mode is deterministic and
+    equals the dropout-free tower."""
+    from transformers import BertConfig, BertModel
+    from vit_exp_b200 import text_tower
+    torch.manual_seed(0)
+    bert = BertModel(BertConfig(vocab_size=30522, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                intermediate_size=1024)).to(cuda_dev).train()
+    ids = torch.randint(0, 30522, (2, 128), generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+    mask = torch.ones(2, 128, dtype=torch.int64, device=cuda_dev)
+    a = text_tower.encode(bert, ids, mask)
+    b = text_tower.encode(bert, ids, mask)
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
+    a[:, 0, :].square().sum().backward()
+    assert all(torch.isfinite(p.grad).all() for n, p in bert.named_parameters() if p.grad is not None)
+    e1 = text_tower.encode(bert.eval(), ids, mask)
+    e2 = text_tower.encode(bert, ids, mask)
+    assert torch.equal(e1, e2)
+    ref = bert(ids, attention_mask=mask)[0]
+    assert _rel(e1[:, 0, :], ref[:, 0, :]) < 2e-2
+
+
 def test_ctclip_step_with_ctk_text_tower(cuda_dev):
     """CTCLIP(config={'ctk_text_tower': True}) gives the same loss as the stock text encoder path (1e-3 relative,
     the north star's loss tolerance) on identical weights and inputs."""

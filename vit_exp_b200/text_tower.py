@@ -5,9 +5,12 @@ attention_mask=text.attention_mask)`; constructed in scripts/run_train.py:2,143-
 The caller's `BertModel` stays the parameter holder (its state-dict keys are the checkpoint format); this module
 only *reads its parameters* and runs the arithmetic of `BertEmbeddings`, `BertLayer` x depth (post-LayerNorm:
 attention -> dense + residual -> LayerNorm -> intermediate dense + erf GELU -> dense + residual -> LayerNorm)
-through the same tcgen05 GEMM (`ctk_gemm_bf16`, epilogues BF16 / RESID_F32 / GELU / GELU_BWD / ATOMIC_F32) and
+through the same tcgen05 GEMM (`ctk_gemm_bf16`, epilogues BF16 / RESID_F32 / F32 / GELU / GELU_BWD / ATOMIC_F32) and
 LayerNorm kernels the image encoder uses (bias gradients are dY^T 1 products on the same GEMM).  The pooler is not evaluated (CTCLIP reads `[0][:, 0, :]` only,
-ct_clip.py:1273,1313), so `pooler.dense.*` receives no gradient, exactly as in the reference.
+ct_clip.py:1273,1313), so `pooler.dense.*` receives no gradient, exactly as in the reference.  Dropout (training
+mode, hidden 0.1 / attention 0.1 in CXR-BERT): the three hidden dropouts use torch's dropout kernel (the residual add
+then leaves the GEMM epilogue), the attention-probability dropout is SDPA's `dropout_p`; masks are statistically,
+not bitwise, those of the stock module.
 
 Data layout: M = B*L token rows, hidden H; fp32 residual stream, bf16 GEMM operands written by the producing
 kernel, packed `qkv` bf16 [M, 3H] (q | k | v, heads contiguous inside each third).
@@ -44,8 +47,6 @@ def unsupported_reason(bert, training: bool) -> Optional[str]:
         return "relative position embeddings"
     if getattr(cfg, "is_decoder", False) or getattr(cfg, "add_cross_attention", False):
         return "decoder / cross-attention configuration"
-    if training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0):
-        return "dropout > 0 in training mode"
     H, heads = cfg.hidden_size, cfg.num_attention_heads
     if H % 64 or H > 1024 or cfg.intermediate_size % 32 or H % heads:
         return f"hidden size {H} / intermediate {cfg.intermediate_size}: LayerNorm needs H % 64 == 0, H <= 1024"
@@ -77,6 +78,11 @@ class _Shape:
         self.I = cfg.intermediate_size
         self.depth = len(bert.encoder.layer)
         self.eps = float(cfg.layer_norm_eps)
+        # BertEmbeddings / BertSelfOutput / BertOutput dropout and the attention-probability dropout: active in
+        # training mode only (CXR-BERT ships with 0.1 / 0.1)
+        self.pad_idx = bert.embeddings.word_embeddings.padding_idx      # nn.Embedding(padding_idx=pad_token_id)
+        self.p_hidden = float(cfg.hidden_dropout_prob) if bert.training else 0.0
+        self.p_attn = float(cfg.attention_probs_dropout_prob) if bert.training else 0.0
 
 
 def _operand(w: torch.Tensor) -> torch.Tensor:
@@ -85,6 +91,15 @@ def _operand(w: torch.Tensor) -> torch.Tensor:
 
 def _operand_t(w: torch.Tensor) -> torch.Tensor:
     return ops.transpose_cast_bf16(w.contiguous())
+
+
+def _dropout(x: torch.Tensor, p: float):
+    """(x * mask / (1 - p), mask) - torch's own dropout kernel and Philox stream, like nn.Dropout in the HF module"""
+    return torch.native_dropout(x, p, True)
+
+
+def _dropout_bwd(g: torch.Tensor, mask: torch.Tensor, p: float) -> torch.Tensor:
+    return g * mask * (1.0 / (1.0 - p))
 
 
 def _prep_layer(lp: List[torch.Tensor], need_bwd: bool) -> Dict[str, torch.Tensor]:
@@ -105,9 +120,9 @@ def _attention(qkv: torch.Tensor, s: _Shape, key_mask: Optional[torch.Tensor], n
     if need_bwd:
         with torch.enable_grad():
             q, k, v = (t.detach().requires_grad_(True) for t in (q, k, v))
-            o = F.scaled_dot_product_attention(q, k, v, attn_mask=key_mask, scale=s.dh ** -0.5)
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=key_mask, dropout_p=s.p_attn, scale=s.dh ** -0.5)
     else:
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=key_mask, scale=s.dh ** -0.5)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=key_mask, dropout_p=s.p_attn, scale=s.dh ** -0.5)
     ctx = o.detach().transpose(1, 2).reshape(s.M, s.H).contiguous()
     return ctx, ((q, k, v, o) if need_bwd else None)
 
@@ -151,7 +166,14 @@ def _forward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, k
     e = e + pos[: s.L].unsqueeze(0)
     e = e + (typ[0] if token_type_ids is None else F.embedding(token_type_ids, typ))
     e = e.reshape(M, H).float().contiguous()
-    xb, x, _, mue, rse = ops.layernorm_fwd(e, ge, be, want_bf16=True, want_f32=True, eps=s.eps)
+    ph = s.p_hidden
+    m0 = None
+    if ph > 0:
+        _, x, _, mue, rse = ops.layernorm_fwd(e, ge, be, want_bf16=False, want_f32=True, eps=s.eps)
+        x, m0 = _dropout(x, ph)
+        xb = ops.cast_bf16(x)
+    else:
+        xb, x, _, mue, rse = ops.layernorm_fwd(e, ge, be, want_bf16=True, want_f32=True, eps=s.eps)
     saved = []
     for li in range(s.depth):
         lp = params[N_EMB + li * N_PER_LAYER: N_EMB + (li + 1) * N_PER_LAYER]
@@ -161,19 +183,30 @@ def _forward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, k
         ops.gemm(xb, w["wqkv"], ops.EPI_BF16, qkv, M=M, N=3 * H, K=H, bias=w["bqkv"])
         ctxb, attn_saved = _attention(qkv, s, key_mask, save)
         y1 = torch.empty(M, H, dtype=torch.float32, device=dev)
-        ops.gemm(ctxb, w["wo"], ops.EPI_RESID_F32, y1, M=M, N=H, K=H, bias=bo, resid=x)      # BertSelfOutput
+        m1 = m2 = None
+        if ph > 0:      # BertSelfOutput: dense -> dropout -> + input (the residual add leaves the epilogue)
+            ops.gemm(ctxb, w["wo"], ops.EPI_F32, y1, M=M, N=H, K=H, bias=bo)
+            y1, m1 = _dropout(y1, ph)
+            y1 = y1.add_(x)
+        else:
+            ops.gemm(ctxb, w["wo"], ops.EPI_RESID_F32, y1, M=M, N=H, K=H, bias=bo, resid=x)  # BertSelfOutput
         x1b, x1, _, mu1, rs1 = ops.layernorm_fwd(y1, g1, b1, want_bf16=True, want_f32=True, eps=s.eps)
         U = torch.empty(M, I, dtype=od, device=dev)
         G = torch.empty(M, I, dtype=od, device=dev)
         ops.gemm(x1b, w["wi"], ops.EPI_GELU, U, M=M, N=I, K=H, bias=bi, aux0=G, ld_aux0=I)       # BertIntermediate
         y2 = torch.empty(M, H, dtype=torch.float32, device=dev)
-        ops.gemm(G, w["wo2"], ops.EPI_RESID_F32, y2, M=M, N=H, K=I, bias=bo2, resid=x1)         # BertOutput
+        if ph > 0:      # BertOutput: dense -> dropout -> + input
+            ops.gemm(G, w["wo2"], ops.EPI_F32, y2, M=M, N=H, K=I, bias=bo2)
+            y2, m2 = _dropout(y2, ph)
+            y2 = y2.add_(x1)
+        else:
+            ops.gemm(G, w["wo2"], ops.EPI_RESID_F32, y2, M=M, N=H, K=I, bias=bo2, resid=x1)     # BertOutput
         x2b, x2, _, mu2, rs2 = ops.layernorm_fwd(y2, g2, b2, want_bf16=True, want_f32=True, eps=s.eps)
         if save:
             saved.append(dict(w=w, xb=xb, attn=attn_saved, ctxb=ctxb, y1=y1, mu1=mu1, rs1=rs1, x1b=x1b, U=U, G=G,
-                              y2=y2, mu2=mu2, rs2=rs2))
+                              y2=y2, mu2=mu2, rs2=rs2, m1=m1, m2=m2))
         x, xb = x2, x2b
-    emb_saved = dict(e=e, mu=mue, rs=rse) if save else None
+    emb_saved = dict(e=e, mu=mue, rs=rse, m0=m0) if save else None
     return x.view(s.B, s.L, H), saved, emb_saved
 
 
@@ -202,6 +235,8 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
         dg2, db2 = torch.zeros(H, **f32), torch.zeros(H, **f32)
         dy2b = torch.empty(M, H, dtype=od, device=dev)
         dy2 = ops.layernorm_bwd(g, sv["y2"], g2, sv["mu2"], sv["rs2"], dg2, db2, dx_bf16=dy2b)
+        if sv["m2"] is not None:         # the dense branch sees the masked gradient, the residual branch dy2 itself
+            dy2b = ops.cast_bf16(_dropout_bwd(dy2, sv["m2"], s.p_hidden))
         dbo2 = bias_grad(dy2b, H)
         dwo2 = torch.zeros(H, I, **f32)
         ops.gemm(dy2b, sv["G"], ops.EPI_ATOMIC_F32, dwo2, M=H, N=I, K=M, mn_major=True, ldc=I)
@@ -217,6 +252,8 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
         dg1, db1 = torch.zeros(H, **f32), torch.zeros(H, **f32)
         dy1b = torch.empty(M, H, dtype=od, device=dev)
         dy1 = ops.layernorm_bwd(dx1, sv["y1"], g1, sv["mu1"], sv["rs1"], dg1, db1, dx_bf16=dy1b)
+        if sv["m1"] is not None:
+            dy1b = ops.cast_bf16(_dropout_bwd(dy1, sv["m1"], s.p_hidden))
         dbo = bias_grad(dy1b, H)
         dwo = torch.zeros(H, H, **f32)
         ops.gemm(dy1b, sv["ctxb"], ops.EPI_ATOMIC_F32, dwo, M=H, N=H, K=M, mn_major=True, ldc=H)
@@ -236,8 +273,12 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
     # ---- embeddings
     word, pos, typ, ge, be = params[:N_EMB]
     dge, dbe = torch.zeros(H, **f32), torch.zeros(H, **f32)
+    if emb_saved["m0"] is not None:
+        g = _dropout_bwd(g, emb_saved["m0"], s.p_hidden)
     de = ops.layernorm_bwd(g, emb_saved["e"], ge, emb_saved["mu"], emb_saved["rs"], dge, dbe)
     dword = torch.zeros_like(word, dtype=torch.float32).index_add_(0, input_ids.reshape(-1), de)
+    if s.pad_idx is not None:
+        dword[s.pad_idx].zero_()                   # nn.Embedding never updates its padding row
     dpos = torch.zeros_like(pos, dtype=torch.float32)
     dpos[: s.L] = de.view(s.B, s.L, H).sum(0)
     dtyp = torch.zeros_like(typ, dtype=torch.float32)
