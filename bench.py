@@ -146,7 +146,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_model(dev, seed=0, config=None):
+def build_model(dev, seed=0, config=None, text_dropout=0.0):
     import torch
     from transformers import BertConfig, BertModel
     from vit_exp_b200.ct_clip import CTCLIP
@@ -154,7 +154,7 @@ def build_model(dev, seed=0, config=None):
     torch.manual_seed(seed)
     vit = CTViT(dim=512, codebook_size=8192, image_size=480, patch_size=20, temporal_patch_size=10,
                 spatial_depth=4, temporal_depth=4, dim_head=32, heads=8)          # run_train.py:56-66
-    bert = BertModel(BertConfig(vocab_size=30522, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    bert = BertModel(BertConfig(vocab_size=30522, hidden_dropout_prob=text_dropout, attention_probs_dropout_prob=text_dropout))
     clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=512, dim_latent=512, config=dict(config or {}))
     return clip.to(dev)
 
@@ -193,7 +193,7 @@ def run_ours(args):
     cfg = {} if args.sync_loss_read else {"defer_loss_read": True}
     if args.text_tower == "ctk":
         cfg["ctk_text_tower"] = True
-    clip = build_model(dev, seed=0, config=cfg)
+    clip = build_model(dev, seed=0, config=cfg, text_dropout=args.text_dropout)
     clip.train()
     bert = clip.text_transformer
     model = clip
@@ -398,9 +398,9 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (1.77 GB of volumes per step); two alternating batches",
                    "e2e_pipeline": "host batch (pinned) -> H2D on a side stream into one of 3 device slots while the "
                                    "previous step computes; loss read back (.item()) every step",
-                   "text_tower": ("BertModel parameters through libctk (vit_exp_b200/text_tower.py), dropout 0"
-                                  if args.text_tower == "ctk" else
-                                  "stock PyTorch BertModel under bf16 autocast, dropout 0 (both arms)"),
+                   "text_tower": (("BertModel parameters through libctk (vit_exp_b200/text_tower.py)"
+                                   if args.text_tower == "ctk" else "stock PyTorch BertModel under bf16 autocast")
+                                  + f", dropout {args.text_dropout} (CXR-BERT ships 0.1; the CPU arm uses 0)"),
                    "loss_read": "loss.item() inside forward" if args.sync_loss_read else
                                 "config['defer_loss_read']: async D2H copy, read every step after the step is enqueued",
                    "launch": "encoder forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
@@ -533,6 +533,8 @@ def main():
                     help="also time the e2e pipeline from float16 STORED arrays through vit_exp_b200.data / ctk_volume_prep (informational)")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: libctk clip+Adam (2 launches); torch: clip_grad_norm_ + torch.optim.Adam(fused=True)")
+    ap.add_argument("--text-dropout", type=float, default=0.0,
+                    help="hidden / attention dropout of the random-init BERT-base text tower (CXR-BERT's config has 0.1)")
     ap.add_argument("--text-tower", default="hf", choices=["hf", "ctk"],
                     help="hf: the BertModel runs as passed (stock PyTorch, bf16 autocast); ctk: its forward/backward run "
                          "through libctk (vit_exp_b200/text_tower.py; opt-in until validated on hardware)")
