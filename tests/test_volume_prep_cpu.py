@@ -40,3 +40,21 @@ def test_axis_plan_covers_target(n, t):
         assert length == t and pad == 0 and start == (n - t) // 2
     else:
         assert start == 0 and length == n and pad == (t - n) // 2
+
+
+def test_data_module_host_side(tmp_path):
+    """vit_exp_b200.data: staging keeps the stored dtype, unsupported dtypes are refused, and there is no CPU path."""
+    import torch
+
+    from vit_exp_b200 import data
+    arr16 = V.synthetic_volume((5, 6, 7), "float16", 1)
+    p = tmp_path / "v.npz"
+    np.savez(p, arr16)
+    t = data.stage(str(p), pin=False)
+    assert t.dtype == torch.float16 and tuple(t.shape) == (5, 6, 7) and np.array_equal(t.numpy(), arr16)
+    assert data.stage(arr16.astype(np.float32), pin=False).dtype == torch.float32
+    with pytest.raises(TypeError):
+        data.stage(arr16.astype(np.float64), pin=False)
+    with pytest.raises(AssertionError):
+        data.npz_to_tensor(arr16, device="cpu")
+    assert data.TARGET_DHW == (V.TARGET_HWD[2], V.TARGET_HWD[0], V.TARGET_HWD[1])
