@@ -161,7 +161,7 @@ def _forward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, k
     od = OPERAND_DTYPE
     dev = input_ids.device
     M, H, I = s.M, s.H, s.I
-    # BertEmbeddings: word + position (absolute, 0..L-1) + token type, LayerNorm (dropout is 0 on this path)
+    # BertEmbeddings: word + position (absolute, 0..L-1) + token type, LayerNorm, dropout
     e = F.embedding(input_ids, word)
     e = e + pos[: s.L].unsqueeze(0)
     e = e + (typ[0] if token_type_ids is None else F.embedding(token_type_ids, typ))
