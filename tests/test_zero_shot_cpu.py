@@ -48,8 +48,8 @@ def _worker(rank, world, port, out, n):
     from vit_exp_b200 import zero_shot as Z
 
     class _Scorer(Z.ZeroShotScorer):             # the per-volume arithmetic is libctk's (GPU suite); here: volume i -> row i
-        def score(self, volume):
-            return volume.reshape(-1)[:18] * 2.0
+        def score_many(self, volumes):
+            return volumes.reshape(volumes.shape[0], -1)[:, :18] * 2.0
 
     sc = _Scorer(clip=None)
     sc.prompt_latents = torch.zeros(36, 4)
@@ -58,7 +58,7 @@ def _worker(rank, world, port, out, n):
     def load(i):
         loaded.append(i)
         return torch.full((1, 1, 2, 3, 3), float(i))
-    res = sc.run(n, load)
+    res = sc.run(n, load, batch_size=2)
     torch.save(dict(res=res, loaded=loaded), f"{out}.{rank}")
     dist.barrier()
     dist.destroy_process_group()
@@ -105,6 +105,8 @@ def test_scorer_matches_forward_infer_math(monkeypatch):
     sc = Z.ZeroShotScorer(clip)
     sc.prepare(text_embeds=[(e,) for e in emb])
     got = sc.score(torch.zeros(1, 1, 6, 8, 12))
+    many = sc.score_many(torch.zeros(1, 1, 6, 8, 12))
+    assert many.shape == (1, 18) and torch.equal(many[0], got)
     il = O.image_latent(tokens, clip.to_visual_latent.weight.detach())
     want = []
     for e in emb:

@@ -34,5 +34,6 @@ grep -h '^{' gpurun_out/r2_bench_ctk.log > gpurun_out/r2_bench_ctk.json
 CTK_CLIP_LOSS_TC=0 run configs_simt 600 python tools/bench_configs.py
 CTK_CLIP_LOSS_TC=1 run configs_tc 600 python tools/bench_configs.py
 run zero_shot_bench 600 python tools/bench_zero_shot.py --volumes 32
+run zero_shot_bench_b8 600 python tools/bench_zero_shot.py --volumes 64 --batch 8
 run config1 300 python tools/bench_config1.py --gpu
 run h2d_probe 300 python tools/h2d_probe.py

@@ -95,21 +95,31 @@ class ZeroShotScorer:
     @torch.no_grad()
     def score(self, volume: torch.Tensor) -> torch.Tensor:
         """volume (1, 1, D, H, W) -> P(present) [n_path]"""
-        assert self.prompt_latents is not None, "call prepare() first"
-        _, il = self.clip.latents(image=volume)
-        lt = self.clip.temperature.detach().reshape(1).float()
-        return probs_from_logits(ops.pair_logits(self.prompt_latents, il[0].contiguous(), lt))
+        return self.score_many(volume)[0]
 
     @torch.no_grad()
-    def run(self, n_volumes: int, load: Callable[[int], torch.Tensor]) -> torch.Tensor:
-        """Scores volumes [0, n_volumes): this rank calls `load(i)` for its contiguous share only; every rank
-        returns the full [n_volumes, n_path] matrix in volume order."""
+    def score_many(self, volumes: torch.Tensor) -> torch.Tensor:
+        """volumes (B, 1, D, H, W) -> P(present) [B, n_path].  Volumes are independent, so one encoder pass over B of
+        them (the encoder runs ~1.7x faster per volume at B = 8 than at B = 1, profiles/r1_side_configs.jsonl) gives
+        exactly the per-volume results of the reference's batch-1 loop (zero_shot.py:543-550)."""
+        assert self.prompt_latents is not None, "call prepare() first"
+        _, il = self.clip.latents(image=volumes)
+        lt = self.clip.temperature.detach().reshape(1).float()
+        rows = [probs_from_logits(ops.pair_logits(self.prompt_latents, il[b].contiguous(), lt)) for b in range(il.shape[0])]
+        return torch.stack(rows)
+
+    @torch.no_grad()
+    def run(self, n_volumes: int, load: Callable[[int], torch.Tensor], batch_size: int = 1) -> torch.Tensor:
+        """Scores volumes [0, n_volumes): this rank calls `load(i)` (-> (1, 1, D, H, W)) for its contiguous share only,
+        `batch_size` volumes per encoder pass; every rank returns the full [n_volumes, n_path] matrix in volume order."""
         on = dist.is_available() and dist.is_initialized()
         world = dist.get_world_size(self.group) if on else 1
         rank = dist.get_rank(self.group) if on else 0
         lo, hi = shard_bounds(n_volumes, world, rank)
         n_path = self.prompt_latents.shape[0] // 2
         local = torch.empty(hi - lo, n_path, dtype=torch.float32, device=self.prompt_latents.device)
-        for j, i in enumerate(range(lo, hi)):
-            local[j] = self.score(load(i))
+        for i0 in range(lo, hi, max(1, batch_size)):
+            i1 = min(hi, i0 + max(1, batch_size))
+            vols = torch.cat([load(i) for i in range(i0, i1)], dim=0)
+            local[i0 - lo: i1 - lo] = self.score_many(vols)
         return gather_rows(local, n_volumes, self.group)
