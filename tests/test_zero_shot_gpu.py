@@ -39,3 +39,27 @@ def test_scorer_vs_oracle(cuda_dev):
             tl = O.text_latent(emb[p].cpu().double(), clip.to_text_latent.weight.detach().cpu().double())
             want = torch.softmax(O.forward_infer_logits(tl, il, clip.temperature.detach().cpu().double()), 0)[0]
             assert abs(float(probs[i, p]) - float(want)) < 1e-4
+
+
+def test_eval_graph_replay_matches_eager(cuda_dev):
+    """opt-in CUDA-graph replay of the no-grad eval forward (CTViT.eval_graphs): bit-identical to eager launches, across
+    different input volumes and after a parameter update (the graph reads the fp32 masters each replay)."""
+    from vit_exp_b200.transformer_maskgit import CTViT
+    torch.manual_seed(0)
+    vit = CTViT(dim=128, codebook_size=256, image_size=40, patch_size=20, temporal_patch_size=10, spatial_depth=1,
+                temporal_depth=1, dim_head=32, heads=4).to(cuda_dev).eval()
+    g = torch.Generator().manual_seed(1)
+    vols = [torch.rand(1, 1, 20, 40, 40, generator=g).to(cuda_dev) for _ in range(5)]
+    with torch.no_grad():
+        vit.eval_graphs = False
+        eager = [vit(v, return_encoded_tokens=True).clone() for v in vols]
+        vit.eval_graphs = True
+        replay = [vit(v, return_encoded_tokens=True).clone() for v in vols]        # calls 1-2 eager, 3 captures, 4-5 replay
+        assert len(vit._graphs) == 1 and next(iter(vit._graphs.values())).fwd is not None
+        for a, b in zip(eager, replay):
+            assert torch.equal(a, b)
+        vit.to_patch_emb[2].weight.mul_(1.01)
+        vit.eval_graphs = False
+        want = vit(vols[0], return_encoded_tokens=True).clone()
+        vit.eval_graphs = True
+        assert torch.equal(vit(vols[0], return_encoded_tokens=True), want)

@@ -37,3 +37,5 @@ run zero_shot_bench 600 python tools/bench_zero_shot.py --volumes 32
 run zero_shot_bench_b8 600 python tools/bench_zero_shot.py --volumes 64 --batch 8
 run config1 300 python tools/bench_config1.py --gpu
 run h2d_probe 300 python tools/h2d_probe.py
+CTK_EVAL_GRAPHS=1 run configs_evalgraph 600 python tools/bench_configs.py
+CTK_EVAL_GRAPHS=1 run zero_shot_bench_graph 600 python tools/bench_zero_shot.py --volumes 32

@@ -489,6 +489,45 @@ def _graph_launch(vit: "CTViT", video: torch.Tensor, training: bool, params: Lis
     return dict(eg=eg, out=out.clone(), ind=ind.clone(), pre_vq=pre_vq.clone(), saved=saved, token=token)
 
 
+def _eval_graph_forward(vit: "CTViT", video: torch.Tensor, params: List[torch.Tensor]):
+    """No-grad, eval-mode forward replayed from a CUDA graph (opt-in: `CTViT.eval_graphs` / CTK_EVAL_GRAPHS=1, not yet
+    run on hardware).  At one volume per call (zero-shot scoring, BASELINE configs 2 and 4) the ~260 launches of the
+    forward cost about as much host time as the GPU needs to execute them; replaying them as one graph removes that.
+    Same mechanics as the training graphs: the patch gather stays outside (it reads the caller's volume) and writes into
+    static buffers, the caller receives private copies of the outputs.  Returns None when this call runs eagerly."""
+    if not (vit.eval_graphs and ops.GEMM_PROFILE is None and not torch.cuda.is_current_stream_capturing()):
+        return None
+    key = ("eval",) + _graph_key(video, False, params, vit.vq._codebook.embed)
+    eg = vit._graphs.get(key)
+    if eg is None:
+        if len(vit._graphs) >= 4:
+            vit._graphs.clear()
+        eg = vit._graphs[key] = _EncoderGraph()
+    eg.calls += 1
+    if eg.failed or eg.calls <= _EncoderGraph.WARMUP:
+        return None
+    cfg = _Cfg(vit, video)
+    if eg.fwd is None:
+        try:
+            eg.pool = torch.cuda.graph_pool_handle()
+            st_x = ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2)
+            g, outs, n = _capture(lambda: _encode_forward(vit, video, params, save=False, training=False, xhat=st_x[0]),
+                                  eg.pool)
+            eg.fwd = dict(graph=g, outs=outs, launches=n, xbuf=st_x)
+        except Exception as e:                                                  # pragma: no cover
+            import warnings
+            warnings.warn(f"CTViT: CUDA-graph capture of the eval forward failed ({e}); staying on eager launches")
+            eg.failed = True
+            torch.cuda.synchronize()
+            return None
+    f = eg.fwd
+    ops.patch_norm_fwd(video, cfg.pt, cfg.p1, cfg.p2, out=f["xbuf"])
+    f["graph"].replay()
+    ops.GRAPH_LAUNCHES += f["launches"]
+    out, ind, pre_vq, _ = f["outs"]
+    return out.clone(), ind.clone(), pre_vq.clone()
+
+
 class _CTViTEncode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vit, video, training, launched, *params):
@@ -566,6 +605,8 @@ class CTViT(nn.Module):
         # training-shape forward / backward are replayed from CUDA graphs after two eager steps (see _EncoderGraph);
         # set to False to keep every step on eager launches
         self.cuda_graphs = os.environ.get("CTK_CUDA_GRAPHS", "1") != "0"
+        # opt-in (not yet validated on hardware): the no-grad eval forward is replayed from a CUDA graph as well
+        self.eval_graphs = os.environ.get("CTK_EVAL_GRAPHS", "0") == "1"
         self._graphs = {}
 
     # -- reference helpers kept for callers --------------------------------------------------------
@@ -613,6 +654,10 @@ class CTViT(nn.Module):
         video = video.contiguous().float()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _CTViTEncode.apply(self, video, self.training, None, *params)
+        if self.eval_graphs and not self.training:
+            replayed = _eval_graph_forward(self, video, params)
+            if replayed is not None:
+                return replayed
         out, ind, pre, _ = _encode_forward(self, video, params, save=False, training=self.training)
         return out, ind, pre
 
