@@ -153,3 +153,27 @@ def test_training_forward_updates_codebook_like_oracle(doubles):
     assert torch.equal(ind.reshape(-1), ind_ref.reshape(-1))
     assert _rel(vit.vq._codebook.cluster_size[0], cs_ref) < 1e-6
     assert _rel(vit.vq._codebook.embed[0], embed_ref) < 1e-5
+
+
+def test_bf16_operands_stay_within_the_stated_tolerances(monkeypatch):
+    """bf16 operand copies / fp32 accumulation and residual stream, as the kernels compute: pre-VQ tokens within 2e-2
+    relative L2 of the fp32 oracle, parameter gradients within 5e-2."""
+    o = _Ops()
+    monkeypatch.setattr(TM, "ops", o)
+    E.OPERAND = torch.bfloat16
+    vit = _vit(seed=9)
+    video = torch.rand(2, 1, 6, 8, 12, generator=torch.Generator().manual_seed(10))
+    params = [p.detach() for p in vit._flat_params()]
+    _, _, pre_vq, ctx = TM._encode_forward(vit, video, params, save=True, training=False)
+    p = _oracle_params(vit)
+    ref = _oracle_tokens(video, p, vit)
+    assert _rel(pre_vq.view(ref.shape), ref) < 2e-2
+    dtok = torch.randn(ref.shape, generator=torch.Generator().manual_seed(11))
+    (ref * dtok).sum().backward()
+    grads = TM._encode_backward(vit, params, ctx, dtok)
+    by_param = {id(q): n for n, q in vit.named_parameters()}
+    for q, g in zip(vit._flat_params(), grads):
+        n = by_param[id(q)]
+        if n == "spatial_rel_pos_bias.net.2.bias":
+            continue
+        assert _rel(g, p[n].grad) < 5e-2, (n, _rel(g, p[n].grad))
