@@ -70,9 +70,13 @@ typedef enum {
                               [ceil(N/128), M, 3] online softmax statistics (max, sum e^(x-max), sum x e^(x-max)) of
                               every row over each block of 128 columns; aux0 (fp32 [M], may be NULL) receives the
                               logit with row + i0 == col (the positives, ct_clip.py:1355-1358)                 */
-    CTK_EPI_CLIP_GRAD = 11 /* dloss/dlogit of the symmetric InfoNCE, scaled for the latent
+    CTK_EPI_CLIP_GRAD = 11,/* dloss/dlogit of the symmetric InfoNCE, scaled for the latent
                               gradients: g = alpha * exp(*vec1) * (e^(x - vec0[row]) + e^(x - bias[col])
                               - 2 [row + i0 == col + i1]); C = bf16 hi part [M,N], aux0 = bf16 lo part (g - hi) */
+    CTK_EPI_ARGMAX_PART = 12 /* exact VQ code search, pass 1 (ctvit.py:403): for every row and every block of 128
+                              columns, C = uint64 [ceil(N/128), M] = (orderable(best acc) << 32 | ~col) and aux0 = fp32
+                              [ceil(N/128), M] = the block's SECOND best value; ctk_vq_select re-scores in fp32 whatever
+                              lies within the bf16 rounding bound of the row maximum, so the chosen code is the fp32 one */
 } ctk_epilogue;
 
 typedef struct {
@@ -200,6 +204,14 @@ int ctk_l2norm_rows(const float* x, void* xn_bf16, float* xn_f32, long long rows
                     void* stream);
 /* best = uint64 [rows] filled by CTK_EPI_ARGMAX (pre-zeroed). ind int64 [rows];
  * quant fp32 [rows, dim] = embed[ind]. */
+/* Exact code selection (pass 2 of the VQ search).  part_key / part_second: output of CTK_EPI_ARGMAX_PART over
+ * nblk = ceil(C/128) column blocks (similarities of bf16-rounded unit vectors).  Every code whose bf16 similarity lies
+ * within `margin` of the row maximum (margin >= 2^-7 bounds the rounding of two unit vectors) is re-scored as the fp32
+ * dot product of x/max(|x|,1e-12) with en (= l2-normalised codebook, fp32 [C, dim]); the arg-max of those (lowest index
+ * on ties) goes to ind[rows] (int64) and quant[rows, dim] = embed[ind] (raw fp32 codebook rows). dim % 32 == 0, <= 1024. */
+int ctk_vq_select(const void* part_key, const float* part_second, int nblk, const float* x, const float* en,
+                  const float* embed, long long* ind, float* quant, long long rows, int dim,
+                  int codebook_size, float margin, void* stream);
 int ctk_vq_gather(const void* best, const float* embed, long long* ind, float* quant,
                   long long rows, int dim, int codebook_size, void* stream);
 /* training-mode EMA update of cluster_size [C] and embed [C, dim] (decay 0.8);

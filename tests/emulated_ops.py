@@ -389,6 +389,15 @@ def l2norm_rows(x, want_f32=False):
     return xn.to(OPERAND), (xn if want_f32 else None)
 
 
+def vq_search(x, embed, want_xn_f32=False):
+    """double of ops.vq_search: the fp32 arg-max of the cosine similarities (what pass 1 + pass 2 deliver)"""
+    CALLS.append(("vq_search",))
+    xn = x / x.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    en = embed / embed.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    ind = (xn @ en.t()).argmax(dim=1)
+    return ind, embed[ind].float(), (xn if want_xn_f32 else None)
+
+
 def vq_gather(best, embed):
     ind = best.long()
     return ind, embed[ind].float()

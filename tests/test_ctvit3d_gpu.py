@@ -2,7 +2,7 @@
 tokens 2e-2 relative L2, parameter gradients 5e-2).  Uses libctk kernels validated for CTViT (at
 dim 768) plus library SDPA for the joint attention core.
 
-NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent): skipped unless CTK_TEST_UNVERIFIED=1.
+Validated on a B200 in round 2.
 """
 import os
 from types import SimpleNamespace
@@ -10,9 +10,7 @@ from types import SimpleNamespace
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CTK_TEST_UNVERIFIED") != "1",
-                                 reason="CTViT3D path not run on hardware yet (set CTK_TEST_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _rel(a, b):

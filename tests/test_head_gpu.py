@@ -106,3 +106,46 @@ def test_fused_clip_adam_matches_torch(cuda_dev, wd, max_norm):
         for p, q in zip(ref_p, our_p):
             assert torch.allclose(p, q, rtol=2e-5, atol=1e-7), (step, tuple(p.shape), (p - q).abs().max().item())
     assert torch.equal(ref_p[-1], our_p[-1])
+
+
+@pytest.mark.gpu
+def test_fused_clip_adam_state_dict_round_trip(cuda_dev):
+    """resume: state_dict() -> a fresh optimizer -> load_state_dict() -> step continues with the right bias correction
+    (the step count lives in the per-parameter state like torch.optim.Adam's, so the two are interchangeable), and a
+    parameter whose first gradient arrives late keeps its own step count."""
+    import torch
+    from vit_exp_b200.optim import FusedClipAdam
+    g = torch.Generator().manual_seed(5)
+    shapes = [(33,), (130, 17), (4099,)]
+    ref_p = [torch.nn.Parameter(torch.randn(*s, generator=g).to(cuda_dev)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    kw = dict(lr=1e-2, betas=(0.9, 0.99))
+    ref_opt = torch.optim.Adam(ref_p, **kw)
+    our_opt = FusedClipAdam(our_p, **kw)
+
+    def both_step(ro, oo, active):
+        for i, (p, q) in enumerate(zip(ref_p, our_p)):
+            gr = torch.randn(*p.shape, generator=g).to(cuda_dev) if i in active else None
+            p.grad = None if gr is None else gr.clone()
+            q.grad = None if gr is None else gr.clone()
+        ro.step()
+        oo.step()
+    both_step(ref_opt, our_opt, {0, 1})                 # parameter 2 joins one step late
+    both_step(ref_opt, our_opt, {0, 1, 2})
+    sd = our_opt.state_dict()
+    assert float(sd["state"][0]["step"]) == 2.0 and float(sd["state"][2]["step"]) == 1.0
+    resumed = FusedClipAdam(our_p, **kw)
+    resumed.load_state_dict(sd)
+    both_step(ref_opt, resumed, {0, 1, 2})
+    for p, q in zip(ref_p, our_p):
+        assert torch.allclose(p, q, rtol=2e-5, atol=1e-7), (tuple(p.shape), (p - q).abs().max().item())
+    # torch's own Adam state loads into FusedClipAdam (same keys: step / exp_avg / exp_avg_sq)
+    swapped = FusedClipAdam(our_p, **kw)
+    for q, p in zip(our_p, ref_p):
+        q.data.copy_(p.data)
+    import copy
+    tsd = copy.deepcopy(ref_opt.state_dict())      # load_state_dict keeps same-dtype/device tensors by reference
+    swapped.load_state_dict({"state": tsd["state"], "param_groups": resumed.state_dict()["param_groups"]})
+    both_step(ref_opt, swapped, {0, 1, 2})
+    for p, q in zip(ref_p, our_p):
+        assert torch.allclose(p, q, rtol=2e-5, atol=1e-7)

@@ -96,10 +96,7 @@ def test_vq_idempotent_on_codebook_rows(cuda_dev):
     from vit_exp_b200 import ops
     C, dim = 8192, 512
     embed = (F.normalize(torch.randn(C, dim, generator=_g(4)), dim=-1) * 1.01).to(cuda_dev).contiguous()
-    xb, _ = ops.l2norm_rows(embed)
-    best = torch.zeros(C, dtype=torch.int64, device=cuda_dev)
-    ops.gemm(xb, xb, ops.EPI_ARGMAX, best, M=C, N=C, K=dim, ldc=0)
-    ind, quant = ops.vq_gather(best, embed)
+    ind, quant, _ = ops.vq_search(embed, embed)
     assert torch.equal(ind.cpu(), torch.arange(C))
     assert torch.equal(quant, embed)
 

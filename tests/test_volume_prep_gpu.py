@@ -1,6 +1,6 @@
 """ctk_volume_prep (vit_exp_b200.data.npz_to_tensor) against the oracle pinned to scripts/data.py:49-111: BIT-EXACT.
 
-NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent): skipped unless CTK_TEST_UNVERIFIED=1.
+Validated on a B200 in round 2 (6 passed).
 """
 import json
 import os
@@ -12,9 +12,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "volume_prep_golden.json")))
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CTK_TEST_UNVERIFIED") != "1",
-                                 reason="volume-prep kernel not validated on hardware yet (set CTK_TEST_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: "x".join(map(str, c["shape"])) + "_" + c["dtype"])

@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libctk.so"
 
 CTK_OK = 0
 (EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_GEGLU, EPI_GEGLU_BWD, EPI_QKV, EPI_ATOMIC_F32, EPI_ARGMAX, EPI_GELU,
- EPI_GELU_BWD, EPI_LSE_PART, EPI_CLIP_GRAD) = range(12)
+ EPI_GELU_BWD, EPI_LSE_PART, EPI_CLIP_GRAD, EPI_ARGMAX_PART) = range(13)
 
 _vp = C.c_void_p
 _ll = C.c_longlong
@@ -56,6 +56,7 @@ SIGNATURES = {
     "ctk_attn_bwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _i, _vp]),
     "ctk_qknorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _ll, _i, _vp]),
     "ctk_l2norm_rows": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "ctk_vq_select": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _vp]),
     "ctk_vq_gather": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "ctk_vq_ema_update": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _vp]),
     "ctk_mean_pool_fwd": (_i, [_vp, _vp, _i, _ll, _i, _vp]),

@@ -273,11 +273,7 @@ template <int NH>
 int launch_fwd(const CUtensorMap& tq, __nv_bfloat16* out, float* lse, int nseq, cudaStream_t s) {
     auto kern = attn_seq24_fwd_kernel<NH>;
     constexpr int smem = STAGES * 3 * NH * TILE + 512 + 2 * STAGES * 8 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    CTK_SET_MAX_SMEM(kern, smem);
     const int per_sm = (227 * 1024) / (smem + 1024) > 0 ? (227 * 1024) / (smem + 1024) : 1;
     int grid = ctk_num_sms() * (per_sm > 4 ? 4 : per_sm);
     if (grid > nseq) grid = nseq;
@@ -290,11 +286,7 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap&
                int nseq, cudaStream_t s) {
     auto kern = attn_seq24_bwd_kernel<NH>;
     constexpr int smem = STAGES * 5 * NH * TILE + 512 + 2 * STAGES * 8 + NH * 64 * 4 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    CTK_SET_MAX_SMEM(kern, smem);
     const int per_sm = (227 * 1024) / (smem + 1024) > 0 ? (227 * 1024) / (smem + 1024) : 1;
     int grid = ctk_num_sms() * (per_sm > 4 ? 4 : per_sm);
     if (grid > nseq) grid = nseq;

@@ -361,11 +361,7 @@ int ctk_attn_fwd_tc(const void* qkv, const float* table, void* out, float* lse, 
     int rc;
     if ((rc = ctk_make_tmap(&tq, qkv, false, 2, dims, strides, box_q, 2))) return rc;
     if ((rc = ctk_make_tmap(&tkv, qkv, false, 2, dims, strides, box_kv, 2))) return rc;
-    static bool configured = false;
-    if (!configured) {
-        CTK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
+    CTK_SET_MAX_SMEM(attn_fwd_tc_kernel, SMEM_BYTES);
     const long long G = (long long)nseq * heads * NQT;
     long long grid = 2LL * ctk_num_sms();
     if (grid > G) grid = G;

@@ -588,11 +588,7 @@ template <bool DKV>
 int launch_bwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, const float* table,
                const float* lse, const float* delta, __nv_bfloat16* dqkv, int nseq, int heads, cudaStream_t stream) {
     auto kern = attn_bwd_tc_kernel<DKV>;
-    static bool configured = false;
-    if (!configured) {
-        CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_BYTES));
-        configured = true;
-    }
+    CTK_SET_MAX_SMEM(kern, B_SMEM_BYTES);
     const long long G = (long long)nseq * heads * NQT;
     long long grid = 2LL * ctk_num_sms();
     if (grid > G) grid = G;
@@ -628,11 +624,7 @@ int ctk_attn_bwd_tc(const void* qkv, const float* table, const void* dout, const
     CUtensorMap te;
     const unsigned int box_chunk[2] = {32, DC};
     if ((rc = ctk_make_tmap(&te, qkv, false, 2, dims_qkv, str_qkv, box_chunk, 2))) return rc;
-    static bool configured = false;
-    if (!configured) {
-        CTK_CUDA(cudaFuncSetAttribute(attn_dbias_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
-        configured = true;
-    }
+    CTK_SET_MAX_SMEM(attn_dbias_tc_kernel, D_SMEM_BYTES);
     // two CTAs per SM (256 TMEM columns each): one CTA's control / MMA round trip is covered by the other's
     // softmax; split the slices so that there are ~5 items per CTA
     const int blocks = heads * NQT * NDC;

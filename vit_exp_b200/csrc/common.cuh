@@ -63,16 +63,36 @@ int ctk_attn_seq24_bwd(const void* qkv, const void* out, const void* dout, const
 
 #define CTK_ALIGNED(p, a) ((reinterpret_cast<uintptr_t>(p) % (a)) == 0)
 
-static inline int ctk_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+// Per-DEVICE caches (a process may touch several GPUs; attributes set with cudaFuncSetAttribute and the SM count are
+// properties of the device, not of the process).  Plain int / byte stores of an idempotent value: safe across threads.
+constexpr int CTK_MAX_DEVICES = 64;
+static inline int ctk_current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
 }
+static inline int ctk_num_sms() {
+    static int n[CTK_MAX_DEVICES] = {};
+    const int dev = ctk_current_device();
+    const int slot = (dev >= 0 && dev < CTK_MAX_DEVICES) ? dev : 0;
+    if (n[slot] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[slot] = v > 0 ? v : 148;
+    }
+    return n[slot];
+}
+// opt a kernel into `bytes` of dynamic shared memory, once per device
+#define CTK_SET_MAX_SMEM(kern, bytes)                                                                          \
+    do {                                                                                                       \
+        static volatile unsigned char _ctk_done[CTK_MAX_DEVICES] = {};                                         \
+        const int _ctk_dev = ctk_current_device();                                                             \
+        const bool _ctk_in = _ctk_dev >= 0 && _ctk_dev < CTK_MAX_DEVICES;                                      \
+        if (!_ctk_in || !_ctk_done[_ctk_dev]) {                                                                \
+            CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+            if (_ctk_in) _ctk_done[_ctk_dev] = 1;                                                              \
+        }                                                                                                      \
+    } while (0)
 
 // ----------------------------------------------------------------------------------------------
 // device helpers

@@ -910,6 +910,95 @@ __global__ void vq_gather_kernel(const unsigned long long* __restrict__ best,
     for (int c = lane; c < dim; c += 32) quant[row * dim + c] = __ldg(e + c);
 }
 
+// Exact VQ code selection (pass 2; pass 1 = the CTK_EPI_ARGMAX_PART GEMM epilogue on bf16-rounded unit vectors).
+// CTA = 32 rows: the per-block (best key, second value) pairs are staged in shared memory with coalesced loads,
+// then each warp resolves 4 rows.  A row whose bf16 maximum is unique within `margin` keeps that code; otherwise
+// every code that may be the fp32 maximum - the best of each block within the margin, or all 128 codes of a block
+// whose second best is within it too - is re-scored as an fp32 dot product and the largest (lowest index on ties) wins.
+__device__ __forceinline__ float vq_key_value(unsigned long long k) {
+    uint32_t u = (uint32_t)(k >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256)
+vq_select_kernel(const unsigned long long* __restrict__ pkey, const float* __restrict__ psec, int nblk,
+                 const float* __restrict__ x, const float* __restrict__ en, const float* __restrict__ embed,
+                 long long* __restrict__ ind, float* __restrict__ quant, long long rows, int dim, int C, float margin) {
+    extern __shared__ __align__(16) uint8_t vq_sm[];
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(vq_sm);
+    float* ss = reinterpret_cast<float*>(sk + (size_t)nblk * 32);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long row0 = (long long)blockIdx.x * 32;
+    for (int i = tid; i < nblk * 32; i += 256) {
+        const int b = i >> 5, r = i & 31;
+        const bool ok = row0 + r < rows;
+        sk[i] = ok ? pkey[(long long)b * rows + row0 + r] : 0ull;
+        ss[i] = ok ? psec[(long long)b * rows + row0 + r] : -INFINITY;
+    }
+    __syncthreads();
+    const int nv = dim >> 5;
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp * 4 + rr;
+        const long long row = row0 + r;
+        if (row >= rows) break;                                   // warp-uniform
+        unsigned long long kb = 0ull;
+        for (int b = lane; b < nblk; b += 32) { const unsigned long long k = sk[b * 32 + r]; kb = k > kb ? k : kb; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, kb, o);
+            kb = t > kb ? t : kb;
+        }
+        const float thr = vq_key_value(kb) - margin;
+        int ncand = 0;
+        for (int b = lane; b < nblk; b += 32)
+            ncand += (vq_key_value(sk[b * 32 + r]) >= thr ? 1 : 0) + (ss[b * 32 + r] >= thr ? 2 : 0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+        long long best_i = (long long)(0xffffffffu - (uint32_t)(kb & 0xffffffffull));
+        if (ncand > 1) {
+            // fp32 re-score: xn = x * (1 / max(|x|, 1e-12)) exactly as ctk_l2norm_rows forms it
+            float xv[32];
+            const float* xr = x + row * dim;
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                xv[j] = j < nv ? xr[lane + 32 * j] : 0.f;
+                sq = fmaf(xv[j], xv[j], sq);
+            }
+            const float rn = 1.0f / fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xv[j] *= rn;
+            float best_v = -INFINITY;
+            best_i = 0x7fffffffffffffffLL;
+            auto score = [&](long long c) {
+                const float* e = en + c * dim;
+                float d = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) d = fmaf(xv[j], __ldg(e + lane + 32 * j), d);
+                d = warp_sum(d);
+                if (d > best_v || (d == best_v && c < best_i)) { best_v = d; best_i = c; }
+            };
+            for (int b = 0; b < nblk; ++b) {
+                const unsigned long long k = sk[b * 32 + r];
+                if (vq_key_value(k) < thr) continue;              // warp-uniform (shared-memory broadcast)
+                if (ss[b * 32 + r] >= thr) {
+                    const int c1 = min(C, (b + 1) * 128);
+                    for (int c = b * 128; c < c1; ++c) score(c);
+                } else {
+                    score((long long)(0xffffffffu - (uint32_t)(k & 0xffffffffull)));
+                }
+            }
+        }
+        if (best_i < 0 || best_i >= C) best_i = 0;
+        if (lane == 0) ind[row] = best_i;
+        const float4* e4 = reinterpret_cast<const float4*>(embed + best_i * dim);
+        float4* q4 = reinterpret_cast<float4*>(quant + row * dim);
+        for (int c = lane; c < dim / 4; c += 32) q4[c] = __ldg(e4 + c);
+    }
+}
+
 // embed_sum[code] += xn[row]; bins[code] += 1
 __global__ void vq_scatter_kernel(const float* __restrict__ xn, const long long* __restrict__ ind,
                                   float* __restrict__ esum, float* __restrict__ bins, long long rows,
@@ -1150,6 +1239,27 @@ extern "C" int ctk_l2norm_rows(const float* x, void* xn_bf16, float* xn_f32, lon
     CTK_REQUIRE(x && (xn_bf16 || xn_f32) && rows > 0 && dim > 0, CTK_ERR_SHAPE, "l2norm_rows: bad args");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     l2norm_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(xn_bf16), xn_f32, rows, dim);
+    CTK_LAUNCH_CHECK();
+    return CTK_OK;
+}
+
+extern "C" int ctk_vq_select(const void* part_key, const float* part_second, int nblk, const float* x, const float* en,
+                             const float* embed, long long* ind, float* quant, long long rows, int dim,
+                             int codebook_size, float margin, void* stream) {
+    int rc = ctk_check_device();
+    if (rc != CTK_OK) return rc;
+    CTK_REQUIRE(part_key && part_second && x && en && embed && ind && quant && rows > 0, CTK_ERR_SHAPE, "vq_select: bad args");
+    CTK_REQUIRE(dim > 0 && dim % 32 == 0 && dim <= 1024 && codebook_size > 0 && nblk == (codebook_size + 127) / 128,
+                CTK_ERR_SHAPE, "vq_select: dim %d (need %% 32 == 0, <= 1024), codebook %d, nblk %d", dim, codebook_size, nblk);
+    CTK_REQUIRE(margin > 0.f, CTK_ERR_SHAPE, "vq_select: margin must be positive");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)nblk * 32 * 12;
+    CTK_REQUIRE(smem <= 200 * 1024, CTK_ERR_SHAPE, "vq_select: codebook too large (%d blocks)", nblk);
+    if (smem > 48 * 1024)
+        CTK_CUDA(cudaFuncSetAttribute(vq_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vq_select_kernel<<<(unsigned)((rows + 31) / 32), 256, smem, s>>>(
+        reinterpret_cast<const unsigned long long*>(part_key), part_second, nblk, x, en, embed, ind, quant, rows, dim,
+        codebook_size, margin);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }

@@ -483,6 +483,36 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
                 (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - (uint32_t)bi);
             atomicMax(best + row, key);
         }
+    } else if constexpr (EPI == CTK_EPI_ARGMAX_PART) {
+        // best (value, column) and second-best value of this warp's 32 rows over its block of 128 columns:
+        // key[blk][row], second[blk][row] with blk = column / 128.  No atomics; ctk_vq_select merges the blocks.
+        const int cbase = n0 + hf * 128;
+        if (cbase < N) {
+            float b1 = -INFINITY, b2 = -INFINITY;
+            int bi = cbase;
+#pragma unroll 1
+            for (int cc = 0; cc < 128; cc += 32) {
+                const int col = cbase + cc;
+                if (col >= N) break;
+                float v[32];
+                ld_acc(t_row + hf * 128 + cc, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (col + i < N) {
+                        if (v[i] > b1) { b2 = b1; b1 = v[i]; bi = col + i; }
+                        else if (v[i] > b2) b2 = v[i];
+                    }
+                }
+            }
+            if (row_ok) {
+                uint32_t u = __float_as_uint(b1);
+                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                const long long slot = (long long)(cbase / 128) * M + row;
+                reinterpret_cast<unsigned long long*>(p.C)[slot] =
+                    (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - (uint32_t)bi);
+                reinterpret_cast<float*>(p.aux0)[slot] = b2;
+            }
+        }
     }
 }
 
@@ -735,11 +765,7 @@ template <int EPI, bool A_MN, bool B_MN, bool PAIR>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc0, const CUtensorMap& tc1, int M,
            int N, int K, int splits, const EpiParams& ep, cudaStream_t stream) {
     auto kern = gemm_kernel<EPI, A_MN, B_MN, PAIR>;
-    static bool configured = false;
-    if (!configured) {
-        CTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
+    CTK_SET_MAX_SMEM(kern, SMEM_BYTES);
     const int rows = PAIR ? 2 * BM : BM;
     const long long work = (long long)((M + rows - 1) / rows) * ((N + BN - 1) / BN) * splits;
     const int sms = ctk_num_sms();
@@ -828,6 +854,8 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (epilogue == CTK_EPI_CLIP_GRAD)
         CTK_REQUIRE(e->vec0 && e->vec1 && e->bias && e->aux0 && !a_mn_major, CTK_ERR_SHAPE,
                     "gemm: CLIP_GRAD needs both lse vectors, the log-scale pointer, the lo buffer and K-major operands");
+    if (epilogue == CTK_EPI_ARGMAX_PART)
+        CTK_REQUIRE(e->aux0 && !a_mn_major, CTK_ERR_SHAPE, "gemm: ARGMAX_PART needs the second-best buffer and K-major operands");
     if (epilogue == CTK_EPI_GEGLU)
         CTK_REQUIRE(N % BN == 0 && e->aux0, CTK_ERR_SHAPE, "gemm: GEGLU needs N %% 256 == 0 and an H buffer");
     if (epilogue == CTK_EPI_GEGLU_BWD)
@@ -909,6 +937,7 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
         CTK_GEMM_CASE_KMAJOR(CTK_EPI_GELU_BWD)
         CTK_GEMM_CASE_KMAJOR(CTK_EPI_LSE_PART)
         CTK_GEMM_CASE_KMAJOR(CTK_EPI_CLIP_GRAD)
+        CTK_GEMM_CASE_KMAJOR(CTK_EPI_ARGMAX_PART)
         CTK_GEMM_CASE(CTK_EPI_BF16)
         CTK_GEMM_CASE(CTK_EPI_F32)
         CTK_GEMM_CASE(CTK_EPI_RESID_F32)

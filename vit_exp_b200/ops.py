@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_ARGMAX, EPI_ATOMIC_F32, EPI_BF16, EPI_CLIP_GRAD, EPI_F32, EPI_GEGLU, EPI_GEGLU_BWD,  # noqa: F401
+from ._lib import (EPI_ARGMAX, EPI_ARGMAX_PART, EPI_ATOMIC_F32, EPI_BF16, EPI_CLIP_GRAD, EPI_F32, EPI_GEGLU, EPI_GEGLU_BWD,  # noqa: F401
                    EPI_GELU, EPI_GELU_BWD, EPI_LSE_PART, EPI_QKV, EPI_RESID_F32, GemmEpilogue, check)
 
 
@@ -306,6 +306,35 @@ def vq_gather(best, embed):
     quant = torch.empty(rows, dim, dtype=torch.float32, device=embed.device)
     check(_lib.load().ctk_vq_gather(_p(best), _p(embed), _p(ind), _p(quant), rows, dim, C, _stream()), "ctk_vq_gather")
     return ind, quant
+
+
+# two bf16-rounded unit vectors: |sim_bf16 - sim_fp32| <= 2 * 2^-9 + O(2^-18), so two candidates can swap order only if
+# their bf16 similarities are closer than 2^-7 (plus fp32 accumulation noise)
+VQ_RESCORE_MARGIN = 2.0 ** -7 + 1e-5
+
+
+def vq_search(x: torch.Tensor, embed: torch.Tensor, want_xn_f32: bool = False):
+    """Cosine-similarity code search of VectorQuantize(use_cosine_sim=True) (ctvit.py:188,403) with the fp32 arg-max:
+    pass 1 = tcgen05 GEMM of the bf16-rounded unit vectors keeping, per row and 128-code block, the best code and the
+    second-best value (the 13824 x 8192 similarities are never stored); pass 2 (ctk_vq_select) re-scores in fp32 every
+    code inside the bf16 rounding bound of the row maximum.  x fp32 [rows, dim] (raw), embed fp32 [C, dim] (raw).
+    Returns (ind int64 [rows], quant fp32 [rows, dim] = embed[ind], xn fp32 or None)."""
+    _chk(x, torch.float32, "x")
+    _chk(embed, torch.float32, "embed")
+    rows, dim = x.shape
+    C = embed.shape[0]
+    dev = x.device
+    xb, xf = l2norm_rows(x, want_f32=want_xn_f32)
+    eb, en = l2norm_rows(embed, want_f32=True)
+    nblk = (C + 127) // 128
+    key = torch.empty(nblk, rows, dtype=torch.int64, device=dev)
+    sec = torch.empty(nblk, rows, dtype=torch.float32, device=dev)
+    gemm(xb, eb, EPI_ARGMAX_PART, key, M=rows, N=C, K=dim, ldc=0, aux0=sec)
+    ind = torch.empty(rows, dtype=torch.int64, device=dev)
+    quant = torch.empty(rows, dim, dtype=torch.float32, device=dev)
+    check(_lib.load().ctk_vq_select(_p(key), _p(sec), nblk, _p(x), _p(en), _p(embed), _p(ind), _p(quant), rows, dim, C,
+                                    VQ_RESCORE_MARGIN, _stream()), "ctk_vq_select")
+    return ind, quant, xf
 
 
 def vq_ema_update_(xn_f32, ind, cluster_size, embed, decay: float = 0.8):

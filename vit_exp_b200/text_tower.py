@@ -117,12 +117,13 @@ def _attention(qkv: torch.Tensor, s: _Shape, key_mask: Optional[torch.Tensor], n
     key-padding mask broadcast over heads and queries."""
     q5 = qkv.view(s.B, s.L, 3, s.heads, s.dh)
     q, k, v = (q5[:, :, i].transpose(1, 2) for i in range(3))            # [B, heads, L, dh] views
+    mask4 = None if key_mask is None else key_mask.view(s.B, 1, 1, s.L)
     if need_bwd:
         with torch.enable_grad():
             q, k, v = (t.detach().requires_grad_(True) for t in (q, k, v))
-            o = F.scaled_dot_product_attention(q, k, v, attn_mask=key_mask, dropout_p=s.p_attn, scale=s.dh ** -0.5)
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask4, dropout_p=s.p_attn, scale=s.dh ** -0.5)
     else:
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=key_mask, dropout_p=s.p_attn, scale=s.dh ** -0.5)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask4, dropout_p=s.p_attn, scale=s.dh ** -0.5)
     ctx = o.detach().transpose(1, 2).reshape(s.M, s.H).contiguous()
     return ctx, ((q, k, v, o) if need_bwd else None)
 
@@ -138,22 +139,13 @@ def _attention_bwd(saved, dctx: torch.Tensor, s: _Shape) -> torch.Tensor:
 
 
 def _key_mask(attention_mask: Optional[torch.Tensor], s: _Shape) -> Optional[torch.Tensor]:
-    """bool [B, 1, 1, L] (True = attend) or None when nothing is padded (the tokenizer pads reports to 512,
-    CTCLIPTrainer.py:562, so real batches do carry padding)."""
+    """bool [B, L] (True = attend) or None when the caller passed no mask.  The tokenizer pads reports to 512
+    (CTCLIPTrainer.py:562), so real batches do carry padding; the mask is always handed to the attention kernel - no
+    host-side 'is it all ones' shortcut (that needs a device sync per batch, and caching its answer by tensor address
+    is wrong as soon as the allocator reuses the address)."""
     if attention_mask is None:
         return None
-    keep = attention_mask.to(torch.bool)
-    key = (attention_mask.data_ptr(), attention_mask._version, tuple(attention_mask.shape))
-    hit = _key_mask.cache.get(key)
-    if hit is None:
-        hit = bool(keep.all())                       # one host sync per distinct mask tensor
-        if len(_key_mask.cache) > 64:
-            _key_mask.cache.clear()
-        _key_mask.cache[key] = hit
-    return None if hit else keep.view(s.B, 1, 1, s.L)
-
-
-_key_mask.cache = {}
+    return attention_mask.to(torch.bool).reshape(s.B, s.L)
 
 
 def _forward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, key_mask, save: bool):

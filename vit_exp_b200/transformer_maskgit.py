@@ -325,13 +325,9 @@ def _encode_forward(vit: "CTViT", video: torch.Tensor, params: List[torch.Tensor
     xs, sp_saved, sp_fin = _transformer_fwd(x0, sp, sp_norm, cfg, table, cfg.B * cfg.t, hw, cfg.h, cfg.w,
                                             (cfg.t, hw), save, save)
     xt, tp_saved, tp_fin = _transformer_fwd(xs, tp, tp_norm, cfg, None, cfg.B * hw, cfg.t, 0, 0, (hw, cfg.t), save, save)
-    # ---- vector quantisation (ctvit.py:403): cosine-sim code search on the tensor cores
+    # ---- vector quantisation (ctvit.py:403): cosine-sim code search on the tensor cores, fp32-exact selection
     embed = vit.vq._codebook.embed[0]
-    xb, xf = ops.l2norm_rows(xt, want_f32=training)
-    eb, _ = ops.l2norm_rows(embed)
-    best = torch.zeros(M, dtype=torch.int64, device=video.device)
-    ops.gemm(xb, eb, ops.EPI_ARGMAX, best, M=M, N=embed.shape[0], K=dim, ldc=0)
-    ind, quant = ops.vq_gather(best, embed)
+    ind, quant, xf = ops.vq_search(xt, embed.contiguous(), want_xn_f32=training)
     if training:
         ops.vq_ema_update_(xf, ind, vit.vq._codebook.cluster_size[0], embed, vit.vq.decay)
     out = quant.view(cfg.B, cfg.t, cfg.h, cfg.w, dim)
@@ -559,7 +555,10 @@ class _CTViTEncode(torch.autograd.Function):
         b = eg.bwd.get(bkey)
         if b is None:
             dy_static = dy.clone()
-            g, grads, n = _capture(lambda: _encode_backward(ctx.vit, ctx.params, ctx.saved, None, dy_in=(dy_static, bcast)),
+            # _transformer_bwd drops its references to the saved activations layer by layer; the graph's static
+            # activations must survive for later captures (another gradient layout), so it gets shallow copies
+            saved_view = dict(ctx.saved, sp_saved=list(ctx.saved["sp_saved"]), tp_saved=list(ctx.saved["tp_saved"]))
+            g, grads, n = _capture(lambda: _encode_backward(ctx.vit, ctx.params, saved_view, None, dy_in=(dy_static, bcast)),
                                    eg.pool)
             b = eg.bwd[bkey] = dict(graph=g, grads=grads, launches=n, dy=dy_static)
         b["dy"].copy_(dy)
@@ -672,7 +671,7 @@ class CTViT(nn.Module):
         assert mask is None, "frame masks are not used on the CT-CLIP path"
         tokens, indices, _ = self.encode_with_aux(video, _launched=_launched)
         if return_only_codebook_ids:
-            return indices.reshape(b, -1)
+            return indices                      # (b, t, h, w), as the reference unpacks them (ctvit.py:399-400)
         if return_encoded_tokens:
             return tokens
         raise NotImplementedError("only the encoder branch (return_encoded_tokens=True / return_only_codebook_ids=True) "
