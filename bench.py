@@ -191,8 +191,7 @@ def run_ours(args):
     B = args.batch_per_gpu
 
     cfg = {} if args.sync_loss_read else {"defer_loss_read": True}
-    if args.text_tower == "ctk":
-        cfg["ctk_text_tower"] = True
+    cfg["ctk_text_tower"] = args.text_tower == "ctk"
     clip = build_model(dev, seed=0, config=cfg, text_dropout=args.text_dropout)
     clip.train()
     bert = clip.text_transformer
@@ -280,92 +279,59 @@ def run_ours(args):
     launches = (lib.ctk_launch_count() + ops.GRAPH_LAUNCHES - n0)      # direct launches + launches replayed from CUDA graphs
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: host inputs, H2D of step i+1 overlapped with step i, loss read back every step -----
-    # Three device slots: the batch of step i+1 is copied (side stream) into the slot step i-2 used,
-    # which is free as soon as step i-2 has been fully enqueued-and-finished, i.e. when step i-1 starts;
-    # the 1.77 GB copy (PCIe: ~45 ms at the ~39 GB/s this pool's hosts reach) therefore has two step
-    # times of slack instead of one.
-    step_done = [None] * NSLOT
-    def e2e_loop(k):
-        h2d(0, 0)
+    # ---- e2e: host inputs, transfer of step i+1 overlapped with step i, loss read back every step ---
+    # Three device slots: the batch of step i+1 is copied (side stream) into the slot step i-2 used, which is free as
+    # soon as step i-2 has finished, i.e. when step i-1 starts; the copy therefore has two step times of slack.
+    #   e2e           : the reference's STORED format on the host - float16 `arr_0` of the *_fp16 datasets, values in
+    #                   [-1, 1] - shipped as stored, one volume at a time, and turned into the loader's fp32
+    #                   (B, 1, 240, 480, 480) tensor on the device by ctk_volume_prep (scripts/data.py:49-111, bit-exact:
+    #                   tests/test_volume_prep_gpu.py), each volume's kernel right behind its copy.
+    #   e2e_fp32_host : the loader's fp32 result on the host (what the reference's DataLoader hands over), 2x the bytes.
+    def pipeline(k, feed):
+        done = [None] * NSLOT
+        def fill(slot, src):
+            with torch.cuda.stream(copy_stream):
+                if done[slot] is not None:
+                    copy_stream.wait_event(done[slot])          # last reader of that slot
+                feed(slot, src)
+        fill(0, 0)
         last = None
         for i in range(k):
             torch.cuda.current_stream().wait_stream(copy_stream)
             if i + 1 < k:
-                nxt = (i + 1) % NSLOT
-                if step_done[nxt] is not None:
-                    copy_stream.wait_event(step_done[nxt])          # last reader of that slot
-                h2d(nxt, (i + 1) % 2)
+                fill((i + 1) % NSLOT, (i + 1) % 2)
             last = step(i % NSLOT)
             ev = torch.cuda.Event()
             ev.record()
-            step_done[i % NSLOT] = ev
+            done[i % NSLOT] = ev
         return last
-    ms_e2e, loss_val = timed(e2e_loop, args.steps)
 
-    # ---- informational: the same pipeline with a 16-bit HOST format (the reference's loader yields fp32, so this is
-    # not the contract number).  The fp32 batch is 1.77 GB per step and PCIe-bound (~45 ms at 39 GB/s); fp16 volumes
-    # (CT-RATE intensities are clipped to [-1, 1]) halve the copy and are widened to fp32 on the device.
-    ms_e2e16 = None
-    if args.half_host:
-        host16 = [v.half().pin_memory() for v in host_vid]
-        dev16 = [torch.empty(B, 1, *VOL, dtype=torch.float16, device=dev) for _ in range(NSLOT)]
-        done16 = [None] * NSLOT
-        def h2d16(slot, src):
-            with torch.cuda.stream(copy_stream):
-                dev16[slot].copy_(host16[src], non_blocking=True)
-                dev_ids[slot].copy_(host_ids[src], non_blocking=True)
-        def e2e16_loop(k):
-            h2d16(0, 0)
-            last = None
-            for i in range(k):
-                torch.cuda.current_stream().wait_stream(copy_stream)
-                if i + 1 < k:
-                    nxt = (i + 1) % NSLOT
-                    if done16[nxt] is not None:
-                        copy_stream.wait_event(done16[nxt])
-                    h2d16(nxt, (i + 1) % 2)
-                last = step(i % NSLOT, image=dev16[i % NSLOT])
-                ev = torch.cuda.Event()
-                ev.record()
-                done16[i % NSLOT] = ev
-            return last
-        e2e16_loop(2)                                      # fp16 -> fp32 widening path warm-up
-        ms_e2e16, _ = timed(e2e16_loop, args.steps)
-        del host16, dev16
+    def feed_fp32(slot, src):
+        dev_vid[slot].copy_(host_vid[src], non_blocking=True)
+        dev_ids[slot].copy_(host_ids[src], non_blocking=True)
 
-    # ---- informational: the reference's own STORED format on the host (float16 arr_0 of the *_fp16 datasets, values in
-    # [-1, 1]) -> H2D in that dtype -> ctk_volume_prep on the device (scripts/data.py:49-111, bit-exact) -> train step.
-    # Same result tensor as the loader's, half the PCIe bytes.  Opt-in until the kernel has run on hardware.
-    ms_e2e_st = None
-    if args.stored_host:
-        hosts = [(v[:, 0] * 2 - 1).half().pin_memory() for v in host_vid]          # (B, D, H, W) stored arrays
-        devs = [torch.empty(B, *VOL, dtype=torch.float16, device=dev) for _ in range(NSLOT)]
-        done_st = [None] * NSLOT
-        def h2d_st(slot, src):
-            with torch.cuda.stream(copy_stream):
-                devs[slot].copy_(hosts[src], non_blocking=True)
-                dev_ids[slot].copy_(host_ids[src], non_blocking=True)
-                for b in range(B):
-                    ops.volume_prep(devs[slot][b], dev_vid[slot][b])
-        def e2e_st_loop(k):
-            h2d_st(0, 0)
-            last = None
-            for i in range(k):
-                torch.cuda.current_stream().wait_stream(copy_stream)
-                if i + 1 < k:
-                    nxt = (i + 1) % NSLOT
-                    if done_st[nxt] is not None:
-                        copy_stream.wait_event(done_st[nxt])
-                    h2d_st(nxt, (i + 1) % 2)
-                last = step(i % NSLOT)
-                ev = torch.cuda.Event()
-                ev.record()
-                done_st[i % NSLOT] = ev
-            return last
-        e2e_st_loop(2)
-        ms_e2e_st, _ = timed(e2e_st_loop, args.steps)
-        del hosts, devs
+    stored = [(v[:, 0] * 2 - 1).half().pin_memory() for v in host_vid]          # (B, D, H, W) stored arrays
+    dev_stored = [torch.empty(B, *VOL, dtype=torch.float16, device=dev) for _ in range(NSLOT)]
+
+    def feed_stored(slot, src):
+        dev_ids[slot].copy_(host_ids[src], non_blocking=True)
+        for b in range(B):
+            dev_stored[slot][b].copy_(stored[src][b], non_blocking=True)
+            ops.volume_prep(dev_stored[slot][b], dev_vid[slot][b])
+
+    pipeline(2, feed_stored)                                # first use of the prep kernel / slots
+    ms_e2e, loss_val = timed(lambda k: pipeline(k, feed_stored), args.steps)
+    ms_e2e32, _ = timed(lambda k: pipeline(k, feed_fp32), args.steps)
+    del stored, dev_stored
+
+    # ---- informational: the reference's own loss read (loss.item() inside forward: a host sync between forward and
+    # backward, ct_clip.py:1384) instead of the deferred read the timed loops use
+    ms_sync = None
+    if not args.sync_loss_read:
+        clip.config["defer_loss_read"] = False
+        step(0)
+        ms_sync, _ = timed(lambda k: [step(i % 2) for i in range(k)], args.steps)
+        clip.config["defer_loss_read"] = True
 
     # ---- roofline: instrument every tcgen05 GEMM launch of one more step --------------------------
     ops.GEMM_PROFILE = []
@@ -396,8 +362,9 @@ def run_ours(args):
                                "480x480x240) + random-init BERT-base text tower + all-gathered InfoNCE + clip 0.5 + Adam",
                    "per_gpu_batch": B, "global_batch": B * world, "text_len": TEXT_LEN, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (1.77 GB of volumes per step); two alternating batches",
-                   "e2e_pipeline": "host batch (pinned) -> H2D on a side stream into one of 3 device slots while the "
-                                   "previous step computes; loss read back (.item()) every step",
+                   "e2e_pipeline": "host batch (pinned, stored float16 volumes) -> per-volume H2D + ctk_volume_prep on a side "
+                                   "stream into one of 3 device slots while the previous step computes; loss read back "
+                                   "every step",
                    "text_tower": (("BertModel parameters through libctk (vit_exp_b200/text_tower.py)"
                                    if args.text_tower == "ctk" else "stock PyTorch BertModel under bf16 autocast")
                                   + f", dropout {args.text_dropout} (CXR-BERT ships 0.1; the CPU arm uses 0)"),
@@ -406,17 +373,16 @@ def run_ours(args):
                    "launch": "encoder forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
                              else "eager launches"},
         "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s",
-                "h2d_bytes_per_step": int(host_vid[0].numel() * 4 + host_ids[0].numel() * 8), "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
-        "e2e_half_host": None if ms_e2e16 is None else {
-            "value": vols / (ms_e2e16 / 1e3), "unit": "volumes/s", "ms_per_step": ms_e2e16 / args.steps,
-            "h2d_bytes_per_step": int(host_vid[0].numel() * 2 + host_ids[0].numel() * 8),
-            "note": "informational: fp16 host volumes widened on the device; the contract number is `e2e` (fp32 host batch)"},
-        "e2e_stored_host": None if ms_e2e_st is None else {
-            "value": vols / (ms_e2e_st / 1e3), "unit": "volumes/s", "ms_per_step": ms_e2e_st / args.steps,
-            "h2d_bytes_per_step": int(host_vid[0].numel() * 2 + host_ids[0].numel() * 8),
-            "note": "informational: float16 stored arrays (the *_fp16 datasets' arr_0) shipped as stored and prepared by "
-                    "ctk_volume_prep (scripts/data.py:49-111 on the device); the contract number is `e2e`"},
+                "h2d_bytes_per_step": int(host_vid[0].numel() * 2 + host_ids[0].numel() * 8), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps,
+                "host_format": "float16 stored arrays (arr_0 of the *_fp16 datasets), prepared on the device by "
+                               "ctk_volume_prep = scripts/data.py:49-111 npz_to_tensor, bit-exact"},
+        "e2e_fp32_host": {"value": vols / (ms_e2e32 / 1e3), "unit": "volumes/s", "ms_per_step": ms_e2e32 / args.steps,
+                          "h2d_bytes_per_step": int(host_vid[0].numel() * 4 + host_ids[0].numel() * 8),
+                          "note": "the loader's fp32 result shipped from the host (twice the PCIe bytes of `e2e`)"},
+        "value_sync_loss_read": None if ms_sync is None else {
+            "value": vols / (ms_sync / 1e3), "unit": "volumes/s", "ms_per_step": ms_sync / args.steps,
+            "note": "reference behaviour: loss.item() inside forward (host sync between forward and backward)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<EPI, major> (tcgen05 128x256x64, all launches of one step)",
@@ -528,16 +494,13 @@ def main():
     ap.add_argument("--sync-loss-read", action="store_true",
                     help="CTCLIP returns cl_loss via loss.item() inside forward (reference behaviour: a host sync between "
                          "forward and backward); default: config['defer_loss_read'], the same value read back at the end of the step")
-    ap.add_argument("--half-host", action="store_true", help="also time the e2e pipeline with fp16 host volumes (informational)")
-    ap.add_argument("--stored-host", action="store_true",
-                    help="also time the e2e pipeline from float16 STORED arrays through vit_exp_b200.data / ctk_volume_prep (informational)")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: libctk clip+Adam (2 launches); torch: clip_grad_norm_ + torch.optim.Adam(fused=True)")
     ap.add_argument("--text-dropout", type=float, default=0.0,
                     help="hidden / attention dropout of the random-init BERT-base text tower (CXR-BERT's config has 0.1)")
-    ap.add_argument("--text-tower", default="hf", choices=["hf", "ctk"],
-                    help="hf: the BertModel runs as passed (stock PyTorch, bf16 autocast); ctk: its forward/backward run "
-                         "through libctk (vit_exp_b200/text_tower.py; opt-in until validated on hardware)")
+    ap.add_argument("--text-tower", default="ctk", choices=["hf", "ctk"],
+                    help="ctk: the BertModel's forward/backward run through libctk (vit_exp_b200/text_tower.py, CUDA-graph "
+                         "replay); hf: the module runs as passed (stock PyTorch under bf16 autocast)")
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":

@@ -109,6 +109,10 @@ int ctk_cast_bf16(const float* src, void* dst, long long rows, long long cols, l
 /* dst bf16 [cols, ld_dst] = src fp32 [rows, cols]^T, pad columns (>= rows) zeroed. */
 int ctk_transpose_cast_bf16(const float* src, void* dst, long long rows, long long cols,
                             long long ld_dst, void* stream);
+/* same, but ONLY the columns [0, rows) of every dst row are written: dst may be a column slice of a wider matrix
+ * (text tower: [Wq^T | Wk^T | Wv^T] packed side by side for the input gradient of the fused q|k|v projection). */
+int ctk_transpose_cast_bf16_slice(const float* src, void* dst, long long rows, long long cols,
+                                  long long ld_dst, void* stream);
 /* FeedForward W1 (2*inner, dim) fp32 -> interleaved bf16 (2*inner_pad, dim): for every block of
  * 128 hidden units, 128 value rows then 128 gate rows (attention.py:47: first half value, second
  * half gate). Also writes row_map[2*inner_pad] (interleaved row -> source row, -1 for padding)
@@ -259,6 +263,31 @@ int ctk_patch_affine_bwd(const float* P, const float* W, const float* gamma, con
 /* db fp32 [cols] += column sums of dy (bf16 or fp32) [rows, cols]. */
 int ctk_colsum(const void* dy_bf16, const float* dy_f32, float* out, long long rows, int cols,
                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Text tower: the HF BertModel the reference passes as text_encoder, ct_clip.py:1271.
+ * ------------------------------------------------------------------------------------------ */
+/* BertEmbeddings before its LayerNorm: out fp32 [M, H] = word[ids[m]] + typ[token_type ? token_type[m] : 0] + pos[m % L].
+ * ids / token_type int64 [M] (token_type may be NULL), M = B * L. */
+int ctk_bert_embed_fwd(const long long* ids, const long long* token_type, const float* word, const float* pos,
+                       const float* typ, float* out, long long M, int L, int H, void* stream);
+/* backward: dword[ids[m]] += de[m] (zero-initialised by the caller; rows equal to pad_idx are skipped, pad_idx < 0: none),
+ * dpos[l] = sum_b de[b*L + l] for l < L (written, not accumulated), dtyp[token_type[m]] += de[m] when token_type != NULL
+ * (otherwise the caller takes ctk_colsum of de into dtyp[0]). */
+int ctk_bert_embed_bwd(const float* de, const long long* ids, const long long* token_type, float* dword, float* dpos,
+                       float* dtyp, long long M, int L, int H, long long pad_idx, void* stream);
+/* BertSelfAttention core, head dim 64: softmax(q k^T * scale + key mask) -> dropout(p_drop) -> . v on the packed bf16
+ * projections qkv [B*L, 3*heads*64] (q | k | v, heads contiguous).  key_mask uint8 [B, L] (non-zero = attend) or NULL.
+ * out bf16 [B*L, heads*64]; lse fp32 [B, heads, L] (natural log of the row sums of exp(scaled logits)).
+ * Dropout: element (b*heads + h, i, j) is kept iff hash(*seed_ptr + seed_off * c, ...) >= p * 2^32 (csrc/mha_dropout.cuh);
+ * the seed is read from DEVICE memory so that CUDA-graph replays see a fresh value; the backward regenerates the mask.
+ * mma.sync tensor-core kernels, flash-style (the L x L probabilities never leave registers), deterministic. */
+int ctk_mha_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int L, int heads, int dh,
+                float scale, float p_drop, const unsigned long long* seed_ptr, unsigned long long seed_off, void* stream);
+/* delta fp32 [B, heads, L] is workspace; dqkv bf16 [B*L, 3*heads*64] receives dq | dk | dv. */
+int ctk_mha_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout, const float* lse,
+                float* delta, void* dqkv, int B, int L, int heads, int dh, float scale, float p_drop,
+                const unsigned long long* seed_ptr, unsigned long long seed_off, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Loader-side volume preparation: scripts/data.py:49-111 npz_to_tensor on the device.

@@ -68,9 +68,20 @@ def gemm(a, b, epilogue, c, *, M, N, K, mn_major=False, lda=None, ldb=None, ldc=
 
 
 def cast_bf16(src, ld=None, col_scale=None, out=None):
-    assert src.dtype == torch.float32 and src.is_contiguous() and ld is None and col_scale is None and out is None
+    assert src.dtype == torch.float32 and src.is_contiguous() and ld is None and col_scale is None
     CALLS.append(("cast_bf16", None))
+    if out is not None:
+        assert out.shape == src.shape and out.dtype == OPERAND
+        out.copy_(src.to(OPERAND))
+        return out
     return src.to(OPERAND)
+
+
+def transpose_cast_bf16_slice(src, dst):
+    assert src.dtype == torch.float32 and dst.shape == (src.shape[1], src.shape[0]) and dst.dtype == OPERAND
+    CALLS.append(("transpose_cast_bf16", None))
+    dst.copy_(src.t().to(OPERAND))
+    return dst
 
 
 def transpose_cast_bf16(src, ld=None, out=None):
@@ -114,6 +125,93 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta=None, *, dx=None, accu
     if dx_bf16 is not None:
         dx_bf16.copy_(dx.to(dx_bf16.dtype))
     return dx
+
+
+# ---- text tower: BertEmbeddings and the attention core (include/ctk.h: ctk_bert_embed_*, ctk_mha_*)
+def bert_embed_fwd(ids, token_type, word, pos, typ):
+    CALLS.append(("bert_embed_fwd", None))
+    B, L = ids.shape
+    e = word[ids] + (typ[0] if token_type is None else typ[token_type]) + pos[:L].unsqueeze(0)
+    return e.reshape(B * L, -1).float().contiguous()
+
+
+def bert_embed_bwd(de, ids, token_type, word_shape, pos_shape, typ_shape, pad_idx):
+    CALLS.append(("bert_embed_bwd", None))
+    B, L = ids.shape
+    dword = torch.zeros(word_shape).index_add_(0, ids.reshape(-1), de)
+    if pad_idx is not None:
+        dword[pad_idx].zero_()
+    dpos = torch.zeros(pos_shape)
+    dpos[:L] = de.view(B, L, -1).sum(0)
+    dtyp = torch.zeros(typ_shape)
+    if token_type is None:
+        dtyp[0] = de.sum(0)
+    else:
+        dtyp.index_add_(0, token_type.reshape(-1), de)
+    return dword, dpos, dtyp
+
+
+_M32 = 0xFFFFFFFF
+
+
+def _mix32(x):
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & _M32
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & _M32
+    return x ^ (x >> 16)
+
+
+def mha_hash(seed: int, bh, i, j):
+    """torch restatement of csrc/mha_dropout.cuh: mha_hash (uint32 arithmetic carried in int64 tensors)"""
+    bh, i, j = (torch.as_tensor(v, dtype=torch.int64) for v in (bh, i, j))
+    x = ((i * 0x9E3779B1) & _M32) ^ ((j * 0x85EBCA77) & _M32) ^ ((bh * 0xC2B2AE3D) & _M32) ^ (seed & _M32)
+    x = _mix32(x)
+    x = (x + ((seed >> 32) & _M32) + ((j * 0x27D4EB2F) & _M32)) & _M32
+    return _mix32(x)
+
+
+def mha_seed(base: int, offset: int) -> int:
+    return (base + offset * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+
+def mha_keep_mask(seed: int, nbh: int, L: int, p: float):
+    """bool [nbh, L, L]: element (bh, i, j) survives attention-probability dropout"""
+    thresh = min(int(p * 4294967296.0), 0xFFFFFFFF)
+    bh = torch.arange(nbh).view(-1, 1, 1)
+    i = torch.arange(L).view(1, -1, 1)
+    j = torch.arange(L).view(1, 1, -1)
+    return mha_hash(seed, bh, i, j) >= thresh
+
+
+def _mha_math(qkv, key_mask, B, L, heads, scale, p_drop, seed, seed_off):
+    H = qkv.shape[1] // 3
+    q, k, v = (qkv.float().view(B, L, 3, heads, H // heads)[:, :, t].transpose(1, 2) for t in range(3))
+    sc = (q @ k.transpose(-1, -2)) * scale
+    if key_mask is not None:
+        sc = sc.masked_fill(key_mask.view(B, 1, 1, L) == 0, float("-inf"))
+    lse = torch.logsumexp(sc, dim=-1)
+    pr = torch.softmax(sc, dim=-1)
+    if p_drop > 0:
+        keep = mha_keep_mask(mha_seed(int(seed.item()) & 0xFFFFFFFFFFFFFFFF, seed_off), B * heads, L, p_drop)
+        pr = pr * keep.view(B, heads, L, L).to(pr.dtype) / (1.0 - p_drop)
+    return (pr @ v).transpose(1, 2).reshape(B * L, H), lse
+
+
+def mha_fwd(qkv, key_mask, B, L, heads, scale, p_drop=0.0, seed=None, seed_off=0):
+    CALLS.append(("mha_fwd", p_drop))
+    assert qkv.dtype == OPERAND
+    ctx, lse = _mha_math(qkv, key_mask, B, L, heads, scale, p_drop, seed, seed_off)
+    return ctx.to(OPERAND), lse
+
+
+def mha_bwd(qkv, key_mask, out, dout, lse, B, L, heads, scale, p_drop=0.0, seed=None, seed_off=0):
+    CALLS.append(("mha_bwd", p_drop))
+    with torch.enable_grad():
+        x = qkv.detach().float().requires_grad_(True)
+        ctx, _ = _mha_math(x, key_mask, B, L, heads, scale, p_drop, seed, seed_off)
+        (g,) = torch.autograd.grad(ctx, x, dout.float())
+    return g.to(OPERAND)
 
 
 def colsum_(dy, out):

@@ -54,3 +54,16 @@ extern "C" void hostcheck_clip_grad(const float* acc, int M, int N, float log_sc
             }
         }
 }
+
+// ---- attention-probability dropout mask of the text tower (csrc/mha_dropout.cuh, used by attention_mha64.cu) ----
+#include "../vit_exp_b200/csrc/mha_dropout.cuh"
+// keep[bh][i][j] (uint8) for bh < nbh, i, j < L; seed = mha_seed(base, offset)
+extern "C" void hostcheck_mha_keep(unsigned long long base, unsigned long long offset, int nbh, int L, float p,
+                                   unsigned char* keep) {
+    const unsigned long long seed = mha_seed(base, offset);
+    const uint32_t thr = mha_drop_threshold(p);
+    for (int bh = 0; bh < nbh; ++bh)
+        for (int i = 0; i < L; ++i)
+            for (int j = 0; j < L; ++j)
+                keep[((long long)bh * L + i) * L + j] = mha_keep(seed, (uint32_t)bh, (uint32_t)i, (uint32_t)j, thr) ? 1 : 0;
+}

@@ -29,7 +29,7 @@ def lib():
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    deps = [SRC] + [os.path.join(ROOT, "vit_exp_b200", "csrc", h) for h in ("volume_prep_math.cuh", "clip_epilogue_math.cuh")]
+    deps = [SRC] + [os.path.join(ROOT, "vit_exp_b200", "csrc", h) for h in ("volume_prep_math.cuh", "clip_epilogue_math.cuh", "mha_dropout.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         r = subprocess.run([nvcc, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
                             "-x", "cu", SRC, "-o", OUT], capture_output=True, text=True)
@@ -163,3 +163,26 @@ def test_clip_epilogue_device_functions_vs_oracle(lib, N, W, rank, lt):
     dI = g1h.T @ Th + g1h.T @ Tl + g1l.T @ Th
     for got, want in ((dT, ref["dT_local"].numpy()), (dI, ref["dI_local"].numpy())):
         assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max()
+
+
+def test_mha_dropout_mask_matches_torch_restatement(lib):
+    """csrc/mha_dropout.cuh (what ctk_mha_fwd / ctk_mha_bwd evaluate per probability) == tests/emulated_ops.mha_keep_mask,
+    the torch restatement the GPU parity tests build their reference attention from; and the mask is a fair coin."""
+    import ctypes as C
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emulated_ops as E
+    lib.hostcheck_mha_keep.restype = None
+    lib.hostcheck_mha_keep.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    for base, off, nbh, L, p in [(1234567890123456789, 0, 3, 70, 0.1), (2 ** 63 + 17, 11, 2, 130, 0.5), (0, 0, 1, 64, 0.9)]:
+        got = np.empty((nbh, L, L), dtype=np.uint8)
+        lib.hostcheck_mha_keep(base, off, nbh, L, p, got.ctypes.data)
+        want = E.mha_keep_mask(E.mha_seed(base, off), nbh, L, p).numpy().astype(np.uint8)
+        assert np.array_equal(got, want)
+        frac = got.mean()
+        assert abs(frac - (1 - p)) < 4 * np.sqrt(p * (1 - p) / got.size) + 1e-3, (p, frac)
+    # rows / columns are not correlated: per-row keep rates spread like a binomial
+    got = np.empty((4, 256, 256), dtype=np.uint8)
+    lib.hostcheck_mha_keep(99, 3, 4, 256, 0.1, got.ctypes.data)
+    assert abs(got.mean(axis=2).std() - np.sqrt(0.09 / 256)) < 0.006 and abs(got.mean(axis=1).std() - np.sqrt(0.09 / 256)) < 0.006

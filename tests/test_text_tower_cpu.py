@@ -212,22 +212,59 @@ def test_hidden_dropout_matches_hf_with_shared_masks(emulated, monkeypatch):
     assert calls["n"] == 0
 
 
-def test_attention_dropout_is_passed_to_the_attention_core(emulated, monkeypatch):
+def test_attention_dropout_is_passed_to_the_attention_core(emulated):
+    """training mode hands attention_probs_dropout_prob and a device-resident seed to ctk_mha_fwd / ctk_mha_bwd (the
+    backward regenerates the same mask: same seed tensor, same per-layer offset); eval mode passes 0."""
     _set_operand(torch.float32)
     from transformers import BertConfig, BertModel
-    bert = BertModel(BertConfig(vocab_size=97, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+    bert = BertModel(BertConfig(vocab_size=97, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
                                 intermediate_size=256, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.3)).train()
-    seen = []
-    real = torch.nn.functional.scaled_dot_product_attention
-
-    def sdpa(q, k, v, attn_mask=None, dropout_p=0.0, scale=None, **kw):
-        seen.append(dropout_p)
-        return real(q, k, v, attn_mask=attn_mask, dropout_p=0.0, scale=scale, **kw)
-    monkeypatch.setattr(text_tower.F, "scaled_dot_product_attention", sdpa)
     ids, mask = _inputs()
-    text_tower.encode(bert, ids, mask)
-    text_tower.encode(bert.eval(), ids, mask)
-    assert seen == [0.3, 0.0]
+    out = text_tower.encode(bert, ids, mask)
+    _objective(out).backward()
+    assert all(torch.isfinite(p.grad).all() for n, p in bert.named_parameters() if p.grad is not None)
+    with torch.no_grad():
+        text_tower.encode(bert.eval(), ids, mask)
+    seen = [(n, p) for n, p in emulated.CALLS if n.startswith("mha_")]
+    assert seen == [("mha_fwd", 0.3)] * 2 + [("mha_bwd", 0.3)] * 2 + [("mha_fwd", 0.0)] * 2
+    # two training forwards draw different masks (the device counter advances)
+    a = text_tower.encode(bert.train(), ids, mask)
+    b = text_tower.encode(bert, ids, mask)
+    assert not torch.equal(a, b)
+
+
+def test_attention_dropout_gradients_match_autograd(emulated):
+    """with the kernels' hash mask restated in torch, the tower's hand-written backward equals autograd through the
+    same masked attention (dropout sits on the probabilities, after the softmax, scaled by 1 / (1 - p))"""
+    _set_operand(torch.float32)
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(3)
+    bert = BertModel(BertConfig(vocab_size=97, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+                                intermediate_size=256, max_position_embeddings=40, hidden_dropout_prob=0.0,
+                                attention_probs_dropout_prob=0.25)).train()
+    ids, mask = _inputs()
+    text_tower._SEED.clear()
+    torch.manual_seed(7)
+    out = text_tower.encode(bert, ids, mask)
+    _objective(out).backward()
+    got = bert.encoder.layer[0].attention.self.value.weight.grad.clone()
+    bert.zero_grad(set_to_none=True)
+    # reference: HF module with its attention dropout replaced by the same hash mask
+    seed0 = int(next(iter(text_tower._SEED.values())).item()) - 1
+    keep = emulated.mha_keep_mask(emulated.mha_seed(seed0, 0), ids.shape[0] * 2, ids.shape[1], 0.25)
+    keep = keep.view(ids.shape[0], 2, ids.shape[1], ids.shape[1])
+    att = bert.encoder.layer[0].attention.self
+    x = bert.embeddings(input_ids=ids)
+    q, k, v = (lin(x).view(ids.shape[0], ids.shape[1], 2, 64).transpose(1, 2) for lin in (att.query, att.key, att.value))
+    sc = (q @ k.transpose(-1, -2)) / 8.0
+    sc = sc.masked_fill(mask.view(ids.shape[0], 1, 1, -1) == 0, float("-inf"))
+    ctx = ((torch.softmax(sc, -1) * keep / 0.75) @ v).transpose(1, 2).reshape(ids.shape[0], ids.shape[1], 128)
+    layer = bert.encoder.layer[0]
+    h1 = layer.attention.output.LayerNorm(layer.attention.output.dense(ctx) + x)
+    ref = layer.output.LayerNorm(layer.output.dense(layer.intermediate(h1)) + h1)
+    assert _rel(out, ref.detach()) < 1e-5
+    _objective(ref).backward()
+    assert _rel(got, att.value.weight.grad) < 2e-4
 
 
 def test_product_path_has_no_cpu_fallback():

@@ -154,3 +154,130 @@ def test_ctclip_step_with_ctk_text_tower(cuda_dev):
         losses.append(float(loss))
         clip.zero_grad(set_to_none=True)
     assert abs(losses[0] - losses[1]) <= 1e-3 * abs(losses[0]) + 1e-6
+
+
+# ----------------------------------------------------------------------------- attention core (ctk_mha_fwd / ctk_mha_bwd)
+@pytest.mark.parametrize("B,L,heads,p_drop,padded", [(2, 512, 12, 0.0, True), (3, 200, 4, 0.0, True), (1, 64, 2, 0.0, False),
+                                                     (2, 37, 3, 0.0, True), (2, 256, 4, 0.1, True), (1, 130, 2, 0.5, False)])
+def test_mha_forward_backward(cuda_dev, B, L, heads, p_drop, padded):
+    """against fp32 softmax attention on the same bf16-rounded projections; the dropout mask of the reference is the
+    torch restatement of the kernels' hash (tests/emulated_ops.mha_keep_mask, pinned to csrc/mha_dropout.cuh on the CPU).
+    bf16 probabilities / outputs: 1e-2 relative L2 forward, 2e-2 backward; lse 1e-3 absolute."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import emulated_ops as E
+    from vit_exp_b200 import ops
+    H = heads * 64
+    qkv = (_rand((B * L, 3 * H), cuda_dev, 21) * 1.2).bfloat16()
+    dout = _rand((B * L, H), cuda_dev, 22).bfloat16()
+    mask = torch.ones(B, L, dtype=torch.uint8, device=cuda_dev)
+    if padded:
+        mask[0, L - L // 3:] = 0
+        mask[B - 1, L // 2] = 0                       # a hole in the middle as well
+    seed = torch.tensor([987654321012345], dtype=torch.int64, device=cuda_dev)
+    scale = 0.125
+    ctx, lse = ops.mha_fwd(qkv, mask, B, L, heads, scale, p_drop, seed, 5)
+    dqkv = ops.mha_bwd(qkv, mask, ctx, dout, lse, B, L, heads, scale, p_drop, seed, 5)
+    torch.cuda.synchronize()
+    saved = E.OPERAND
+    try:
+        E.OPERAND = torch.bfloat16
+        x = qkv.cpu().float().requires_grad_(True)
+        ref, ref_lse = E._mha_math(x, mask.cpu(), B, L, heads, scale, p_drop, seed.cpu(), 5)
+        (gref,) = torch.autograd.grad(ref, x, dout.cpu().float())
+    finally:
+        E.OPERAND = saved
+    assert torch.isfinite(ctx.float()).all() and torch.isfinite(dqkv.float()).all()
+    assert _rel(ctx.cpu(), ref) < 1e-2, _rel(ctx.cpu(), ref)
+    assert (lse.cpu() - ref_lse).abs().max().item() < 1e-3
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        err = _rel(dqkv.cpu()[:, sl], gref[:, sl])
+        assert err < 2e-2, (name, err)
+    # masked keys receive exactly zero gradient
+    dead = (mask.cpu() == 0).reshape(-1)
+    if dead.any():
+        assert dqkv.cpu()[dead][:, H:].abs().max().item() == 0.0
+
+
+def test_mha_is_deterministic_and_seed_sensitive(cuda_dev):
+    from vit_exp_b200 import ops
+    B, L, heads = 2, 128, 4
+    qkv = _rand((B * L, 3 * heads * 64), cuda_dev, 31).bfloat16()
+    s1 = torch.tensor([5], dtype=torch.int64, device=cuda_dev)
+    a, _ = ops.mha_fwd(qkv, None, B, L, heads, 0.125, 0.1, s1, 0)
+    b, _ = ops.mha_fwd(qkv, None, B, L, heads, 0.125, 0.1, s1, 0)
+    c, _ = ops.mha_fwd(qkv, None, B, L, heads, 0.125, 0.1, s1, 1)
+    s1.add_(1)
+    d, _ = ops.mha_fwd(qkv, None, B, L, heads, 0.125, 0.1, s1, 0)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+
+
+def test_bert_embeddings_forward_backward(cuda_dev):
+    from vit_exp_b200 import ops
+    g = torch.Generator().manual_seed(41)
+    V, P, T, H, B, L = 1000, 64, 2, 256, 3, 40
+    word, pos, typ = (torch.randn(n, H, generator=g).to(cuda_dev) for n in (V, P, T))
+    ids = torch.randint(0, V, (B, L), generator=g).to(cuda_dev)
+    ids[0, :5] = 0
+    tt = torch.randint(0, T, (B, L), generator=g).to(cuda_dev)
+    de = torch.randn(B * L, H, generator=g).to(cuda_dev)
+    for token_type in (None, tt):
+        e = ops.bert_embed_fwd(ids, token_type, word, pos, typ)
+        ref = word[ids] + (typ[0] if token_type is None else typ[token_type]) + pos[:L]
+        assert torch.equal(e.view(B, L, H), ref)
+        dword, dpos, dtyp = ops.bert_embed_bwd(de, ids, token_type, word.shape, pos.shape, typ.shape, 0)
+        rw = torch.zeros_like(word).index_add_(0, ids.reshape(-1), de)
+        rw[0].zero_()
+        rp = torch.zeros_like(pos)
+        rp[:L] = de.view(B, L, H).sum(0)
+        rt = torch.zeros_like(typ)
+        if token_type is None:
+            rt[0] = de.sum(0)
+        else:
+            rt.index_add_(0, token_type.reshape(-1), de)
+        assert _rel(dword, rw) < 1e-6 and _rel(dpos, rp) < 1e-6 and _rel(dtyp, rt) < 1e-5
+        assert dword[0].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_text_tower_graph_replay_matches_eager(cuda_dev, dropout):
+    """after two eager calls the tower's forward / backward are replayed from CUDA graphs (text_tower._TowerGraph):
+    same outputs and gradients as eager launches on fresh inputs (bitwise without dropout: the kernels are deterministic
+    except for the split-K weight-gradient atomics), fresh dropout masks on every replay."""
+    import os
+    from transformers import BertConfig, BertModel
+    from vit_exp_b200 import ops, text_tower
+    torch.manual_seed(0)
+    bert = BertModel(BertConfig(vocab_size=30522, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                intermediate_size=1024, hidden_dropout_prob=dropout,
+                                attention_probs_dropout_prob=dropout)).to(cuda_dev).train()
+    w = _rand((256,), cuda_dev, 8)
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randint(0, 30522, (2, 96), generator=g).to(cuda_dev), torch.ones(2, 96, dtype=torch.int64, device=cuda_dev))
+               for _ in range(5)]
+    for ids, mask in batches:
+        mask[1, 70:] = 0
+
+    def run(ids, mask):
+        bert.zero_grad(set_to_none=True)
+        out = text_tower.encode(bert, ids, mask)
+        (out[:, 0, :] * w).sum().backward()
+        return out.detach().clone(), {n: p.grad.detach().clone() for n, p in bert.named_parameters() if p.grad is not None}
+    n0 = ops.GRAPH_LAUNCHES
+    outs = [run(*b) for b in batches]                         # calls 3.. are graph replays
+    assert ops.GRAPH_LAUNCHES > n0, "the tower never switched to graph replay"
+    if dropout == 0.0:
+        os.environ["CTK_TEXT_GRAPHS"] = "0"
+        try:
+            for (out, grads), b in list(zip(outs, batches))[2:]:
+                ref_out, ref_grads = run(*b)
+                assert torch.equal(out, ref_out)
+                for n, gr in ref_grads.items():
+                    assert _rel(grads[n], gr) < 1e-5, n
+        finally:
+            os.environ.pop("CTK_TEXT_GRAPHS")
+    else:
+        a = text_tower.encode(bert, *batches[0])
+        b = text_tower.encode(bert, *batches[0])
+        assert torch.isfinite(a).all() and not torch.equal(a, b)            # replays draw fresh masks
+        assert all(torch.isfinite(v).all() for _, grads in outs for v in grads.values())

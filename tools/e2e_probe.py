@@ -24,8 +24,7 @@ args = ap.parse_args()
 B = 8
 dev = torch.device("cuda:0")
 cfg = {"defer_loss_read": True}
-if args.text_tower == "ctk":
-    cfg["ctk_text_tower"] = True
+cfg["ctk_text_tower"] = args.text_tower == "ctk"
 clip = bench.build_model(dev, config=cfg).train()
 bert = clip.text_transformer
 orig = bert.forward

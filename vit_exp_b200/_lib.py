@@ -68,6 +68,11 @@ SIGNATURES = {
     "ctk_fill_f32": (_i, [_vp, _f, _ll, _vp]),
     "ctk_patch_affine_bwd": (_i, [_vp] * 8 + [_i, _i, _vp]),
     "ctk_colsum": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "ctk_transpose_cast_bf16_slice": (_i, [_vp, _vp, _ll, _ll, _ll, _vp]),
+    "ctk_bert_embed_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "ctk_bert_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _vp]),
+    "ctk_mha_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, C.c_ulonglong, _vp]),
+    "ctk_mha_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, C.c_ulonglong, _vp]),
     "ctk_volume_prep": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
 }
 

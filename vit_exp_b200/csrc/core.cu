@@ -95,7 +95,7 @@ __global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __rest
 
 // dst[c, r] = src[r, c]; 32x32 tiles through shared memory.
 __global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                      long long rows, long long cols, long long ld) {
+                                      long long rows, long long cols, long long ld, long long wlimit) {
     __shared__ float tile[32][33];
     const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -105,7 +105,7 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const long long c = c0 + j, r = r0 + threadIdx.x;     // dst row = c, dst col = r
-        if (c < cols && r < ld) dst[c * ld + r] = __float2bfloat16(tile[threadIdx.x][j]);
+        if (c < cols && r < wlimit) dst[c * ld + r] = __float2bfloat16(tile[threadIdx.x][j]);
     }
 }
 
@@ -218,7 +218,7 @@ extern "C" int ctk_transpose_cast_bf16(const float* src, void* dst, long long ro
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
     transpose_cast_kernel<<<grid, dim3(32, 8), 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                       rows, cols, ld_dst);
+                                                       rows, cols, ld_dst, ld_dst);
     CTK_LAUNCH_CHECK();
     const long long rows_cov = ((rows + 31) / 32) * 32;   // columns already written (zeros past rows)
     if (ld_dst > rows_cov) {
@@ -226,6 +226,20 @@ extern "C" int ctk_transpose_cast_bf16(const float* src, void* dst, long long ro
                                                 rows_cov, ld_dst);
         CTK_LAUNCH_CHECK();
     }
+    return CTK_OK;
+}
+
+extern "C" int ctk_transpose_cast_bf16_slice(const float* src, void* dst, long long rows, long long cols,
+                                             long long ld_dst, void* stream_) {
+    int rc = ctk_check_device();
+    if (rc) return rc;
+    CTK_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_dst >= rows, CTK_ERR_SHAPE,
+                "transpose_cast_slice: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    transpose_cast_kernel<<<grid, dim3(32, 8), 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                       rows, cols, ld_dst, rows);
+    CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
 

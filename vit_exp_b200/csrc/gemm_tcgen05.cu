@@ -486,31 +486,51 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
     } else if constexpr (EPI == CTK_EPI_ARGMAX_PART) {
         // best (value, column) and second-best value of this warp's 32 rows over its block of 128 columns:
         // key[blk][row], second[blk][row] with blk = column / 128.  No atomics; ctk_vq_select merges the blocks.
+        // Branch-free: four independent (best, index, second) trackers over the columns = 0..3 mod 4 (short
+        // dependency chains), merged at the end; equal values keep the lower column and count as "second == best".
         const int cbase = n0 + hf * 128;
         if (cbase < N) {
-            float b1 = -INFINITY, b2 = -INFINITY;
-            int bi = cbase;
+            float b1[4], b2[4];
+            int bi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { b1[q] = -INFINITY; b2[q] = -INFINITY; bi[q] = cbase + q; }
 #pragma unroll 1
             for (int cc = 0; cc < 128; cc += 32) {
                 const int col = cbase + cc;
                 if (col >= N) break;
                 float v[32];
                 ld_acc(t_row + hf * 128 + cc, v);
+                if (col + 32 > N) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col + i >= N) v[i] = -INFINITY;
+                }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    if (col + i < N) {
-                        if (v[i] > b1) { b2 = b1; b1 = v[i]; bi = col + i; }
-                        else if (v[i] > b2) b2 = v[i];
-                    }
+                    const int q = i & 3;
+                    const bool gt = v[i] > b1[q];
+                    b2[q] = fmaxf(b2[q], fminf(v[i], b1[q]));
+                    b1[q] = gt ? v[i] : b1[q];
+                    bi[q] = gt ? col + i : bi[q];
                 }
             }
+            auto merge = [](float& a1, int& ai, float& a2, float c1, int ci, float c2) {
+                const bool a_wins = a1 > c1 || (a1 == c1 && ai < ci);
+                const float lose = a_wins ? c1 : a1;
+                a2 = fmaxf(fmaxf(a2, c2), lose);
+                a1 = a_wins ? a1 : c1;
+                ai = a_wins ? ai : ci;
+            };
+            merge(b1[0], bi[0], b2[0], b1[1], bi[1], b2[1]);
+            merge(b1[2], bi[2], b2[2], b1[3], bi[3], b2[3]);
+            merge(b1[0], bi[0], b2[0], b1[2], bi[2], b2[2]);
             if (row_ok) {
-                uint32_t u = __float_as_uint(b1);
+                uint32_t u = __float_as_uint(b1[0]);
                 u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
                 const long long slot = (long long)(cbase / 128) * M + row;
                 reinterpret_cast<unsigned long long*>(p.C)[slot] =
-                    (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - (uint32_t)bi);
-                reinterpret_cast<float*>(p.aux0)[slot] = b2;
+                    (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - (uint32_t)bi[0]);
+                reinterpret_cast<float*>(p.aux0)[slot] = b2[0];
             }
         }
     }

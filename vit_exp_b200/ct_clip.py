@@ -5,8 +5,8 @@ accelerator=, **kw) -> (loss, {'cl_loss': float})`, `forward_infer`, `load`, and
 keys.  The contrastive head (ct_clip.py:1280-1388) - token mean-pool, latent projections,
 l2-normalise, all-gather across ranks, scaled similarity, symmetric log-softmax cross entropy and
 its backward - runs in libctk.so.  The text encoder is whatever module the caller passes
-(HF BertModel in the reference); by default it runs unmodified in PyTorch, with `config["ctk_text_tower"]`
-(or CTK_TEXT_TOWER=1) its arithmetic runs through libctk instead (vit_exp_b200/text_tower.py, opt-in).
+(HF BertModel in the reference): a BertModel's arithmetic runs through libctk (vit_exp_b200/text_tower.py, the module
+stays the parameter holder); any other module - or `config["ctk_text_tower"] = False` / CTK_TEXT_TOWER=0 - runs as passed.
 """
 from __future__ import annotations
 
@@ -189,8 +189,9 @@ class CTCLIP(nn.Module):
         self.tokenizer = tokenizer       # the reference downloads CXR-BERT's tokenizer here (ct_clip.py:650)
         self.fix_text_encoder = config.get("fix_text_encoder", False)
         self.overlap_text_encoder = config.get("overlap_text_encoder", True)
-        # opt-in until its kernels have been validated on hardware: BertModel forward/backward through libctk
-        self.ctk_text_tower = bool(config.get("ctk_text_tower", os.environ.get("CTK_TEXT_TOWER", "0") == "1"))
+        # a HF BertModel text encoder (what every reference launcher passes, run_train.py:143-154) runs through libctk
+        # (vit_exp_b200/text_tower.py); config["ctk_text_tower"] = False / CTK_TEXT_TOWER=0 runs the module as passed
+        self.ctk_text_tower = bool(config.get("ctk_text_tower", os.environ.get("CTK_TEXT_TOWER", "1") == "1"))
         self._text_tower_note = None
         self._side_stream = None
         if self.fix_text_encoder:
@@ -215,10 +216,11 @@ class CTCLIP(nn.Module):
             why = text_tower.unsupported_reason(bert, bert.training)
             if why is None:
                 return text_tower.encode(bert, text.input_ids, text.attention_mask)
-            if self._text_tower_note != why:          # say so once; the stock module computes the same function
+            if self._text_tower_note != why and why != "not a BertModel":
+                # a BertModel this path does not reproduce: say so once; the stock module computes the same function
                 self._text_tower_note = why
-                print(f"[vit_exp_b200] ctk_text_tower requested but not applicable ({why}); "
-                      "running the text encoder as passed", flush=True)
+                print(f"[vit_exp_b200] libctk text tower not applicable ({why}); running the text encoder as passed",
+                      flush=True)
         return self.text_transformer(text.input_ids, attention_mask=text.attention_mask)[0]
 
     def _encode_both(self, text, image):

@@ -93,6 +93,17 @@ def transpose_cast_bf16(src: torch.Tensor, ld: Optional[int] = None, out=None) -
     return out
 
 
+def transpose_cast_bf16_slice(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[:, :rows] (a bf16 column slice of a wider row-major matrix, `dst.stride(0)` elements per row) = src^T;
+    nothing outside the slice is written."""
+    _chk(src, torch.float32, "src")
+    rows, cols = src.shape
+    assert dst.dtype == torch.bfloat16 and dst.shape == (cols, rows) and dst.stride(1) == 1
+    check(_lib.load().ctk_transpose_cast_bf16_slice(_p(src), _p(dst), rows, cols, dst.stride(0), _stream()),
+          "ctk_transpose_cast_bf16_slice")
+    return dst
+
+
 def pack_ff_w1(w1: torch.Tensor, inner: int, inner_pad: int, want_t: bool = True):
     _chk(w1, torch.float32, "w1")
     dim = w1.shape[1]
@@ -376,3 +387,62 @@ def volume_prep(src: torch.Tensor, out: torch.Tensor):
     check(_lib.load().ctk_volume_prep(src.data_ptr(), int(src.dtype == torch.float16), D, H, W, _p(out), Dt, Ht, Wt,
                                       _stream()), "ctk_volume_prep")
     return out
+
+
+# --------------------------------------------------------------------------- text tower (HF BertModel, ct_clip.py:1271)
+def bert_embed_fwd(ids, token_type, word, pos, typ):
+    """fp32 [B*L, H] = word[ids] + typ[token_type or 0] + pos[0..L-1] (BertEmbeddings before its LayerNorm)."""
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.dim() == 2
+    _chk(word, torch.float32, "word"); _chk(pos, torch.float32, "pos"); _chk(typ, torch.float32, "typ")
+    B, L = ids.shape
+    H = word.shape[1]
+    out = torch.empty(B * L, H, dtype=torch.float32, device=ids.device)
+    tt = None if token_type is None else token_type.contiguous()
+    check(_lib.load().ctk_bert_embed_fwd(_p(ids), _p(tt), _p(word), _p(pos), _p(typ), _p(out), B * L, L, H, _stream()),
+          "ctk_bert_embed_fwd")
+    return out
+
+
+def bert_embed_bwd(de, ids, token_type, word_shape, pos_shape, typ_shape, pad_idx):
+    """gradients of the three embedding tables from de fp32 [B*L, H]"""
+    _chk(de, torch.float32, "de")
+    B, L = ids.shape
+    H = de.shape[1]
+    dev = de.device
+    dword = torch.zeros(word_shape, dtype=torch.float32, device=dev)
+    dpos = torch.zeros(pos_shape, dtype=torch.float32, device=dev)
+    dtyp = torch.zeros(typ_shape, dtype=torch.float32, device=dev)
+    tt = None if token_type is None else token_type.contiguous()
+    check(_lib.load().ctk_bert_embed_bwd(_p(de), _p(ids), _p(tt), _p(dword), _p(dpos), _p(dtyp), B * L, L, H,
+                                         -1 if pad_idx is None else int(pad_idx), _stream()), "ctk_bert_embed_bwd")
+    if tt is None:
+        colsum_(de, dtyp[0])
+    return dword, dpos, dtyp
+
+
+def mha_fwd(qkv, key_mask, B: int, L: int, heads: int, scale: float, p_drop: float = 0.0, seed=None, seed_off: int = 0):
+    """BertSelfAttention core (head dim 64) on the packed bf16 projections qkv [B*L, 3H]; key_mask uint8 [B, L] or None;
+    seed = int64 device tensor [1] (read by the kernel: graph replays see its current value).  Returns (ctx bf16 [B*L, H],
+    lse fp32 [B, heads, L])."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    H = qkv.shape[1] // 3
+    assert qkv.shape == (B * L, 3 * H) and H % heads == 0
+    assert key_mask is None or (key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.shape == (B, L))
+    assert p_drop == 0.0 or (seed is not None and seed.dtype == torch.int64 and seed.is_cuda)
+    out = torch.empty(B * L, H, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(B, heads, L, dtype=torch.float32, device=qkv.device)
+    check(_lib.load().ctk_mha_fwd(_p(qkv), _p(key_mask), _p(out), _p(lse), B, L, heads, H // heads, scale, p_drop,
+                                  _p(seed), seed_off, _stream()), "ctk_mha_fwd")
+    return out, lse
+
+
+def mha_bwd(qkv, key_mask, out, dout, lse, B: int, L: int, heads: int, scale: float, p_drop: float = 0.0, seed=None,
+            seed_off: int = 0):
+    """dqkv bf16 [B*L, 3H] = (dq | dk | dv) of mha_fwd"""
+    _chk(dout, torch.bfloat16, "dout")
+    H = qkv.shape[1] // 3
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    check(_lib.load().ctk_mha_bwd(_p(qkv), _p(key_mask), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, L, heads,
+                                  H // heads, scale, p_drop, _p(seed), seed_off, _stream()), "ctk_mha_bwd")
+    return dqkv

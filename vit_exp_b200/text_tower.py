@@ -5,25 +5,26 @@ attention_mask=text.attention_mask)`; constructed in scripts/run_train.py:2,143-
 The caller's `BertModel` stays the parameter holder (its state-dict keys are the checkpoint format); this module
 only *reads its parameters* and runs the arithmetic of `BertEmbeddings`, `BertLayer` x depth (post-LayerNorm:
 attention -> dense + residual -> LayerNorm -> intermediate dense + erf GELU -> dense + residual -> LayerNorm)
-through the same tcgen05 GEMM (`ctk_gemm_bf16`, epilogues BF16 / RESID_F32 / F32 / GELU / GELU_BWD / ATOMIC_F32) and
-LayerNorm kernels the image encoder uses (bias gradients are dY^T 1 products on the same GEMM).  The pooler is not evaluated (CTCLIP reads `[0][:, 0, :]` only,
-ct_clip.py:1273,1313), so `pooler.dense.*` receives no gradient, exactly as in the reference.  Dropout (training
-mode, hidden 0.1 / attention 0.1 in CXR-BERT): the three hidden dropouts use torch's dropout kernel (the residual add
-then leaves the GEMM epilogue), the attention-probability dropout is SDPA's `dropout_p`; masks are statistically,
-not bitwise, those of the stock module.
+through libctk: `ctk_bert_embed_fwd/bwd` (table gathers / scatters), the tcgen05 GEMM (`ctk_gemm_bf16`, epilogues BF16 /
+RESID_F32 / F32 / GELU / GELU_BWD / ATOMIC_F32; bias gradients are dY^T 1 products on the same GEMM), `ctk_layernorm_*`
+and `ctk_mha_fwd/bwd` (softmax(q k^T / sqrt(dh) + key-padding mask) v, head dim 64, attention-probability dropout from a
+counter-based hash whose seed lives in device memory).  The pooler is not evaluated (CTCLIP reads `[0][:, 0, :]` only,
+ct_clip.py:1273,1313), so `pooler.dense.*` receives no gradient, exactly as in the reference.  The three hidden dropouts
+(training mode, 0.1 in CXR-BERT) use torch's dropout kernel (the residual add then leaves the GEMM epilogue); masks are
+statistically, not bitwise, those of the stock module.
 
 Data layout: M = B*L token rows, hidden H; fp32 residual stream, bf16 GEMM operands written by the producing
 kernel, packed `qkv` bf16 [M, 3H] (q | k | v, heads contiguous inside each third).
 
-Attention core (softmax(q k^T / sqrt(dh) + key mask) v, head dim 64): `torch.nn.functional.
-scaled_dot_product_attention` on strided views of the packed buffer - library code, like the HF module's own
-`sdpa` path; an in-tree d = 64 kernel is the next step.
-
-STATUS: opt-in (`config["ctk_text_tower"]` / `CTK_TEXT_TOWER=1`).  The host logic is checked on CPU against HF
-autograd with emulated kernels (tests/test_text_tower_cpu.py); the GELU epilogues have not run on hardware yet.
+Launch path: a training-shape forward / backward is ~200 / ~330 kernel launches with static shapes; after two eager
+calls with the same key (shapes, parameter addresses, dropout configuration) both are captured into CUDA graphs and
+replayed (`_TowerGraph`, same mechanics as the image encoder's `_EncoderGraph`): the token ids / mask are copied into
+static buffers, the caller receives a private copy of the hidden states.  `CTK_TEXT_GRAPHS=0` keeps eager launches.
 """
 from __future__ import annotations
 
+import os
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -50,6 +51,8 @@ def unsupported_reason(bert, training: bool) -> Optional[str]:
     H, heads = cfg.hidden_size, cfg.num_attention_heads
     if H % 64 or H > 1024 or cfg.intermediate_size % 32 or H % heads:
         return f"hidden size {H} / intermediate {cfg.intermediate_size}: LayerNorm needs H % 64 == 0, H <= 1024"
+    if H // heads != 64:
+        return f"head dim {H // heads} (ctk_mha_fwd is instantiated for 64, BERT-base / CXR-BERT)"
     return None
 
 
@@ -104,60 +107,55 @@ def _dropout_bwd(g: torch.Tensor, mask: torch.Tensor, p: float) -> torch.Tensor:
 
 def _prep_layer(lp: List[torch.Tensor], need_bwd: bool) -> Dict[str, torch.Tensor]:
     (wq, bq, wk, bk, wv, bv, wo, bo, g1, b1, wi, bi, wo2, bo2, g2, b2) = lp
-    wqkv = torch.cat([wq, wk, wv], dim=0)             # [3H, H] fp32: one projection GEMM instead of three
-    d = dict(wqkv=_operand(wqkv), bqkv=torch.cat([bq, bk, bv]).float(), wo=_operand(wo), wi=_operand(wi),
-             wo2=_operand(wo2))
+    H = wq.shape[0]
+    # one projection GEMM instead of three: q | k | v weights cast straight into the row blocks of one bf16 operand
+    wqkv = torch.empty(3 * H, H, dtype=OPERAND_DTYPE, device=wq.device)
+    for i, w in enumerate((wq, wk, wv)):
+        ops.cast_bf16(w.contiguous(), out=wqkv[i * H:(i + 1) * H])
+    d = dict(wqkv=wqkv, bqkv=torch.cat([bq, bk, bv]).float(), wo=_operand(wo), wi=_operand(wi), wo2=_operand(wo2))
     if need_bwd:
-        d.update(wqkv_t=_operand_t(wqkv), wo_t=_operand_t(wo), wi_t=_operand_t(wi), wo2_t=_operand_t(wo2))
+        wqkv_t = torch.empty(H, 3 * H, dtype=OPERAND_DTYPE, device=wq.device)       # [Wq^T | Wk^T | Wv^T]
+        for i, w in enumerate((wq, wk, wv)):
+            ops.transpose_cast_bf16_slice(w.contiguous(), wqkv_t[:, i * H:(i + 1) * H])
+        d.update(wqkv_t=wqkv_t, wo_t=_operand_t(wo), wi_t=_operand_t(wi), wo2_t=_operand_t(wo2))
     return d
 
 
-def _attention(qkv: torch.Tensor, s: _Shape, key_mask: Optional[torch.Tensor], need_bwd: bool):
-    """qkv [M, 3H] -> (context [M, H], closure for the backward).  BertSelfAttention: scale 1/sqrt(dh), additive
-    key-padding mask broadcast over heads and queries."""
-    q5 = qkv.view(s.B, s.L, 3, s.heads, s.dh)
-    q, k, v = (q5[:, :, i].transpose(1, 2) for i in range(3))            # [B, heads, L, dh] views
-    mask4 = None if key_mask is None else key_mask.view(s.B, 1, 1, s.L)
-    if need_bwd:
-        with torch.enable_grad():
-            q, k, v = (t.detach().requires_grad_(True) for t in (q, k, v))
-            o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask4, dropout_p=s.p_attn, scale=s.dh ** -0.5)
-    else:
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask4, dropout_p=s.p_attn, scale=s.dh ** -0.5)
-    ctx = o.detach().transpose(1, 2).reshape(s.M, s.H).contiguous()
-    return ctx, ((q, k, v, o) if need_bwd else None)
-
-
-def _attention_bwd(saved, dctx: torch.Tensor, s: _Shape) -> torch.Tensor:
-    q, k, v, o = saved
-    do = dctx.view(s.B, s.L, s.heads, s.dh).transpose(1, 2)
-    dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
-    dqkv = torch.empty(s.B, s.L, 3, s.heads, s.dh, dtype=dctx.dtype, device=dctx.device)
-    for i, t in enumerate((dq, dk, dv)):
-        dqkv[:, :, i].copy_(t.transpose(1, 2))
-    return dqkv.view(s.M, 3 * s.H)
-
-
 def _key_mask(attention_mask: Optional[torch.Tensor], s: _Shape) -> Optional[torch.Tensor]:
-    """bool [B, L] (True = attend) or None when the caller passed no mask.  The tokenizer pads reports to 512
+    """uint8 [B, L] (non-zero = attend) or None when the caller passed no mask.  The tokenizer pads reports to 512
     (CTCLIPTrainer.py:562), so real batches do carry padding; the mask is always handed to the attention kernel - no
     host-side 'is it all ones' shortcut (that needs a device sync per batch, and caching its answer by tensor address
     is wrong as soon as the allocator reuses the address)."""
     if attention_mask is None:
         return None
-    return attention_mask.to(torch.bool).reshape(s.B, s.L)
+    return (attention_mask.reshape(s.B, s.L) != 0).to(torch.uint8).contiguous()
+
+
+# attention-probability dropout: the kernels hash (seed, report*head, query, key); the seed is a device counter so that
+# CUDA-graph replays draw fresh masks.  One counter per device, started from torch's CPU generator (torch.manual_seed).
+_SEED: Dict[torch.device, torch.Tensor] = {}
+
+
+def _next_seed(dev: torch.device) -> torch.Tensor:
+    """int64 [1] device tensor holding this forward's seed (a private copy: the backward reads it again)"""
+    st = _SEED.get(dev)
+    if st is None:
+        st = _SEED[dev] = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(dev)
+    seed = st.clone()
+    st.add_(1)
+    return seed
 
 
 def _forward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, key_mask, save: bool):
+    """key_mask: uint8 [B, L] or None.  Returns (hidden fp32 [B, L, H], saved per layer, saved embeddings)."""
     word, pos, typ, ge, be = params[:N_EMB]
     od = OPERAND_DTYPE
     dev = input_ids.device
     M, H, I = s.M, s.H, s.I
-    # BertEmbeddings: word + position (absolute, 0..L-1) + token type, LayerNorm, dropout
-    e = F.embedding(input_ids, word)
-    e = e + pos[: s.L].unsqueeze(0)
-    e = e + (typ[0] if token_type_ids is None else F.embedding(token_type_ids, typ))
-    e = e.reshape(M, H).float().contiguous()
+    # BertEmbeddings: word + token type + position (absolute, 0..L-1), LayerNorm, dropout
+    e = ops.bert_embed_fwd(input_ids.contiguous(), token_type_ids, word.contiguous(), pos.contiguous(), typ.contiguous())
+    seed = _next_seed(dev) if s.p_attn > 0 else None
+    scale = s.dh ** -0.5
     ph = s.p_hidden
     m0 = None
     if ph > 0:
@@ -173,7 +171,9 @@ def _forward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, k
         w = _prep_layer(lp, save)
         qkv = torch.empty(M, 3 * H, dtype=od, device=dev)
         ops.gemm(xb, w["wqkv"], ops.EPI_BF16, qkv, M=M, N=3 * H, K=H, bias=w["bqkv"])
-        ctxb, attn_saved = _attention(qkv, s, key_mask, save)
+        # BertSelfAttention core: scale 1/sqrt(dh), key-padding mask broadcast over heads and queries, dropout on the
+        # probabilities (training mode)
+        ctxb, lse = ops.mha_fwd(qkv, key_mask, s.B, s.L, s.heads, scale, s.p_attn, seed, li)
         y1 = torch.empty(M, H, dtype=torch.float32, device=dev)
         m1 = m2 = None
         if ph > 0:      # BertSelfOutput: dense -> dropout -> + input (the residual add leaves the epilogue)
@@ -195,10 +195,10 @@ def _forward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, k
             ops.gemm(G, w["wo2"], ops.EPI_RESID_F32, y2, M=M, N=H, K=I, bias=bo2, resid=x1)     # BertOutput
         x2b, x2, _, mu2, rs2 = ops.layernorm_fwd(y2, g2, b2, want_bf16=True, want_f32=True, eps=s.eps)
         if save:
-            saved.append(dict(w=w, xb=xb, attn=attn_saved, ctxb=ctxb, y1=y1, mu1=mu1, rs1=rs1, x1b=x1b, U=U, G=G,
+            saved.append(dict(w=w, xb=xb, qkv=qkv, lse=lse, ctxb=ctxb, y1=y1, mu1=mu1, rs1=rs1, x1b=x1b, U=U, G=G,
                               y2=y2, mu2=mu2, rs2=rs2, m1=m1, m2=m2))
         x, xb = x2, x2b
-    emb_saved = dict(e=e, mu=mue, rs=rse, m0=m0) if save else None
+    emb_saved = dict(e=e, mu=mue, rs=rse, m0=m0, key_mask=key_mask, seed=seed) if save else None
     return x.view(s.B, s.L, H), saved, emb_saved
 
 
@@ -252,7 +252,8 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
         dctx = torch.empty(M, H, dtype=od, device=dev)
         ops.gemm(dy1b, w["wo_t"], ops.EPI_BF16, dctx, M=M, N=H, K=H)
         # ---- attention core and the packed q|k|v projection
-        dqkv = _attention_bwd(sv["attn"], dctx, s)
+        dqkv = ops.mha_bwd(sv["qkv"], emb_saved["key_mask"], sv["ctxb"], dctx, sv["lse"], s.B, s.L, s.heads, s.dh ** -0.5,
+                           s.p_attn, emb_saved["seed"], li)
         dbqkv = bias_grad(dqkv, 3 * H)
         dwqkv = torch.zeros(3 * H, H, **f32)
         ops.gemm(dqkv, sv["xb"], ops.EPI_ATOMIC_F32, dwqkv, M=3 * H, N=H, K=M, mn_major=True, ldc=H)
@@ -268,18 +269,109 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
     if emb_saved["m0"] is not None:
         g = _dropout_bwd(g, emb_saved["m0"], s.p_hidden)
     de = ops.layernorm_bwd(g, emb_saved["e"], ge, emb_saved["mu"], emb_saved["rs"], dge, dbe)
-    dword = torch.zeros_like(word, dtype=torch.float32).index_add_(0, input_ids.reshape(-1), de)
-    if s.pad_idx is not None:
-        dword[s.pad_idx].zero_()                   # nn.Embedding never updates its padding row
-    dpos = torch.zeros_like(pos, dtype=torch.float32)
-    dpos[: s.L] = de.view(s.B, s.L, H).sum(0)
-    dtyp = torch.zeros_like(typ, dtype=torch.float32)
-    if token_type_ids is None:
-        dtyp[0] = de.sum(0)
-    else:
-        dtyp.index_add_(0, token_type_ids.reshape(-1), de)
+    # nn.Embedding never updates its padding row (pad_idx); positions >= L and unused token types stay zero
+    dword, dpos, dtyp = ops.bert_embed_bwd(de, input_ids.contiguous(), token_type_ids, word.shape, pos.shape, typ.shape,
+                                           s.pad_idx)
     grads[:N_EMB] = [dword, dpos, dtyp, dge, dbe]
     return grads
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the training-shape forward / backward
+# ------------------------------------------------------------------------------------------------
+class _TowerGraph:
+    """Graphs of one (shape, parameter addresses, dropout configuration) of the tower.  Eagerly the tower is ~200
+    forward + ~330 backward launches through ctypes (~15 ms of host time per step, which made the whole train step
+    launch-bound on the host); replayed, it is two graph launches.  The token ids / mask / incoming gradient are
+    copied into static buffers; saved activations live in the graphs' private pool."""
+    WARMUP = 2
+
+    def __init__(self):
+        self.calls = 0
+        self.fwd = None
+        self.bwd = None
+        self.pool = None
+        self.failed = False
+        self.owner = None        # weakref to the token of the forward whose activations sit in the static buffers
+
+
+class _Token:
+    __slots__ = ("done", "__weakref__")
+
+    def __init__(self):
+        self.done = False
+
+
+def _graphs_enabled() -> bool:
+    return os.environ.get("CTK_TEXT_GRAPHS", "1") != "0"
+
+
+def _graph_forward(bert, s: _Shape, plist, input_ids, attention_mask, token_type_ids):
+    """Replay (capturing on first use) the forward graph for these inputs.  Returns None when this call must run on
+    eager launches, else dict(out, eg, token)."""
+    if not (input_ids.is_cuda and _graphs_enabled() and ops.GEMM_PROFILE is None
+            and not torch.cuda.is_current_stream_capturing()):
+        return None
+    from .transformer_maskgit import _capture
+    key = (s.B, s.L, attention_mask is not None, token_type_ids is not None, s.p_hidden, s.p_attn,
+           tuple(p.data_ptr() for p in plist))
+    graphs = bert.__dict__.setdefault("_ctk_graphs", {})
+    eg = graphs.get(key)
+    if eg is None:
+        if len(graphs) >= 4:                       # shapes keep changing: stay eager
+            graphs.clear()
+        eg = graphs[key] = _TowerGraph()
+    eg.calls += 1
+    prev = eg.owner() if eg.owner is not None else None
+    if eg.failed or eg.calls <= _TowerGraph.WARMUP or (prev is not None and not prev.done):
+        return None
+    if eg.fwd is None:
+        try:
+            dev = input_ids.device
+            eg.pool = torch.cuda.graph_pool_handle()
+            st = dict(ids=input_ids.clone(),
+                      mask=None if attention_mask is None else _key_mask(attention_mask, s).clone(),
+                      tt=None if token_type_ids is None else token_type_ids.clone())
+            if s.p_attn > 0:
+                _next_seed(dev)                    # create the device counter outside the capture
+            g, outs, n = _capture(lambda: _forward(s, plist, st["ids"], st["tt"], st["mask"], True), eg.pool)
+            eg.fwd = dict(graph=g, outs=outs, launches=n, st=st)
+        except Exception as e:                                                  # pragma: no cover
+            import warnings
+            warnings.warn(f"ctk text tower: CUDA-graph capture failed ({e}); staying on eager launches")
+            eg.failed = True
+            torch.cuda.synchronize()
+            return None
+    f = eg.fwd
+    st = f["st"]
+    st["ids"].copy_(input_ids)
+    if st["mask"] is not None:
+        st["mask"].copy_(attention_mask.reshape(s.B, s.L) != 0)
+    if st["tt"] is not None:
+        st["tt"].copy_(token_type_ids)
+    f["graph"].replay()
+    ops.GRAPH_LAUNCHES += f["launches"]
+    token = _Token()
+    eg.owner = weakref.ref(token)
+    return dict(out=f["outs"][0].clone(), eg=eg, token=token)     # private copy: the next replay rewrites the buffer
+
+
+def _graph_backward(eg: _TowerGraph, token: _Token, s: _Shape, plist, dout):
+    from .transformer_maskgit import _capture
+    f = eg.fwd
+    if eg.bwd is None:
+        dstat = dout.reshape(s.B, s.L, s.H).float().contiguous().clone()
+        _, saved, emb_saved = f["outs"]
+        st = f["st"]
+        # _backward drops its references to the saved activations layer by layer: hand it a copy of the list
+        g, grads, n = _capture(lambda: _backward(s, plist, st["ids"], st["tt"], list(saved), emb_saved, dstat), eg.pool)
+        eg.bwd = dict(graph=g, grads=grads, launches=n, dout=dstat)
+    b = eg.bwd
+    b["dout"].copy_(dout.reshape(s.B, s.L, s.H))
+    b["graph"].replay()
+    ops.GRAPH_LAUNCHES += b["launches"]
+    token.done = True
+    return b["grads"]
 
 
 class _BertEncode(torch.autograd.Function):
@@ -289,8 +381,12 @@ class _BertEncode(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad[4:])       # grad mode is off inside forward(); encode() checked it
         plist = [p.detach() for p in params]
         with torch.autocast(device_type=input_ids.device.type, enabled=False):
+            launched = _graph_forward(bert, s, plist, input_ids, attention_mask, token_type_ids) if need_bwd else None
+            if launched is not None:
+                ctx.state = ("graph", launched["eg"], launched["token"], s, plist)
+                return launched["out"]
             out, saved, emb_saved = _forward(s, plist, input_ids, token_type_ids, _key_mask(attention_mask, s), need_bwd)
-        ctx.state = (s, plist, input_ids, token_type_ids, saved, emb_saved) if need_bwd else None
+        ctx.state = ("eager", s, plist, input_ids, token_type_ids, saved, emb_saved) if need_bwd else None
         return out
 
     @staticmethod
@@ -303,10 +399,14 @@ class _BertEncode(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         assert ctx.state is not None, "text tower: backward without saved activations"
-        s, plist, input_ids, token_type_ids, saved, emb_saved = ctx.state
-        ctx.state = None
+        state, ctx.state = ctx.state, None
         with torch.autocast(device_type=dout.device.type, enabled=False):
-            grads = _backward(s, plist, input_ids, token_type_ids, saved, emb_saved, dout)
+            if state[0] == "graph":
+                _, eg, token, s, plist = state
+                grads = _graph_backward(eg, token, s, plist, dout)
+            else:
+                _, s, plist, input_ids, token_type_ids, saved, emb_saved = state
+                grads = _backward(s, plist, input_ids, token_type_ids, saved, emb_saved, dout)
         grads = [gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[4:])]
         return (None, None, None, None, *grads)
 
