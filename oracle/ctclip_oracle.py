@@ -77,8 +77,8 @@ def peg(x, shape: Tuple[int, int, int, int], w, b):
 def cpb_bias(p: Params, pre: str, gh: int, gw: int):
     """attention.py:363-382 ContinuousPositionBias (num_dims 2, layers 2, log_dist): all (gh*gw)^2
     relative offsets -> sign*log(|.|+1) -> MLP with LeakyReLU(0.1) -> (heads, i, j)."""
-    dt = p[pre + "net.0.0.weight"].dtype
-    ys, xs = torch.meshgrid(torch.arange(gh), torch.arange(gw), indexing="ij")
+    dt, dev = p[pre + "net.0.0.weight"].dtype, p[pre + "net.0.0.weight"].device
+    ys, xs = torch.meshgrid(torch.arange(gh, device=dev), torch.arange(gw, device=dev), indexing="ij")
     grid = torch.stack([ys, xs]).reshape(2, -1).T                      # (gh*gw, 2)
     rel = (grid[:, None, :] - grid[None, :, :]).to(dt)
     rel = torch.sign(rel) * torch.log(rel.abs() + 1)

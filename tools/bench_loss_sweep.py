@@ -5,7 +5,7 @@ backward (dT_local, dI_local, d log-temperature), at 1/2/4/8 GPUs.
     python tools/bench_loss_sweep.py
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
            tools/bench_loss_sweep.py
-    CTK_CLIP_LOSS_TC=1 ... (tensor-core path for N >= 1024)
+    CTK_CLIP_LOSS_TC=0 ... (force the fp32 SIMT tiles; the tensor-core path is the default for N >= 1024)
 
 One JSON line per N from rank 0: microseconds per step (device-timed, max over ranks), split into gather and loss.
 """
@@ -73,7 +73,7 @@ def main():
             flops = 2.0 * N * N * d * (1 + 2.0 / world)          # full N x N similarity + this rank's two gradient products
             print(json.dumps({"config": 5, "N": N, "n_gpus": world, "b_local": B, "us_per_step": us_step,
                               "us_gather": us_gather, "loss": float(out[0]), "algorithmic_tflops": flops / us_step * 1e-6,
-                              "tensor_core_path": os.environ.get("CTK_CLIP_LOSS_TC", "0") == "1" and N >= 1024}),
+                              "tensor_core_path": os.environ.get("CTK_CLIP_LOSS_TC", "1") != "0" and N >= 1024}),
                   flush=True)
     if world > 1:
         dist.destroy_process_group()

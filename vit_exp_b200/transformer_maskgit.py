@@ -486,8 +486,7 @@ def _graph_launch(vit: "CTViT", video: torch.Tensor, training: bool, params: Lis
 
 
 def _eval_graph_forward(vit: "CTViT", video: torch.Tensor, params: List[torch.Tensor]):
-    """No-grad, eval-mode forward replayed from a CUDA graph (opt-in: `CTViT.eval_graphs` / CTK_EVAL_GRAPHS=1, not yet
-    run on hardware).  At one volume per call (zero-shot scoring, BASELINE configs 2 and 4) the ~260 launches of the
+    """No-grad, eval-mode forward replayed from a CUDA graph (`CTViT.eval_graphs`; CTK_EVAL_GRAPHS=0 disables).  At one volume per call (zero-shot scoring, BASELINE configs 2 and 4) the ~260 launches of the
     forward cost about as much host time as the GPU needs to execute them; replaying them as one graph removes that.
     Same mechanics as the training graphs: the patch gather stays outside (it reads the caller's volume) and writes into
     static buffers, the caller receives private copies of the outputs.  Returns None when this call runs eagerly."""
@@ -604,8 +603,9 @@ class CTViT(nn.Module):
         # training-shape forward / backward are replayed from CUDA graphs after two eager steps (see _EncoderGraph);
         # set to False to keep every step on eager launches
         self.cuda_graphs = os.environ.get("CTK_CUDA_GRAPHS", "1") != "0"
-        # opt-in (not yet validated on hardware): the no-grad eval forward is replayed from a CUDA graph as well
-        self.eval_graphs = os.environ.get("CTK_EVAL_GRAPHS", "0") == "1"
+        # the no-grad eval forward (zero-shot scoring, one volume per call) is replayed from a CUDA graph as well
+        # (CTK_EVAL_GRAPHS=0 keeps eager launches)
+        self.eval_graphs = os.environ.get("CTK_EVAL_GRAPHS", "1") != "0"
         self._graphs = {}
 
     # -- reference helpers kept for callers --------------------------------------------------------

@@ -109,17 +109,41 @@ class ZeroShotScorer:
         return torch.stack(rows)
 
     @torch.no_grad()
-    def run(self, n_volumes: int, load: Callable[[int], torch.Tensor], batch_size: int = 1) -> torch.Tensor:
+    def run(self, n_volumes: int, load: Callable[[int], torch.Tensor], batch_size: int = 1, prefetch: bool = True) -> torch.Tensor:
         """Scores volumes [0, n_volumes): this rank calls `load(i)` (-> (1, 1, D, H, W)) for its contiguous share only,
-        `batch_size` volumes per encoder pass; every rank returns the full [n_volumes, n_path] matrix in volume order."""
+        `batch_size` volumes per encoder pass; every rank returns the full [n_volumes, n_path] matrix in volume order.
+        `prefetch`: `load` of the next batch (host->device copy, `data.npz_to_tensor`) is issued on a side stream while
+        the current batch is scored, so the transfer hides behind the encoder (same results)."""
         on = dist.is_available() and dist.is_initialized()
         world = dist.get_world_size(self.group) if on else 1
         rank = dist.get_rank(self.group) if on else 0
         lo, hi = shard_bounds(n_volumes, world, rank)
         n_path = self.prompt_latents.shape[0] // 2
-        local = torch.empty(hi - lo, n_path, dtype=torch.float32, device=self.prompt_latents.device)
-        for i0 in range(lo, hi, max(1, batch_size)):
-            i1 = min(hi, i0 + max(1, batch_size))
-            vols = torch.cat([load(i) for i in range(i0, i1)], dim=0)
+        dev = self.prompt_latents.device
+        local = torch.empty(hi - lo, n_path, dtype=torch.float32, device=dev)
+        bs = max(1, batch_size)
+        side = torch.cuda.Stream(device=dev) if (prefetch and dev.type == "cuda") else None
+
+        def fetch(i0):
+            i1 = min(hi, i0 + bs)
+            if side is None:
+                vols = [load(i) for i in range(i0, i1)]
+                return (vols[0] if len(vols) == 1 else torch.cat(vols, dim=0)), None
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                vols = [load(i) for i in range(i0, i1)]
+                vols = vols[0] if len(vols) == 1 else torch.cat(vols, dim=0)
+                ev = torch.cuda.Event()
+                ev.record()
+            return vols, ev
+
+        nxt = fetch(lo) if hi > lo else None
+        for i0 in range(lo, hi, bs):
+            i1 = min(hi, i0 + bs)
+            vols, ev = nxt
+            nxt = fetch(i1) if i1 < hi else None
+            if ev is not None:
+                torch.cuda.current_stream(dev).wait_event(ev)
+                vols.record_stream(torch.cuda.current_stream(dev))
             local[i0 - lo: i1 - lo] = self.score_many(vols)
         return gather_rows(local, n_volumes, self.group)
