@@ -197,8 +197,14 @@ def run_ours(args):
     bert = clip.text_transformer
     model = clip
     if world > 1:
+        # find_unused_parameters=True as the reference trainer sets it (CTCLIPTrainer.py:318: pooler, *_extra projections
+        # and the cross-attention norms never get a gradient).  static_graph=True tells DDP that this set is the same
+        # every step, which removes its per-step all-reduce + device->host read of the used-parameter bitmap: that read
+        # is a host sync at the end of every backward pass and left the GPU idle for the ~2.6 ms of host time of
+        # optimizer.step() (profiles/r2_ddp_timeline_n2.txt).  --no-ddp-static-graph keeps the dynamic check.
         model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], find_unused_parameters=True,
-                                                          gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb)
+                                                          gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb,
+                                                          static_graph=not args.no_ddp_static_graph)
     params = [p for p in clip.parameters() if p.requires_grad]
     if args.optimizer == "fused":        # clip_grad_norm_(0.5) + Adam in two libctk launches (vit_exp_b200/optim.py)
         from vit_exp_b200.optim import FusedClipAdam
@@ -349,6 +355,13 @@ def run_ours(args):
     # ---- roofline: instrument every tcgen05 GEMM launch of one more step --------------------------
     # (eager launches, and the two towers run one after the other on one stream: with the text tower on its side stream
     # the events around a GEMM would also count the time its CTAs wait for SMs held by the other tower's kernels)
+    # The timed loops are over: drop the CUDA graphs (their private pools hold one full set of saved activations, 1.7 GB
+    # per volume) before the eager step allocates its own.
+    import gc
+    clip.visual_transformer._graphs.clear()
+    getattr(bert, "__dict__", {}).pop("_ctk_graphs", None)
+    gc.collect()
+    torch.cuda.empty_cache()
     clip.overlap_text_encoder = False
     ops.GEMM_PROFILE = []
     step(0)
@@ -388,8 +401,10 @@ def run_ours(args):
                                   + f", dropout {args.text_dropout} (CXR-BERT ships 0.1; the CPU arm uses 0)"),
                    "loss_read": "loss.item() inside forward" if args.sync_loss_read else
                                 "config['defer_loss_read']: async D2H copy, read every step after the step is enqueued",
-                   "launch": "encoder forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
-                             else "eager launches"},
+                   "launch": "encoder and text tower forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
+                             else "eager launches",
+                   "ddp": None if world == 1 else f"find_unused_parameters=True, gradient_as_bucket_view=True, bucket_cap_mb="
+                                                  f"{args.bucket_mb}, static_graph={not args.no_ddp_static_graph}"},
         "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s",
                 "h2d_bytes_per_step": int(host_vid[0].numel() * 2 + host_ids[0].numel() * 8), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
@@ -577,6 +592,8 @@ def main():
     ap.add_argument("--no-torch-eager", action="store_true",
                     help="skip the informational torch_eager_gpu leg (oracle port + HF BertModel as plain PyTorch eager ops on this GPU)")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (MB)")
+    ap.add_argument("--no-ddp-static-graph", action="store_true",
+                    help="DDP re-discovers the unused parameters every step (a host sync at the end of each backward pass)")
     ap.add_argument("--sync-loss-read", action="store_true",
                     help="CTCLIP returns cl_loss via loss.item() inside forward (reference behaviour: a host sync between "
                          "forward and backward); default: config['defer_loss_read'], the same value read back at the end of the step")

@@ -13,6 +13,8 @@ import torch
 
 from vit_exp_b200._lib import (EPI_ATOMIC_F32, EPI_BF16, EPI_F32, EPI_GELU, EPI_GELU_BWD, EPI_RESID_F32)  # noqa: F401
 
+from vit_exp_b200.ops import ZeroArena  # noqa: E402,F401  (plain torch: a pre-zeroed buffer handed out in slices)
+
 OPERAND = torch.bfloat16        # set to torch.float32 for exact checks of the host math
 CALLS = []                      # (name, epilogue or None) per call, for launch-plan assertions
 
@@ -28,12 +30,16 @@ def _gelu_grad(u):
 
 
 def gemm(a, b, epilogue, c, *, M, N, K, mn_major=False, lda=None, ldb=None, ldc=None, bias=None, resid=None,
-         ldr=None, aux0=None, ld_aux0=0, vec0=None, vec1=None, row_map=None, alpha=1.0, split_k=0, i0=0, i1=0):
+         ldr=None, aux0=None, ld_aux0=0, vec0=None, vec1=None, row_map=None, alpha=1.0, split_k=0, i0=0, i1=0,
+         b_mn_major=None):
     """ctk_gemm_bf16: D = A[M,K] B[N,K]^T (K-major) or A[K,M]^T B[K,N] (MN-major), fp32 accumulate."""
     assert lda is None and ldb is None and row_map is None, "emulation covers the calls the text tower makes"
     assert a.dtype == OPERAND and b.dtype == OPERAND
     CALLS.append(("gemm", epilogue))
-    if mn_major:
+    if b_mn_major and not mn_major:                 # K-major A, MN-major B: dX = dY W with W [K, N] as stored
+        assert a.shape == (M, K) and b.shape == (K, N), (a.shape, b.shape, M, N, K)
+        acc = a.float() @ b.float()
+    elif mn_major:
         assert a.shape[0] == K and b.shape[0] == K and a.shape[1] >= M and b.shape[1] >= N
         acc = a[:, :M].float().t() @ b[:, :N].float()
     else:
@@ -234,10 +240,13 @@ GEMM_PROFILE = None
 
 
 def gemm_full(a, b, epilogue, c, *, M, N, K, mn_major=False, lda=None, ldb=None, ldc=None, bias=None, resid=None,
-              ldr=None, aux0=None, ld_aux0=0, vec0=None, vec1=None, row_map=None, alpha=1.0, split_k=0, i0=0, i1=0):
+              ldr=None, aux0=None, ld_aux0=0, vec0=None, vec1=None, row_map=None, alpha=1.0, split_k=0, i0=0, i1=0,
+              b_mn_major=None):
     """all epilogues; operands may be column-sliced views (their strides play the role of lda / ldb)."""
     CALLS.append(("gemm", epilogue))
-    if mn_major:
+    if b_mn_major and not mn_major:
+        acc = a[:M, :K].float() @ b[:K, :N].float()
+    elif mn_major:
         acc = a[:K, :M].float().t() @ b[:K, :N].float()
     else:
         acc = a[:M, :K].float() @ b[:N, :K].float().t()

@@ -168,3 +168,36 @@ def test_gemm_argmax(cuda_dev):
     # fp32 accumulation order may differ from torch's: accept equal-valued picks
     assert (picked >= sim.max(dim=1).values - 1e-6).all()
     assert (idx == ref_idx).float().mean().item() > 0.99
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(256, 512, 256, "bf16"), (300, 352, 200, "bf16"), (13824, 512, 2816, "bf16"),
+                                       (4096, 768, 3072, "resid"), (520, 256, 512, "resid"), (128, 96, 64, "bf16")])
+def test_gemm_kmajor_a_mnmajor_b(cuda_dev, M, N, K, epi):
+    """D = A[M, K] W[K, N] with the weight used as stored ([out = K, in = N], N contiguous): the input-gradient
+    products of both towers (ops.gemm(b_mn_major=True)) - no transposed weight copy.  Ragged M / N / K included."""
+    from vit_exp_b200 import ops
+    a = _rand((M, K), cuda_dev, 1).bfloat16()
+    w = _rand((K, N), cuda_dev, 2, 0.3).bfloat16()
+    ref = a.float() @ w.float()
+    if epi == "bf16":
+        c = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+        ops.gemm(a, w, ops.EPI_BF16, c, M=M, N=N, K=K, b_mn_major=True)
+        assert _relerr(c, ref) < 8e-3
+    else:
+        x = _rand((M, N), cuda_dev, 3)
+        c = torch.full((M, N), float("nan"), device=cuda_dev)
+        ops.gemm(a, w, ops.EPI_RESID_F32, c, M=M, N=N, K=K, resid=x, b_mn_major=True)
+        assert _relerr(c, ref + x) < 2e-5
+
+
+def test_gemm_mnmajor_b_strided_a_and_padded_weight(cuda_dev):
+    """the two odd operand views of the encoder backward: A = the k|v columns of the packed dqkv buffer (lda = 3*inner),
+    and W2 [dim, ff_pad] whose pad columns are zero (GEGLU_BWD reads it MN-major with N = ff_pad)."""
+    from vit_exp_b200 import ops
+    M, inner, dim = 1000, 256, 512
+    dqkv = _rand((M, 3 * inner), cuda_dev, 4).bfloat16()
+    wkv = _rand((2 * inner, dim), cuda_dev, 5, 0.2).bfloat16()
+    g = _rand((M, dim), cuda_dev, 6)
+    ref = dqkv[:, inner:].float() @ wkv.float() + g
+    ops.gemm(dqkv[:, inner:], wkv, ops.EPI_RESID_F32, g, M=M, N=dim, K=2 * inner, lda=3 * inner, resid=g, b_mn_major=True)
+    assert _relerr(g, ref) < 2e-5

@@ -1,0 +1,90 @@
+"""dev tool: GPU timeline of DDP train steps (torchrun, rank 0 reports): where the NCCL kernels sit relative to the two
+towers' backward graphs and the optimizer, per stream busy time and all-stream idle gaps.
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 tools/ddp_timeline.py
+"""
+import json
+import os
+import sys
+import tempfile
+from types import SimpleNamespace
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+import bench
+from vit_exp_b200.ct_clip import TorchDistAccelerator
+from vit_exp_b200.optim import FusedClipAdam
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+B = 8
+clip = bench.build_model(dev, config={"defer_loss_read": True}).train()
+model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], find_unused_parameters=True,
+                                                  gradient_as_bucket_view=True, bucket_cap_mb=int(os.environ.get("BUCKET_MB", "25")),
+                                                  static_graph=os.environ.get("STATIC_GRAPH", "1") == "1")
+params = [p for p in clip.parameters() if p.requires_grad]
+opt = FusedClipAdam(params, lr=1.25e-6, betas=(0.9, 0.99), max_grad_norm=0.5)
+acc = TorchDistAccelerator()
+vid = torch.rand(B, 1, 240, 480, 480, device=dev)
+ids = torch.randint(0, 30522, (B, 512), device=dev)
+mask = torch.ones_like(ids)
+
+
+def step():
+    batch = {"data_type": ["imagereport"] * B, "text": SimpleNamespace(input_ids=ids, attention_mask=mask), "image": vid}
+    loss, ld = model(batch, device=dev, accelerator=acc)
+    loss.backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    return float(ld["cl_loss"])
+
+
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+dist.barrier()
+from torch.profiler import ProfilerActivity, profile
+
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+if rank == 0:
+    path = os.path.join(tempfile.gettempdir(), "ddp_trace.json")
+    prof.export_chrome_trace(path)
+    ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
+    ev.sort(key=lambda e: e["ts"])
+    t0 = ev[0]["ts"]
+    span = (ev[-1]["ts"] + ev[-1]["dur"] - t0) / 1e3
+    print(f"{len(ev)} GPU activities over {span:.1f} ms, 3 steps -> {span / 3:.2f} ms/step")
+    streams = {}
+    for e in ev:
+        streams.setdefault(e["args"].get("stream"), []).append(e)
+    for sid, lst in sorted(streams.items(), key=lambda kv: -sum(x["dur"] for x in kv[1])):
+        print(f"  stream {sid}: {len(lst):5d} activities, busy {sum(x['dur'] for x in lst) / 1e3:8.2f} ms, e.g. {lst[len(lst) // 2]['name'][:70]}")
+    print("NCCL kernels and step markers:")
+    for e in ev:
+        n = e["name"]
+        if "nccl" in n.lower() or "multi_adam" in n or "multi_sqnorm" in n or "patch_norm" in n or "clip_grad_tiles" in n:
+            print(f"  t={(e['ts'] - t0) / 1e3:8.3f} ms dur={e['dur'] / 1e3:7.3f} ms stream {e['args'].get('stream')}  {n[:80]}")
+    # idle gaps: no activity on any stream
+    end, prev = ev[0]["ts"], ev[0]
+    print("all-stream idle gaps > 0.2 ms:")
+    for e in ev:
+        if e["ts"] - end > 200:
+            print(f"  gap {(e['ts'] - end) / 1e3:6.2f} ms at {(end - t0) / 1e3:8.2f} ms: after {prev['name'][:50]} -> before {e['name'][:50]}")
+        if e["ts"] + e["dur"] > end:
+            end, prev = e["ts"] + e["dur"], e
+    # compute-only gaps: time when only NCCL kernels are running
+    comp = [e for e in ev if "nccl" not in e["name"].lower()]
+    end, prev = comp[0]["ts"], comp[0]
+    print("gaps with no compute kernel running (NCCL-only or idle) > 0.2 ms:")
+    for e in comp:
+        if e["ts"] - end > 200:
+            print(f"  gap {(e['ts'] - end) / 1e3:6.2f} ms at {(end - t0) / 1e3:8.2f} ms: after {prev['name'][:50]} -> before {e['name'][:50]}")
+        if e["ts"] + e["dur"] > end:
+            end, prev = e["ts"] + e["dur"], e
+dist.destroy_process_group()

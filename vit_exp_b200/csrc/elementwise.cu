@@ -950,13 +950,23 @@ vq_select_kernel(const unsigned long long* __restrict__ pkey, const float* __res
             kb = t > kb ? t : kb;
         }
         const float thr = vq_key_value(kb) - margin;
+        // candidate blocks as ballots over groups of 32 blocks: best within the margin / second best within the margin
+        auto ballots = [&](int b0, unsigned& cand, unsigned& full) {
+            const int b = b0 + lane;
+            const bool in = b < nblk;
+            cand = __ballot_sync(0xffffffffu, in && vq_key_value(sk[(in ? b : 0) * 32 + r]) >= thr);
+            full = __ballot_sync(0xffffffffu, in && ss[(in ? b : 0) * 32 + r] >= thr);
+        };
         int ncand = 0;
-        for (int b = lane; b < nblk; b += 32)
-            ncand += (vq_key_value(sk[b * 32 + r]) >= thr ? 1 : 0) + (ss[b * 32 + r] >= thr ? 2 : 0);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+        unsigned anyfull = 0u;
+        for (int b0 = 0; b0 < nblk; b0 += 32) {
+            unsigned c, f;
+            ballots(b0, c, f);
+            ncand += __popc(c);
+            anyfull |= f;
+        }
         long long best_i = (long long)(0xffffffffu - (uint32_t)(kb & 0xffffffffull));
-        if (ncand > 1) {
+        if (ncand > 1 || anyfull != 0u) {
             // fp32 re-score: xn = x * (1 / max(|x|, 1e-12)) exactly as ctk_l2norm_rows forms it
             float xv[32];
             const float* xr = x + row * dim;
@@ -980,14 +990,17 @@ vq_select_kernel(const unsigned long long* __restrict__ pkey, const float* __res
                 d = warp_sum(d);
                 if (d > best_v || (d == best_v && c < best_i)) { best_v = d; best_i = c; }
             };
-            for (int b = 0; b < nblk; ++b) {
-                const unsigned long long k = sk[b * 32 + r];
-                if (vq_key_value(k) < thr) continue;              // warp-uniform (shared-memory broadcast)
-                if (ss[b * 32 + r] >= thr) {
-                    const int c1 = min(C, (b + 1) * 128);
-                    for (int c = b * 128; c < c1; ++c) score(c);
-                } else {
-                    score((long long)(0xffffffffu - (uint32_t)(k & 0xffffffffull)));
+            for (int b0 = 0; b0 < nblk; b0 += 32) {
+                unsigned cand, full;
+                ballots(b0, cand, full);
+                for (unsigned m = cand; m; m &= m - 1) {               // warp-uniform walk over the set bits
+                    const int bit = __ffs(m) - 1, b = b0 + bit;
+                    if ((full >> bit) & 1u) {
+                        const int c1 = min(C, (b + 1) * 128);
+                        for (int c = b * 128; c < c1; ++c) score(c);
+                    } else {
+                        score((long long)(0xffffffffu - (uint32_t)(sk[b * 32 + r] & 0xffffffffull)));
+                    }
                 }
             }
         }

@@ -841,8 +841,14 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     CTK_REQUIRE(M > 0 && N > 0 && K > 0, CTK_ERR_SHAPE, "gemm: bad shape %d %d %d", M, N, K);
     CTK_REQUIRE(CTK_ALIGNED(A, 16) && CTK_ALIGNED(B, 16) && lda % 8 == 0 && ldb % 8 == 0,
                 CTK_ERR_ALIGN, "gemm: operands need 16-byte aligned base and pitch");
-    CTK_REQUIRE(a_mn_major == b_mn_major, CTK_ERR_SHAPE,
-                "gemm: mixed operand majors are not instantiated");
+    CTK_REQUIRE(a_mn_major == b_mn_major || (!a_mn_major && b_mn_major), CTK_ERR_SHAPE,
+                "gemm: an MN-major A with a K-major B is not instantiated");
+    // a K-major A with an MN-major B = the input-gradient products dX = dY W with W [out, in] used as stored
+    // (no transposed weight copy); instantiated for the epilogues those products use
+    const bool mixed = !a_mn_major && b_mn_major;
+    if (mixed)
+        CTK_REQUIRE(epilogue == CTK_EPI_BF16 || epilogue == CTK_EPI_RESID_F32 || epilogue == CTK_EPI_GEGLU_BWD ||
+                    epilogue == CTK_EPI_GELU_BWD, CTK_ERR_SHAPE, "gemm: epilogue %d has no MN-major-B instantiation", epilogue);
 
     EpiParams ep;
     ep.C = e->C; ep.ldc = e->ldc; ep.bias = e->bias; ep.resid = e->resid; ep.ldr = e->ldr;
@@ -868,7 +874,7 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
         epilogue == CTK_EPI_GELU_BWD || epilogue == CTK_EPI_CLIP_GRAD)
         CTK_REQUIRE(N % 32 == 0, CTK_ERR_SHAPE, "gemm: N %% 32 != 0 for a block epilogue");
     if (epilogue == CTK_EPI_GELU || epilogue == CTK_EPI_GELU_BWD)
-        CTK_REQUIRE(e->aux0 && !a_mn_major, CTK_ERR_SHAPE, "gemm: GELU epilogues need the aux0 buffer and K-major operands");
+        CTK_REQUIRE(e->aux0 && !a_mn_major, CTK_ERR_SHAPE, "gemm: GELU epilogues need the aux0 buffer and a K-major A");
     if (epilogue == CTK_EPI_LSE_PART)
         CTK_REQUIRE(e->vec1 && !a_mn_major, CTK_ERR_SHAPE, "gemm: LSE_PART needs the log-scale pointer and K-major operands");
     if (epilogue == CTK_EPI_CLIP_GRAD)
@@ -892,17 +898,12 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     }
     const bool pair = pair_env == 1 && M > BM;
     CUtensorMap ta, tb, tc0, tc1;
-    if (!a_mn_major) {
-        rc = make_tmap(&ta, A, false, K, M, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);   // [M rows][K]
-        if (rc) return rc;
-        rc = make_tmap(&tb, B, false, K, N, ldb, BK, pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);   // [N rows][K]
-        if (rc) return rc;
-    } else {
-        rc = make_tmap(&ta, A, false, M, K, lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);   // [K rows][M]
-        if (rc) return rc;
-        rc = make_tmap(&tb, B, false, N, K, ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);   // [K rows][N]
-        if (rc) return rc;
-    }
+    if (!a_mn_major) rc = make_tmap(&ta, A, false, K, M, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);   // [M rows][K]
+    else rc = make_tmap(&ta, A, false, M, K, lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);                // [K rows][M]
+    if (rc) return rc;
+    if (!b_mn_major) rc = make_tmap(&tb, B, false, K, N, ldb, BK, pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);   // [N rows][K]
+    else rc = make_tmap(&tb, B, false, N, K, ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);                              // [K rows][N]
+    if (rc) return rc;
     // epilogue tensor maps (32x32 blocks). Unused ones alias the A map so the kernel always gets
     // valid descriptors.
     tc0 = ta;
@@ -941,6 +942,21 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     }
     if (rc) return rc;
 
+#define CTK_GEMM_CASE_MIXED(E)                                                                             \
+    case E:                                                                                                \
+        if (pair) return launch<E, false, true, true>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream);      \
+        return launch<E, false, true, false>(ta, tb, tc0, tc1, M, N, K, splits, ep, stream);
+    if (mixed) {
+        switch (epilogue) {
+            CTK_GEMM_CASE_MIXED(CTK_EPI_BF16)
+            CTK_GEMM_CASE_MIXED(CTK_EPI_RESID_F32)
+            CTK_GEMM_CASE_MIXED(CTK_EPI_GEGLU_BWD)
+            CTK_GEMM_CASE_MIXED(CTK_EPI_GELU_BWD)
+            default:
+                break;
+        }
+    }
+#undef CTK_GEMM_CASE_MIXED
 #define CTK_GEMM_CASE(E)                                                                                   \
     case E:                                                                                                \
         if (pair)                                                                                          \

@@ -44,45 +44,69 @@ __global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict_
 
 // ---------------------------------------------------------------- latent projection + l2norm
 // one CTA (256 threads) per sample
-__global__ void latent_fwd_kernel(const float* __restrict__ x, long long x_stride,
-                                  const float* __restrict__ W, float* __restrict__ latent,
-                                  float* __restrict__ rnorm, int din, int dl) {
-    extern __shared__ float sm[];
-    float* xs = sm;            // [din]
-    float* raw = sm + din;     // [dl]
+// raw[b, j] = <W[j, :], x[b, :]>.  One warp per output row j holds W[j, :] in registers (read once, coalesced) and
+// sweeps the B input rows staged in shared memory; grid = dl / 8 CTAs (a B-CTA grid left 140 SMs idle and made every
+// CTA stream the whole weight matrix).  din <= 1024.
+constexpr int LAT_MAX_B = 8;               // input rows staged per pass: 8 x 1024 floats = 32 KB
+__global__ void __launch_bounds__(256)
+latent_raw_kernel(const float* __restrict__ x, long long x_stride, const float* __restrict__ W,
+                  float* __restrict__ raw, int B, int din, int dl) {
+    extern __shared__ float sm[];              // [min(B, LAT_MAX_B)][din]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    float w[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int i = lane + 32 * k;
+        w[k] = (j < dl && i < din) ? __ldg(W + (long long)j * din + i) : 0.f;
+    }
+    for (int b0 = 0; b0 < B; b0 += LAT_MAX_B) {
+        const int nb = min(LAT_MAX_B, B - b0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nb * din; t += blockDim.x)
+            sm[t] = x[(long long)(b0 + t / din) * x_stride + t % din];
+        __syncthreads();
+        for (int b = 0; b < nb; ++b) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int i = lane + 32 * k;
+                if (i < din) acc = fmaf(w[k], sm[b * din + i], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0 && j < dl) raw[(long long)(b0 + b) * dl + j] = acc;
+        }
+    }
+}
+// latent[b, :] = raw[b, :] / max(|raw[b, :]|, 1e-12) in place; rnorm[b] = the reciprocal (F.normalize, ct_clip.py:70-71)
+__global__ void __launch_bounds__(256)
+latent_norm_kernel(float* __restrict__ latent, float* __restrict__ rnorm, int dl) {
     __shared__ float red[8];
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < din; i += blockDim.x) xs[i] = x[(long long)b * x_stride + i];
-    __syncthreads();
-    for (int j = warp; j < dl; j += nwarp) {
-        const float* w = W + (long long)j * din;
-        float acc = 0.f;
-        for (int i = lane; i < din; i += 32) acc = fmaf(__ldg(w + i), xs[i], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) raw[j] = acc;
-    }
-    __syncthreads();
     float ss = 0.f;
-    for (int j = threadIdx.x; j < dl; j += blockDim.x) ss += raw[j] * raw[j];
+    for (int j = threadIdx.x; j < dl; j += blockDim.x) { const float v = latent[(long long)b * dl + j]; ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
     if (lane == 0) red[warp] = ss;
     __syncthreads();
     float tot = 0.f;
     for (int w = 0; w < nwarp; ++w) tot += red[w];
-    const float rn = 1.0f / fmaxf(sqrtf(tot), 1e-12f);       // F.normalize eps (ct_clip.py:70-71)
-    for (int j = threadIdx.x; j < dl; j += blockDim.x) latent[(long long)b * dl + j] = raw[j] * rn;
+    const float rn = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    for (int j = threadIdx.x; j < dl; j += blockDim.x) latent[(long long)b * dl + j] *= rn;
     if (threadIdx.x == 0) rnorm[b] = rn;
 }
 
-// draw[b] = rnorm_b * (dlat_b - lat_b * <lat_b, dlat_b>) ; dx[b, i] = sum_j draw[b, j] W[j, i]
-__global__ void latent_bwd_dx_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
-                                     const float* __restrict__ rnorm, const float* __restrict__ W,
-                                     float* __restrict__ dx, long long dx_stride, int din, int dl) {
+// draw[b] = rnorm_b * (dlat_b - lat_b * <lat_b, dlat_b>) ; dx[b, i] = sum_j draw[b, j] W[j, i].
+// grid (ceil(din / 64), B); 256 threads = 64 columns i x 4 slices of j, reduced through shared memory.
+__global__ void __launch_bounds__(256)
+latent_bwd_dx_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
+                     const float* __restrict__ rnorm, const float* __restrict__ W,
+                     float* __restrict__ dx, long long dx_stride, int din, int dl) {
     extern __shared__ float sm[];
     float* draw = sm;          // [dl]
     __shared__ float red[8];
-    const int b = blockIdx.x;
+    __shared__ float part[4][64];
+    const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     float dot = 0.f;
     for (int j = threadIdx.x; j < dl; j += blockDim.x)
@@ -96,11 +120,14 @@ __global__ void latent_bwd_dx_kernel(const float* __restrict__ dlat, const float
     for (int j = threadIdx.x; j < dl; j += blockDim.x)
         draw[j] = rn * (dlat[(long long)b * dl + j] - lat[(long long)b * dl + j] * coef);
     __syncthreads();
-    for (int i = threadIdx.x; i < din; i += blockDim.x) {
-        float acc = 0.f;
-        for (int j = 0; j < dl; ++j) acc = fmaf(draw[j], __ldg(W + (long long)j * din + i), acc);
-        dx[(long long)b * dx_stride + i] = acc;
-    }
+    const int ic = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + ic;
+    float acc = 0.f;
+    if (i < din)
+        for (int j = q; j < dl; j += 4) acc = fmaf(draw[j], __ldg(W + (long long)j * din + i), acc);
+    part[q][ic] = acc;
+    __syncthreads();
+    if (q == 0 && i < din) dx[(long long)b * dx_stride + i] = (part[0][ic] + part[1][ic]) + (part[2][ic] + part[3][ic]);
 }
 
 // dW[j, i] = sum_b draw[b, j] x[b, i]; one CTA per 8 output rows j
@@ -347,9 +374,11 @@ extern "C" int ctk_latent_fwd(const float* x, long long x_stride, const float* W
     CTK_REQUIRE(x && W && latent && rnorm && B > 0 && din > 0 && dl > 0, CTK_ERR_SHAPE,
                 "latent_fwd: bad args");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    const size_t sm = sizeof(float) * (size_t)(din + dl);
-    CTK_REQUIRE(sm <= 48 * 1024, CTK_ERR_SHAPE, "latent_fwd: din + dl too large");
-    latent_fwd_kernel<<<B, 256, sm, s>>>(x, x_stride, W, latent, rnorm, din, dl);
+    CTK_REQUIRE(din <= 1024, CTK_ERR_SHAPE, "latent_fwd: din %d > 1024", din);
+    const size_t sm = sizeof(float) * (size_t)din * (size_t)(B < LAT_MAX_B ? B : LAT_MAX_B);
+    latent_raw_kernel<<<(dl + 7) / 8, 256, sm, s>>>(x, x_stride, W, latent, B, din, dl);
+    CTK_LAUNCH_CHECK();
+    latent_norm_kernel<<<B, 256, 0, s>>>(latent, rnorm, dl);
     CTK_LAUNCH_CHECK();
     return CTK_OK;
 }
@@ -364,8 +393,8 @@ extern "C" int ctk_latent_bwd(const float* dlatent, const float* latent, const f
                 "latent_bwd: bad args");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     if (dx) {
-        latent_bwd_dx_kernel<<<B, 256, sizeof(float) * dl, s>>>(dlatent, latent, rnorm, W, dx,
-                                                                dx_stride, din, dl);
+        latent_bwd_dx_kernel<<<dim3((din + 63) / 64, B), 256, sizeof(float) * dl, s>>>(dlatent, latent, rnorm, W, dx,
+                                                                                       dx_stride, din, dl);
         CTK_LAUNCH_CHECK();
     }
     if (dW) {

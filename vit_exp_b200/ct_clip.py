@@ -223,12 +223,25 @@ class CTCLIP(nn.Module):
                       flush=True)
         return self.text_transformer(text.input_ids, attention_mask=text.attention_mask)[0]
 
+    def _text_on_ctk(self) -> bool:
+        bert = self.text_transformer
+        return self.ctk_text_tower and text_tower.unsupported_reason(bert, getattr(bert, "training", False)) is None
+
     def _encode_both(self, text, image):
-        """Text tower (stock PyTorch, hundreds of small kernels) on a side stream while the image
-        encoder (libctk) runs on the current stream; autograd replays each backward on the stream of
-        its forward, so the two towers overlap in both directions. Results are identical."""
-        if not (self.overlap_text_encoder and image.is_cuda):
-            return self._encode_text(text), self.visual_transformer(image, return_encoded_tokens=True)
+        """Both towers of one step.
+
+        libctk text tower (the default for a HF BertModel): both towers are CUDA-graph replays, so nothing is gained
+        from a second stream (each fills the GPU); they run back to back on the current stream.  The text tower's
+        autograd node is created LAST, so its (short) backward runs FIRST: its gradients - 80 % of the bytes DDP has to
+        all-reduce - are complete ~4 ms into the backward pass and their buckets travel while the image encoder's
+        backward computes.  (With the tower on a side stream its AccumulateGrad copies queued on the default stream
+        behind the encoder's backward graph, and every all-reduce ended up exposed at the end of the step.)
+
+        Text encoder run as passed (stock PyTorch, hundreds of small launches): on a high-priority side stream next to
+        the image encoder; autograd replays each backward on the stream of its forward.  Results are identical."""
+        if self._text_on_ctk() or not (self.overlap_text_encoder and image.is_cuda):
+            enc_image = self.visual_transformer(image, return_encoded_tokens=True)
+            return self._encode_text(text), enc_image
         cur = torch.cuda.current_stream()
         if self._side_stream is None:
             # high priority: the tower's many small kernels are scheduled ahead of the encoder's persistent,

@@ -40,9 +40,11 @@ GRAPH_LAUNCHES = 0
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, c: torch.Tensor, *, M: int, N: int, K: int,
          mn_major: bool = False, lda: Optional[int] = None, ldb: Optional[int] = None,
          ldc: Optional[int] = None, bias=None, resid=None, ldr: Optional[int] = None, aux0=None,
-         ld_aux0: int = 0, vec0=None, vec1=None, row_map=None, alpha: float = 1.0, split_k: int = 0, i0: int = 0, i1: int = 0):
+         ld_aux0: int = 0, vec0=None, vec1=None, row_map=None, alpha: float = 1.0, split_k: int = 0, i0: int = 0, i1: int = 0,
+         b_mn_major: Optional[bool] = None):
     """D = A[M,K] B[N,K]^T with a fused epilogue (ctk_gemm_bf16). a, b are bf16; K-major:
-    a [M, lda>=K], b [N, ldb>=K]; MN-major: a [K, lda>=M], b [K, ldb>=N]."""
+    a [M, lda>=K], b [N, ldb>=K]; MN-major: a [K, lda>=M], b [K, ldb>=N].  `b_mn_major=True` with a K-major A is the
+    input-gradient product dX = dY W with the weight W [K = out, N = in] used as stored."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lib = _lib.load()
     e = GemmEpilogue()
@@ -65,13 +67,40 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, c: torch.Tensor, *, M:
     if prof is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(lib.ctk_gemm_bf16(_p(a), lda, int(mn_major), _p(b), ldb, int(mn_major), M, N, K, epilogue,
+    check(lib.ctk_gemm_bf16(_p(a), lda, int(mn_major), _p(b), ldb, int(mn_major if b_mn_major is None else b_mn_major),
+                            M, N, K, epilogue,
                             C.byref(e), split_k, _stream()), "ctk_gemm_bf16")
     if prof is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         prof.append((e0, e1, f"epi{epilogue}{'_wgrad' if mn_major else ''}"))
     return c
+
+
+class ZeroArena:
+    """One zero-filled fp32 buffer handed out in 256-byte aligned slices: the backward passes accumulate ~250 gradient
+    tensors with atomics (split-K weight gradients, LayerNorm / PEG parameter gradients), and zeroing them with one
+    fill kernel each cost 0.4 ms of tiny launches per step; this is a single fill.  `take` falls back to torch.zeros
+    if the arena was sized too small."""
+
+    def __init__(self, n_elems: int, device):
+        self.buf = torch.zeros(int(n_elems), dtype=torch.float32, device=device)
+        self.off = 0
+
+    @staticmethod
+    def room(*numels) -> int:
+        return sum((int(n) + 63) // 64 * 64 for n in numels)
+
+    def take(self, *shape) -> torch.Tensor:
+        shape = tuple(shape[0]) if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)) else tuple(shape)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.off + n > self.buf.numel():
+            return torch.zeros(shape, dtype=torch.float32, device=self.buf.device)
+        v = self.buf[self.off: self.off + n].view(shape)
+        self.off += (n + 63) // 64 * 64
+        return v
 
 
 # --------------------------------------------------------------------------- weight prep

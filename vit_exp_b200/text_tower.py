@@ -112,13 +112,9 @@ def _prep_layer(lp: List[torch.Tensor], need_bwd: bool) -> Dict[str, torch.Tenso
     wqkv = torch.empty(3 * H, H, dtype=OPERAND_DTYPE, device=wq.device)
     for i, w in enumerate((wq, wk, wv)):
         ops.cast_bf16(w.contiguous(), out=wqkv[i * H:(i + 1) * H])
-    d = dict(wqkv=wqkv, bqkv=torch.cat([bq, bk, bv]).float(), wo=_operand(wo), wi=_operand(wi), wo2=_operand(wo2))
-    if need_bwd:
-        wqkv_t = torch.empty(H, 3 * H, dtype=OPERAND_DTYPE, device=wq.device)       # [Wq^T | Wk^T | Wv^T]
-        for i, w in enumerate((wq, wk, wv)):
-            ops.transpose_cast_bf16_slice(w.contiguous(), wqkv_t[:, i * H:(i + 1) * H])
-        d.update(wqkv_t=wqkv_t, wo_t=_operand_t(wo), wi_t=_operand_t(wi), wo2_t=_operand_t(wo2))
-    return d
+    # the input-gradient products of the backward pass read these same [out, in] operands MN-major
+    # (ops.gemm(b_mn_major=True)): no transposed weight copies
+    return dict(wqkv=wqkv, bqkv=torch.cat([bq, bk, bv]).float(), wo=_operand(wo), wi=_operand(wi), wo2=_operand(wo2))
 
 
 def _key_mask(attention_mask: Optional[torch.Tensor], s: _Shape) -> Optional[torch.Tensor]:
@@ -210,12 +206,17 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
     grads: List[Optional[torch.Tensor]] = [None] * len(params)
     g = dout.reshape(M, H).float().contiguous()                  # d(last_hidden_state)
     ones = torch.ones(M, 8, dtype=od, device=dev)
+    # zero-initialised accumulation targets (split-K weight gradients, LayerNorm parameter gradients, the [n, 8] bias
+    # gradient products): slices of one pre-filled buffer instead of ~200 fill kernels
+    arena = ops.ZeroArena(ops.ZeroArena.room(*(p.numel() for p in params[N_EMB:]),
+                                             *([8 * H, 8 * I, 8 * H, 8 * 3 * H] * s.depth), H, H), dev)
+    zeros = arena.take
 
     def bias_grad(dyb: torch.Tensor, n: int) -> torch.Tensor:
         """column sums of dY [M, n] as a token-contraction on the tensor cores, dY^T 1: the MN-major split-K product
         of the weight gradients with a ones operand streams dY through TMA at full rate (a plain column-sum kernel
         keeps too few loads in flight for [4096, 3072] matrices)."""
-        out = torch.zeros(n, 8, **f32)
+        out = zeros(n, 8)
         ops.gemm(dyb, ones, ops.EPI_ATOMIC_F32, out, M=n, N=8, K=M, mn_major=True, ldc=8)
         return out[:, 0]
     for li in range(s.depth - 1, -1, -1):
@@ -224,48 +225,48 @@ def _backward(s: _Shape, params: List[torch.Tensor], input_ids, token_type_ids, 
         sv = saved[li]
         w = sv["w"]
         # ---- x2 = LN(y2), y2 = G Wo2^T + bo2 + x1
-        dg2, db2 = torch.zeros(H, **f32), torch.zeros(H, **f32)
+        dg2, db2 = zeros(H), zeros(H)
         dy2b = torch.empty(M, H, dtype=od, device=dev)
         dy2 = ops.layernorm_bwd(g, sv["y2"], g2, sv["mu2"], sv["rs2"], dg2, db2, dx_bf16=dy2b)
         if sv["m2"] is not None:         # the dense branch sees the masked gradient, the residual branch dy2 itself
             dy2b = ops.cast_bf16(_dropout_bwd(dy2, sv["m2"], s.p_hidden))
         dbo2 = bias_grad(dy2b, H)
-        dwo2 = torch.zeros(H, I, **f32)
+        dwo2 = zeros(H, I)
         ops.gemm(dy2b, sv["G"], ops.EPI_ATOMIC_F32, dwo2, M=H, N=I, K=M, mn_major=True, ldc=I)
         # ---- G = gelu(U), U = x1 Wi^T + bi
         dU = torch.empty(M, I, dtype=od, device=dev)
-        ops.gemm(dy2b, w["wo2_t"], ops.EPI_GELU_BWD, dU, M=M, N=I, K=H, aux0=sv["U"], ld_aux0=I)
+        ops.gemm(dy2b, w["wo2"], ops.EPI_GELU_BWD, dU, M=M, N=I, K=H, aux0=sv["U"], ld_aux0=I, b_mn_major=True)
         dbi = bias_grad(dU, I)
-        dwi = torch.zeros(I, H, **f32)
+        dwi = zeros(I, H)
         ops.gemm(dU, sv["x1b"], ops.EPI_ATOMIC_F32, dwi, M=I, N=H, K=M, mn_major=True, ldc=H)
         dx1 = torch.empty(M, H, **f32)
-        ops.gemm(dU, w["wi_t"], ops.EPI_RESID_F32, dx1, M=M, N=H, K=I, resid=dy2)      # + residual branch of y2
+        ops.gemm(dU, w["wi"], ops.EPI_RESID_F32, dx1, M=M, N=H, K=I, resid=dy2, b_mn_major=True)  # + residual branch of y2
         # ---- x1 = LN(y1), y1 = ctx Wo^T + bo + x
-        dg1, db1 = torch.zeros(H, **f32), torch.zeros(H, **f32)
+        dg1, db1 = zeros(H), zeros(H)
         dy1b = torch.empty(M, H, dtype=od, device=dev)
         dy1 = ops.layernorm_bwd(dx1, sv["y1"], g1, sv["mu1"], sv["rs1"], dg1, db1, dx_bf16=dy1b)
         if sv["m1"] is not None:
             dy1b = ops.cast_bf16(_dropout_bwd(dy1, sv["m1"], s.p_hidden))
         dbo = bias_grad(dy1b, H)
-        dwo = torch.zeros(H, H, **f32)
+        dwo = zeros(H, H)
         ops.gemm(dy1b, sv["ctxb"], ops.EPI_ATOMIC_F32, dwo, M=H, N=H, K=M, mn_major=True, ldc=H)
         dctx = torch.empty(M, H, dtype=od, device=dev)
-        ops.gemm(dy1b, w["wo_t"], ops.EPI_BF16, dctx, M=M, N=H, K=H)
+        ops.gemm(dy1b, w["wo"], ops.EPI_BF16, dctx, M=M, N=H, K=H, b_mn_major=True)
         # ---- attention core and the packed q|k|v projection
         dqkv = ops.mha_bwd(sv["qkv"], emb_saved["key_mask"], sv["ctxb"], dctx, sv["lse"], s.B, s.L, s.heads, s.dh ** -0.5,
                            s.p_attn, emb_saved["seed"], li)
         dbqkv = bias_grad(dqkv, 3 * H)
-        dwqkv = torch.zeros(3 * H, H, **f32)
+        dwqkv = zeros(3 * H, H)
         ops.gemm(dqkv, sv["xb"], ops.EPI_ATOMIC_F32, dwqkv, M=3 * H, N=H, K=M, mn_major=True, ldc=H)
         gx = torch.empty(M, H, **f32)
-        ops.gemm(dqkv, w["wqkv_t"], ops.EPI_RESID_F32, gx, M=M, N=H, K=3 * H, resid=dy1)  # + residual branch of y1
+        ops.gemm(dqkv, w["wqkv"], ops.EPI_RESID_F32, gx, M=M, N=H, K=3 * H, resid=dy1, b_mn_major=True)  # + residual of y1
         g = gx
         grads[base: base + N_PER_LAYER] = [dwqkv[:H], dbqkv[:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:],
                                            dbqkv[2 * H:], dwo, dbo, dg1, db1, dwi, dbi, dwo2, dbo2, dg2, db2]
         saved[li] = None
     # ---- embeddings
     word, pos, typ, ge, be = params[:N_EMB]
-    dge, dbe = torch.zeros(H, **f32), torch.zeros(H, **f32)
+    dge, dbe = zeros(H), zeros(H)
     if emb_saved["m0"] is not None:
         g = _dropout_bwd(g, emb_saved["m0"], s.p_hidden)
     de = ops.layernorm_bwd(g, emb_saved["e"], ge, emb_saved["mu"], emb_saved["rs"], dge, dbe)

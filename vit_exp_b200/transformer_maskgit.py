@@ -181,15 +181,10 @@ def _prep_layer_weights(lp: List[torch.Tensor], cfg: _Cfg, need_bwd: bool) -> Di
     d["wq"] = ops.cast_bf16(wq)
     d["wkv"] = ops.cast_bf16(wkv)
     d["wo"] = ops.cast_bf16(wo)
-    d["w1p"], d["w1p_t"], d["w1_map"] = ops.pack_ff_w1(w1, cfg.ff_inner, cfg.ff_pad, want_t=need_bwd)
-    d["w2"] = ops.cast_bf16(w2, ld=cfg.ff_pad)
-    if need_bwd:
-        d["wq_t"] = ops.transpose_cast_bf16(wq)               # [dim, inner]
-        d["wkv_t"] = ops.transpose_cast_bf16(wkv)             # [dim, 2 inner]
-        d["wo_t"] = ops.transpose_cast_bf16(wo)               # [inner, dim]
-        w2t = torch.zeros(cfg.ff_pad, cfg.dim, dtype=torch.bfloat16, device=w2.device)
-        ops.transpose_cast_bf16(w2, out=w2t[: cfg.ff_inner])  # [ff_inner, dim] rows, pad rows stay zero
-        d["w2_t"] = w2t
+    # the input-gradient products read these same [out, in] operands MN-major (ops.gemm(b_mn_major=True)): no
+    # transposed weight copies
+    d["w1p"], _, d["w1_map"] = ops.pack_ff_w1(w1, cfg.ff_inner, cfg.ff_pad, want_t=False)
+    d["w2"] = ops.cast_bf16(w2, ld=cfg.ff_pad)                # pad columns (hidden units >= ff_inner) are zero
     return d
 
 
@@ -230,7 +225,7 @@ def _transformer_fwd(x, lps, norm_gamma, cfg: _Cfg, table, nseq, L, gh, gw, perm
 
 
 def _transformer_bwd(dy, dy_bcast, lps, norm_gamma, cfg: _Cfg, table, dtable, nseq, L, gh, gw, perm, saved, fin,
-                     grads_out: List[Optional[torch.Tensor]], want_bf16_out: bool):
+                     grads_out: List[Optional[torch.Tensor]], want_bf16_out: bool, arena: "ops.ZeroArena"):
     """dy: gradient wrt the (permuted) norm_out output. Returns (dx fp32, dx bf16 or None); fills
     grads_out (same order as _layer_params)."""
     dim, heads, inner, M = cfg.dim, cfg.heads, cfg.inner, cfg.M
@@ -238,7 +233,8 @@ def _transformer_bwd(dy, dy_bcast, lps, norm_gamma, cfg: _Cfg, table, dtable, ns
     shape = (cfg.B, cfg.t, cfg.h, cfg.w)
     f32 = dict(dtype=torch.float32, device=dev)
     bf = dict(dtype=torch.bfloat16, device=dev)
-    dgo = torch.zeros(dim, **f32)
+    zeros = arena.take                     # zero-initialised accumulation targets: slices of one pre-filled buffer
+    dgo = zeros(dim)
     g_bf = torch.empty(M, dim, **bf)
     if dy_bcast is not None:
         rows_per, scale = dy_bcast
@@ -253,39 +249,41 @@ def _transformer_bwd(dy, dy_bcast, lps, norm_gamma, cfg: _Cfg, table, dtable, ns
         s = saved[li]
         w = s["w"]
         # ---- feed-forward: x3 = x2 + W2 geglu(W1 LN(x2))
-        dw2 = torch.zeros_like(w2)
+        dw2 = zeros(w2.shape)
         ops.gemm(g_bf, s["H"], ops.EPI_ATOMIC_F32, dw2, M=dim, N=cfg.ff_inner, K=M, mn_major=True, ldc=cfg.ff_inner)
         dU = torch.empty_like(s["U"])
-        ops.gemm(g_bf, w["w2_t"], ops.EPI_GEGLU_BWD, dU, M=M, N=cfg.ff_pad, K=dim, aux0=s["U"], ld_aux0=2 * cfg.ff_pad)
-        dw1 = torch.zeros_like(w1)
+        ops.gemm(g_bf, w["w2"], ops.EPI_GEGLU_BWD, dU, M=M, N=cfg.ff_pad, K=dim, aux0=s["U"], ld_aux0=2 * cfg.ff_pad,
+                 b_mn_major=True)
+        dw1 = zeros(w1.shape)
         ops.gemm(dU, s["hn"], ops.EPI_ATOMIC_F32, dw1, M=2 * cfg.ff_pad, N=dim, K=M, mn_major=True, ldc=dim,
                  row_map=w["w1_map"])
         dhn = torch.empty(M, dim, **bf)
-        ops.gemm(dU, w["w1p_t"], ops.EPI_BF16, dhn, M=M, N=dim, K=2 * cfg.ff_pad)
-        dfg, dfb = torch.zeros(dim, **f32), torch.zeros(dim, **f32)
+        ops.gemm(dU, w["w1p"], ops.EPI_BF16, dhn, M=M, N=dim, K=2 * cfg.ff_pad, b_mn_major=True)
+        dfg, dfb = zeros(dim), zeros(dim)
         ops.layernorm_bwd(dhn, s["x2"], fg, s["mu2"], s["rs2"], dfg, dfb, dx=g, accum=True, dx_bf16=g_bf)
         # ---- attention: x2 = x1 + Wo attn(q(LN(x1)), kv(x1))
-        dwo = torch.zeros_like(wo)
+        dwo = zeros(wo.shape)
         ops.gemm(g_bf, s["o"], ops.EPI_ATOMIC_F32, dwo, M=dim, N=inner, K=M, mn_major=True, ldc=inner)
         do = torch.empty(M, inner, **bf)
-        ops.gemm(g_bf, w["wo_t"], ops.EPI_BF16, do, M=M, N=inner, K=dim)
+        ops.gemm(g_bf, w["wo"], ops.EPI_BF16, do, M=M, N=inner, K=dim, b_mn_major=True)
         dqkv = ops.attn_bwd(s["qkv"], table, s["o"], do, s["lse"], dtable, nseq, L, heads, gh, gw)
-        dqs, dks = torch.zeros(32, **f32), torch.zeros(32, **f32)
+        dqs, dks = zeros(32), zeros(32)
         ops.qknorm_bwd_(dqkv, s["qkv"], s["rn"], qs, ks, ATTN_SCALE, dqs, dks, heads)
-        dwq = torch.zeros_like(wq)
+        dwq = zeros(wq.shape)
         ops.gemm(dqkv, s["xn"], ops.EPI_ATOMIC_F32, dwq, M=inner, N=dim, K=M, mn_major=True, lda=3 * inner, ldc=dim)
-        dwkv = torch.zeros_like(wkv)
+        dwkv = zeros(wkv.shape)
         dkv_view = dqkv[:, inner:]
         ops.gemm(dkv_view, s["xraw"], ops.EPI_ATOMIC_F32, dwkv, M=2 * inner, N=dim, K=M, mn_major=True,
                  lda=3 * inner, ldc=dim)
         # k/v read the raw stream: their input gradient joins the residual gradient directly
-        ops.gemm(dkv_view, w["wkv_t"], ops.EPI_RESID_F32, g, M=M, N=dim, K=2 * inner, lda=3 * inner, resid=g)
+        ops.gemm(dkv_view, w["wkv"], ops.EPI_RESID_F32, g, M=M, N=dim, K=2 * inner, lda=3 * inner, resid=g,
+                 b_mn_major=True)
         dxn = torch.empty(M, dim, **bf)
-        ops.gemm(dqkv, w["wq_t"], ops.EPI_BF16, dxn, M=M, N=dim, K=inner, lda=3 * inner)
-        dgamma = torch.zeros(dim, **f32)
+        ops.gemm(dqkv, w["wq"], ops.EPI_BF16, dxn, M=M, N=dim, K=inner, lda=3 * inner, b_mn_major=True)
+        dgamma = zeros(dim)
         ops.layernorm_bwd(dxn, s["x1"], gamma, s["mu1"], s["rs1"], dgamma, None, dx=g, accum=True)
         # ---- PEG: x1 = conv(x) + b + x
-        dpw, dpb = torch.zeros(dim, 27, **f32), torch.zeros(dim, **f32)
+        dpw, dpb = zeros(dim, 27), zeros(dim)
         need_bf = li > 0 or want_bf16_out
         g_new = ops.peg_bwd(g, s["x"], w["peg_w"], shape, dpw, dpb, dx_bf16=g_bf if need_bf else None)
         g = g_new
@@ -362,18 +360,21 @@ def _encode_backward(vit: "CTViT", params: List[torch.Tensor], ctx, dtokens: tor
 
     sp_g: List[Optional[torch.Tensor]] = [None] * (cfg.sd * N_PER_LAYER + 1)
     tp_g: List[Optional[torch.Tensor]] = [None] * (cfg.td * N_PER_LAYER + 1)
+    # every zero-initialised accumulation target of this backward pass comes out of one pre-filled buffer
+    arena = ops.ZeroArena(ops.ZeroArena.room(*(p.numel() for p in params), dim * cfg.K, ctx["table"].numel(),
+                                             *([dim] * 8)), dev)
     g, _ = _transformer_bwd(dy, bcast, tp, tp_norm, cfg, None, None, cfg.B * hw, cfg.t, 0, 0, (hw, cfg.t),
-                            ctx["tp_saved"], ctx["tp_fin"], tp_g, False)
-    dtable = torch.zeros_like(ctx["table"])
+                            ctx["tp_saved"], ctx["tp_fin"], tp_g, False, arena)
+    dtable = arena.take(ctx["table"].shape)
     g, _ = _transformer_bwd(g, None, sp, sp_norm, cfg, ctx["table"], dtable, cfg.B * cfg.t, hw, cfg.h, cfg.w,
-                            (cfg.t, hw), ctx["sp_saved"], ctx["sp_fin"], sp_g, False)
+                            (cfg.t, hw), ctx["sp_saved"], ctx["sp_fin"], sp_g, False, arena)
     # ---- patch embedding backward (no input gradient: the volume is data)
-    dg3, db3 = torch.zeros(dim, device=dev), torch.zeros(dim, device=dev)
+    dg3, db3 = arena.take(dim), arena.take(dim)
     dy0_bf = torch.empty(M, dim, dtype=torch.bfloat16, device=dev)
     dy0 = ops.layernorm_bwd(g, ctx["y0"], g3, ctx["mu0"], ctx["rs0"], dg3, db3, dx_bf16=dy0_bf)
-    dbp = torch.zeros(dim, device=dev)
+    dbp = arena.take(dim)
     ops.colsum_(dy0, dbp)
-    P = torch.zeros(dim, cfg.K, device=dev)
+    P = arena.take(dim, cfg.K)
     ops.gemm(dy0_bf, ctx["xhat"], ops.EPI_ATOMIC_F32, P, M=dim, N=cfg.K, K=M, mn_major=True, ldc=cfg.K)
     dwp, dg1, db1 = ops.patch_affine_bwd(P, wp, g1, b1, dbp)
     cpb_g = ops.cpb_bwd(dtable.reshape(cfg.heads, -1), cpb[0], cpb[2], cpb[4], ctx["h0"], ctx["h1"], cfg.h, cfg.w)
