@@ -276,17 +276,23 @@ int ctk_bert_embed_fwd(const long long* ids, const long long* token_type, const 
  * (otherwise the caller takes ctk_colsum of de into dtyp[0]). */
 int ctk_bert_embed_bwd(const float* de, const long long* ids, const long long* token_type, float* dword, float* dpos,
                        float* dtyp, long long M, int L, int H, long long pad_idx, void* stream);
-/* BertSelfAttention core, head dim 64: softmax(q k^T * scale + key mask) -> dropout(p_drop) -> . v on the packed bf16
- * projections qkv [B*L, 3*heads*64] (q | k | v, heads contiguous).  key_mask uint8 [B, L] (non-zero = attend) or NULL.
- * out bf16 [B*L, heads*64]; lse fp32 [B, heads, L] (natural log of the row sums of exp(scaled logits)).
+/* Softmax attention core on packed bf16 projections, head dim 64 (HF BertSelfAttention of the text tower) or 32
+ * (`FlashAttention` of CTViT3D, transformer_maskgit/attention.py:189-284): softmax(q k^T * scale + key mask) ->
+ * dropout(p_drop) -> . v on qkv [B*L, 3*heads*dh] (q | k | v, heads contiguous).  key_mask uint8 [B, L] (non-zero = attend)
+ * or NULL.  null_k / null_v bf16 [heads, n_null, dh] (n_null <= 64, may be 0 / NULL): learned null key/value pairs every
+ * query of every sequence also attends to (attention.py:240-248), processed as one extra key block.
+ * out bf16 [B*L, heads*dh]; lse fp32 [B, heads, L] (natural log of the row sums of exp(scaled logits)).
  * Dropout: element (b*heads + h, i, j) is kept iff hash(*seed_ptr + seed_off * c, ...) >= p * 2^32 (csrc/mha_dropout.cuh);
  * the seed is read from DEVICE memory so that CUDA-graph replays see a fresh value; the backward regenerates the mask.
  * mma.sync tensor-core kernels, flash-style (the L x L probabilities never leave registers), deterministic. */
-int ctk_mha_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int L, int heads, int dh,
-                float scale, float p_drop, const unsigned long long* seed_ptr, unsigned long long seed_off, void* stream);
-/* delta fp32 [B, heads, L] is workspace; dqkv bf16 [B*L, 3*heads*64] receives dq | dk | dv. */
-int ctk_mha_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout, const float* lse,
-                float* delta, void* dqkv, int B, int L, int heads, int dh, float scale, float p_drop,
+int ctk_mha_fwd(const void* qkv, const unsigned char* key_mask, const void* null_k, const void* null_v, int n_null,
+                void* out, float* lse, int B, int L, int heads, int dh, float scale, float p_drop,
+                const unsigned long long* seed_ptr, unsigned long long seed_off, void* stream);
+/* delta fp32 [B, heads, L] is workspace; dqkv bf16 [B*L, 3*heads*dh] receives dq | dk | dv; dnull_k / dnull_v fp32
+ * [B, heads, n_null, dh] receive the null pairs' gradients per sequence (the caller sums over B). */
+int ctk_mha_bwd(const void* qkv, const unsigned char* key_mask, const void* null_k, const void* null_v, int n_null,
+                const void* out, const void* dout, const float* lse, float* delta, void* dqkv, float* dnull_k,
+                float* dnull_v, int B, int L, int heads, int dh, float scale, float p_drop,
                 const unsigned long long* seed_ptr, unsigned long long seed_off, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -190,34 +190,55 @@ def mha_keep_mask(seed: int, nbh: int, L: int, p: float):
     return mha_hash(seed, bh, i, j) >= thresh
 
 
-def _mha_math(qkv, key_mask, B, L, heads, scale, p_drop, seed, seed_off):
+def _mha_math(qkv, key_mask, B, L, heads, scale, p_drop, seed, seed_off, null_k=None, null_v=None):
+    """fp32 softmax attention on the packed projections; null pairs [heads, n_null, dh] are extra keys every query sees
+    (appended here: the order of keys does not change a softmax; the kernels hash them at key index ceil(L/64)*64 + j)."""
     H = qkv.shape[1] // 3
     q, k, v = (qkv.float().view(B, L, 3, heads, H // heads)[:, :, t].transpose(1, 2) for t in range(3))
+    valid = torch.ones(B, 1, 1, L, dtype=torch.bool) if key_mask is None else (key_mask.view(B, 1, 1, L) != 0)
+    n_null = 0
+    if null_k is not None:
+        n_null = null_k.shape[1]
+        k = torch.cat([k, null_k.float()[None].expand(B, -1, -1, -1)], dim=2)
+        v = torch.cat([v, null_v.float()[None].expand(B, -1, -1, -1)], dim=2)
+        valid = torch.cat([valid, torch.ones(B, 1, 1, n_null, dtype=torch.bool)], dim=-1)
     sc = (q @ k.transpose(-1, -2)) * scale
-    if key_mask is not None:
-        sc = sc.masked_fill(key_mask.view(B, 1, 1, L) == 0, float("-inf"))
+    sc = sc.masked_fill(~valid, float("-inf"))
     lse = torch.logsumexp(sc, dim=-1)
     pr = torch.softmax(sc, dim=-1)
     if p_drop > 0:
+        assert n_null == 0, "the doubles restate the dropout mask for plain keys only"
         keep = mha_keep_mask(mha_seed(int(seed.item()) & 0xFFFFFFFFFFFFFFFF, seed_off), B * heads, L, p_drop)
         pr = pr * keep.view(B, heads, L, L).to(pr.dtype) / (1.0 - p_drop)
     return (pr @ v).transpose(1, 2).reshape(B * L, H), lse
 
 
-def mha_fwd(qkv, key_mask, B, L, heads, scale, p_drop=0.0, seed=None, seed_off=0):
+def mha_fwd(qkv, key_mask, B, L, heads, scale, p_drop=0.0, seed=None, seed_off=0, null_k=None, null_v=None):
     CALLS.append(("mha_fwd", p_drop))
     assert qkv.dtype == OPERAND
-    ctx, lse = _mha_math(qkv, key_mask, B, L, heads, scale, p_drop, seed, seed_off)
+    ctx, lse = _mha_math(qkv, key_mask, B, L, heads, scale, p_drop, seed, seed_off, null_k, null_v)
     return ctx.to(OPERAND), lse
 
 
-def mha_bwd(qkv, key_mask, out, dout, lse, B, L, heads, scale, p_drop=0.0, seed=None, seed_off=0):
+def mha_bwd(qkv, key_mask, out, dout, lse, B, L, heads, scale, p_drop=0.0, seed=None, seed_off=0, null_k=None, null_v=None):
     CALLS.append(("mha_bwd", p_drop))
     with torch.enable_grad():
         x = qkv.detach().float().requires_grad_(True)
-        ctx, _ = _mha_math(x, key_mask, B, L, heads, scale, p_drop, seed, seed_off)
-        (g,) = torch.autograd.grad(ctx, x, dout.float())
-    return g.to(OPERAND)
+        leaves = [x]
+        nk = nv = None
+        if null_k is not None:
+            nk = null_k.detach().float().requires_grad_(True)
+            nv = null_v.detach().float().requires_grad_(True)
+            leaves += [nk, nv]
+        ctx, _ = _mha_math(x, key_mask, B, L, heads, scale, p_drop, seed, seed_off, nk, nv)
+        grads = torch.autograd.grad(ctx, leaves, dout.float())
+    if null_k is None:
+        return grads[0].to(OPERAND)
+    # per-sequence slabs [B, heads, n_null, dh] as the kernel writes them: put the whole gradient in slab 0
+    dnk = torch.zeros(B, *null_k.shape)
+    dnv = torch.zeros(B, *null_v.shape)
+    dnk[0], dnv[0] = grads[1], grads[2]
+    return grads[0].to(OPERAND), dnk, dnv
 
 
 def colsum_(dy, out):

@@ -157,46 +157,84 @@ def test_ctclip_step_with_ctk_text_tower(cuda_dev):
 
 
 # ----------------------------------------------------------------------------- attention core (ctk_mha_fwd / ctk_mha_bwd)
-@pytest.mark.parametrize("B,L,heads,p_drop,padded", [(2, 512, 12, 0.0, True), (3, 200, 4, 0.0, True), (1, 64, 2, 0.0, False),
-                                                     (2, 37, 3, 0.0, True), (2, 256, 4, 0.1, True), (1, 130, 2, 0.5, False)])
-def test_mha_forward_backward(cuda_dev, B, L, heads, p_drop, padded):
-    """against fp32 softmax attention on the same bf16-rounded projections; the dropout mask of the reference is the
-    torch restatement of the kernels' hash (tests/emulated_ops.mha_keep_mask, pinned to csrc/mha_dropout.cuh on the CPU).
-    bf16 probabilities / outputs: 1e-2 relative L2 forward, 2e-2 backward; lse 1e-3 absolute."""
+@pytest.mark.parametrize("B,L,heads,dh,p_drop,padded,n_null", [
+    (2, 512, 12, 64, 0.0, True, 0), (3, 200, 4, 64, 0.0, True, 0), (1, 64, 2, 64, 0.0, False, 0), (2, 37, 3, 64, 0.0, True, 0),
+    (2, 256, 4, 64, 0.1, True, 0), (1, 130, 2, 64, 0.5, False, 0),
+    (2, 576, 8, 32, 0.0, False, 2), (1, 1500, 4, 32, 0.0, False, 2), (2, 100, 2, 32, 0.0, True, 5), (1, 256, 2, 32, 0.1, False, 0),
+    (1, 200, 2, 64, 0.0, False, 3)])
+def test_mha_forward_backward(cuda_dev, B, L, heads, dh, p_drop, padded, n_null):
+    """against fp32 softmax attention on the same bf16-rounded projections (head dim 64: text tower; head dim 32 with
+    learned null key/value pairs: CTViT3D's FlashAttention, attention.py:240-260); the dropout mask of the reference is
+    the torch restatement of the kernels' hash (tests/emulated_ops.mha_keep_mask, pinned to csrc/mha_dropout.cuh on the
+    CPU).  bf16 probabilities / outputs: 1e-2 relative L2 forward, 2e-2 backward; lse 1e-3 absolute."""
     import sys, os
     sys.path.insert(0, os.path.dirname(__file__))
     import emulated_ops as E
     from vit_exp_b200 import ops
-    H = heads * 64
-    qkv = (_rand((B * L, 3 * H), cuda_dev, 21) * 1.2).bfloat16()
+    H = heads * dh
+    qkv = (_rand((B * L, 3 * H), cuda_dev, 21) * (1.2 if dh == 64 else 2.0)).bfloat16()
     dout = _rand((B * L, H), cuda_dev, 22).bfloat16()
     mask = torch.ones(B, L, dtype=torch.uint8, device=cuda_dev)
     if padded:
         mask[0, L - L // 3:] = 0
         mask[B - 1, L // 2] = 0                       # a hole in the middle as well
+    nk = nv = None
+    if n_null:
+        nk = _rand((heads, n_null, dh), cuda_dev, 23, 1.5).bfloat16()
+        nv = _rand((heads, n_null, dh), cuda_dev, 24).bfloat16()
     seed = torch.tensor([987654321012345], dtype=torch.int64, device=cuda_dev)
-    scale = 0.125
-    ctx, lse = ops.mha_fwd(qkv, mask, B, L, heads, scale, p_drop, seed, 5)
-    dqkv = ops.mha_bwd(qkv, mask, ctx, dout, lse, B, L, heads, scale, p_drop, seed, 5)
+    scale = dh ** -0.5
+    ctx, lse = ops.mha_fwd(qkv, mask, B, L, heads, scale, p_drop, seed, 5, null_k=nk, null_v=nv)
+    res = ops.mha_bwd(qkv, mask, ctx, dout, lse, B, L, heads, scale, p_drop, seed, 5, null_k=nk, null_v=nv)
+    dqkv = res if n_null == 0 else res[0]
     torch.cuda.synchronize()
-    saved = E.OPERAND
-    try:
-        E.OPERAND = torch.bfloat16
-        x = qkv.cpu().float().requires_grad_(True)
-        ref, ref_lse = E._mha_math(x, mask.cpu(), B, L, heads, scale, p_drop, seed.cpu(), 5)
-        (gref,) = torch.autograd.grad(ref, x, dout.cpu().float())
-    finally:
-        E.OPERAND = saved
+    x = qkv.cpu().float().requires_grad_(True)
+    leaves = [x]
+    nkc = nvc = None
+    if n_null:
+        nkc, nvc = nk.cpu().float().requires_grad_(True), nv.cpu().float().requires_grad_(True)
+        leaves += [nkc, nvc]
+    ref, ref_lse = E._mha_math(x, mask.cpu(), B, L, heads, scale, p_drop, seed.cpu(), 5, nkc, nvc)
+    grefs = torch.autograd.grad(ref, leaves, dout.cpu().float())
+    gref = grefs[0]
     assert torch.isfinite(ctx.float()).all() and torch.isfinite(dqkv.float()).all()
     assert _rel(ctx.cpu(), ref) < 1e-2, _rel(ctx.cpu(), ref)
     assert (lse.cpu() - ref_lse).abs().max().item() < 1e-3
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
         err = _rel(dqkv.cpu()[:, sl], gref[:, sl])
         assert err < 2e-2, (name, err)
+    if n_null:
+        assert res[1].shape == (B, heads, n_null, dh)
+        assert _rel(res[1].sum(0).cpu(), grefs[1]) < 2e-2 and _rel(res[2].sum(0).cpu(), grefs[2]) < 2e-2
     # masked keys receive exactly zero gradient
     dead = (mask.cpu() == 0).reshape(-1)
     if dead.any():
         assert dqkv.cpu()[dead][:, H:].abs().max().item() == 0.0
+
+
+def test_mha_long_sequence_with_null_pairs_vs_sdpa(cuda_dev):
+    """CTViT3D's real shape: 13 824 tokens + 2 null pairs, 8 heads x 32 (attention.py:250-260).  Checker: torch's SDPA in
+    fp32 on the GPU (a library call used as the test's reference only), forward and all gradients."""
+    import torch.nn.functional as F
+    from vit_exp_b200 import ops
+    B, L, heads, dh, n_null = 1, 13824, 8, 32, 2
+    H = heads * dh
+    qkv = (_rand((B * L, 3 * H), cuda_dev, 31) * 1.5).bfloat16()
+    dout = _rand((B * L, H), cuda_dev, 32).bfloat16()
+    nk = _rand((heads, n_null, dh), cuda_dev, 33, 1.5).bfloat16()
+    nv = _rand((heads, n_null, dh), cuda_dev, 34).bfloat16()
+    ctx, lse = ops.mha_fwd(qkv, None, B, L, heads, 1.0, null_k=nk, null_v=nv)
+    dqkv, dnk, dnv = ops.mha_bwd(qkv, None, ctx, dout, lse, B, L, heads, 1.0, null_k=nk, null_v=nv)
+    x = qkv.float().requires_grad_(True)
+    nkf, nvf = nk.float().requires_grad_(True), nv.float().requires_grad_(True)
+    q, k, v = (x.view(B, L, 3, heads, dh)[:, :, t].transpose(1, 2) for t in range(3))
+    K = torch.cat([nkf[None].expand(B, -1, -1, -1), k], dim=2)
+    V = torch.cat([nvf[None].expand(B, -1, -1, -1), v], dim=2)
+    ref = F.scaled_dot_product_attention(q, K, V, scale=1.0).transpose(1, 2).reshape(B * L, H)
+    gx, gnk, gnv = torch.autograd.grad(ref, (x, nkf, nvf), dout.float())
+    assert _rel(ctx, ref) < 1e-2
+    assert _rel(dqkv, gx) < 2e-2
+    assert _rel(dnk.sum(0), gnk) < 2e-2 and _rel(dnv.sum(0), gnv) < 2e-2
 
 
 def test_mha_is_deterministic_and_seed_sensitive(cuda_dev):

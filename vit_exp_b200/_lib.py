@@ -71,8 +71,9 @@ SIGNATURES = {
     "ctk_transpose_cast_bf16_slice": (_i, [_vp, _vp, _ll, _ll, _ll, _vp]),
     "ctk_bert_embed_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "ctk_bert_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _vp]),
-    "ctk_mha_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, C.c_ulonglong, _vp]),
-    "ctk_mha_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, C.c_ulonglong, _vp]),
+    "ctk_mha_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, C.c_ulonglong, _vp]),
+    "ctk_mha_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp,
+                         C.c_ulonglong, _vp]),
     "ctk_volume_prep": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
 }
 

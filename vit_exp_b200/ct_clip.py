@@ -194,6 +194,7 @@ class CTCLIP(nn.Module):
         self.ctk_text_tower = bool(config.get("ctk_text_tower", os.environ.get("CTK_TEXT_TOWER", "1") == "1"))
         self._text_tower_note = None
         self._side_stream = None
+        self._enc_stream = None
         if self.fix_text_encoder:
             for p in self.text_transformer.parameters():
                 p.requires_grad = False
@@ -228,20 +229,39 @@ class CTCLIP(nn.Module):
         return self.ctk_text_tower and text_tower.unsupported_reason(bert, getattr(bert, "training", False)) is None
 
     def _encode_both(self, text, image):
-        """Both towers of one step.
+        """Both towers of one step, on two streams (results are identical to running them one after the other).
 
-        libctk text tower (the default for a HF BertModel): both towers are CUDA-graph replays, so nothing is gained
-        from a second stream (each fills the GPU); they run back to back on the current stream.  The text tower's
-        autograd node is created LAST, so its (short) backward runs FIRST: its gradients - 80 % of the bytes DDP has to
-        all-reduce - are complete ~4 ms into the backward pass and their buckets travel while the image encoder's
-        backward computes.  (With the tower on a side stream its AccumulateGrad copies queued on the default stream
-        behind the encoder's backward graph, and every all-reduce ended up exposed at the end of the step.)
+        libctk text tower (the default for a HF BertModel): both towers are CUDA-graph replays.  The IMAGE ENCODER goes
+        to a side stream and the text tower stays on the caller's stream, its autograd node created last:
+          * forward and backward of the two towers overlap (tensor-bound GEMMs of one next to the HBM-bound LayerNorm /
+            PEG kernels of the other);
+          * under DDP the text tower's gradients - 80 % of the bytes to all-reduce - are complete ~4 ms into the backward
+            pass, and their AccumulateGrad copies run on the caller's stream right behind the tower's backward graph, so
+            their buckets travel while the encoder's backward computes.  (The other way round - tower on the side
+            stream - those copies queued on the caller's stream behind the encoder's 22 ms backward graph and every
+            all-reduce ended up exposed at the end of the step: profiles/r2_ddp_timeline_n2.txt.)
+        CTK_TOWER_STREAMS=serial runs both on the caller's stream.
 
         Text encoder run as passed (stock PyTorch, hundreds of small launches): on a high-priority side stream next to
-        the image encoder; autograd replays each backward on the stream of its forward.  Results are identical."""
-        if self._text_on_ctk() or not (self.overlap_text_encoder and image.is_cuda):
+        the image encoder; autograd replays each backward on the stream of its forward."""
+        if not (self.overlap_text_encoder and image.is_cuda):
             enc_image = self.visual_transformer(image, return_encoded_tokens=True)
             return self._encode_text(text), enc_image
+        if self._text_on_ctk():
+            if os.environ.get("CTK_TOWER_STREAMS", "encoder_side") == "serial":
+                enc_image = self.visual_transformer(image, return_encoded_tokens=True)
+                return self._encode_text(text), enc_image
+            cur = torch.cuda.current_stream()
+            if self._enc_stream is None:
+                self._enc_stream = torch.cuda.Stream(device=image.device)
+            enc = self._enc_stream
+            enc.wait_stream(cur)
+            with torch.cuda.stream(enc):
+                enc_image = self.visual_transformer(image, return_encoded_tokens=True)
+            enc_text = self._encode_text(text)
+            cur.wait_stream(enc)
+            enc_image.record_stream(cur)
+            return enc_text, enc_image
         cur = torch.cuda.current_stream()
         if self._side_stream is None:
             # high priority: the tower's many small kernels are scheduled ahead of the encoder's persistent,

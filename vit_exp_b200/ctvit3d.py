@@ -8,13 +8,14 @@ fixed 3-D sin/cos position table, then 8 x [x += attn(x); x += ff(x)] over ALL 1
 null key/value pairs are prepended per head, l2norm and q/k scales apply to them too, the logit scale is
 1/sqrt(dim_head) (SDPA default) instead of 8, and the position bias is ignored (attention.py:257).
 
-What runs where: LayerNorm, the q / kv projections with the per-head l2norm*scale epilogue (1/sqrt(dh) folded into q),
-the output projection + residual, the GEGLU feed-forward and every gradient product run in libctk (the kernels
-validated for CTViT, at dim 768).  The attention core over 13 826 keys calls `F.scaled_dot_product_attention`
-(library flash kernel) for now: libctk's tcgen05 attention stages all keys of a sequence in shared memory, which
-fits the 576-token slices of CTViT but not 13 826 keys; a streaming-KV tcgen05 kernel is the next step (DESIGN.md
-section 9).  STATUS: written after round 1's GPU budget was spent; host logic checked on CPU against the pinned
-oracle (tests/test_ctvit3d_cpu.py), not yet run on hardware.
+What runs where: everything in libctk.  LayerNorm, the q / kv projections with the per-head l2norm*scale epilogue
+(1/sqrt(dh) folded into q), the output projection + residual, the GEGLU feed-forward and every gradient product are
+the kernels validated for CTViT, at dim 768; the attention core over the 2 null pairs + 13 824 tokens is
+`ctk_mha_fwd / ctk_mha_bwd` (csrc/attention_mha.cu, head dim 32: flash-style mma.sync kernels streaming 64-key blocks,
+the null pairs as one extra block, no 13 826-wide row ever stored).  libctk's tcgen05 attention keeps all keys of a
+sequence in shared memory, which fits the 576-token slices of CTViT but not 13 826 keys; a streaming-KV tcgen05 version
+is the follow-up.  Host logic checked on CPU against the oracle pinned to the reference module
+(tests/test_ctvit3d_cpu.py), kernels on the GPU (tests/test_ctvit3d_gpu.py).
 """
 from __future__ import annotations
 
@@ -108,35 +109,21 @@ def _null_kv(null_kv: torch.Tensor, k_scale: torch.Tensor, need_bwd: bool):
 
 
 def _attention(qkv, nk, nv, cfg: _Cfg3D, need_bwd: bool):
-    """packed qkv [M, 3*inner] (q pre-scaled by q_scale/sqrt(dh), k by k_scale) + null pairs -> context [M, inner]."""
-    B, n, h = cfg.B, cfg.n, cfg.heads
-    q5 = qkv.view(B, n, 3, h, 32)
-    q, k, v = (q5[:, :, i].transpose(1, 2) for i in range(3))                     # [B, h, n, 32] views
-    nkb = nk.detach().to(qkv.dtype)[None].expand(B, -1, -1, -1)
-    nvb = nv.detach().to(qkv.dtype)[None].expand(B, -1, -1, -1)
-    K = torch.cat([nkb, k], dim=2)                                                # null pairs first (attention.py:243)
-    V = torch.cat([nvb, v], dim=2)
-    if need_bwd:
-        with torch.enable_grad():
-            q, K, V = (t.detach().requires_grad_(True) for t in (q, K, V))
-            o = F.scaled_dot_product_attention(q, K, V, scale=1.0)
-    else:
-        o = F.scaled_dot_product_attention(q, K, V, scale=1.0)
-    ctx = o.detach().transpose(1, 2).reshape(cfg.M, cfg.inner).contiguous()
-    return ctx, ((q, K, V, o) if need_bwd else None)
+    """packed qkv [M, 3*inner] (q pre-scaled by q_scale/sqrt(dh), k by k_scale) + null pairs -> context [M, inner].
+    `FlashAttention` core (attention.py:250-260: SDPA over the 2 null pairs + 13 824 tokens, no mask, no bias) on
+    libctk's flash-style kernel (ctk_mha_fwd, head dim 32): the null pairs are one extra key block, the 13 826-wide
+    probability rows never leave registers."""
+    nkb = nk.detach().to(qkv.dtype).contiguous()
+    nvb = nv.detach().to(qkv.dtype).contiguous()
+    ctx, lse = ops.mha_fwd(qkv, None, cfg.B, cfg.n, cfg.heads, 1.0, null_k=nkb, null_v=nvb)
+    return ctx, ((qkv, nkb, nvb, ctx, lse) if need_bwd else None)
 
 
 def _attention_bwd(saved, dctx, cfg: _Cfg3D, n_null: int):
     """-> (dqkv [M, 3*inner] in the packed layout, d nk, d nv [heads, n_null, 32] fp32 summed over the batch)"""
-    q, K, V, o = saved
-    B, n, h = cfg.B, cfg.n, cfg.heads
-    do = dctx.view(B, n, h, 32).transpose(1, 2)
-    dq, dK, dV = torch.autograd.grad(o, (q, K, V), do)
-    dqkv = torch.empty(B, n, 3, h, 32, dtype=dctx.dtype, device=dctx.device)
-    dqkv[:, :, 0].copy_(dq.transpose(1, 2))
-    dqkv[:, :, 1].copy_(dK[:, :, n_null:].transpose(1, 2))
-    dqkv[:, :, 2].copy_(dV[:, :, n_null:].transpose(1, 2))
-    return dqkv.view(cfg.M, 3 * cfg.inner), dK[:, :, :n_null].float().sum(0), dV[:, :, :n_null].float().sum(0)
+    qkv, nkb, nvb, ctx, lse = saved
+    dqkv, dnk, dnv = ops.mha_bwd(qkv, None, ctx, dctx.contiguous(), lse, cfg.B, cfg.n, cfg.heads, 1.0, null_k=nkb, null_v=nvb)
+    return dqkv, dnk.sum(0), dnv.sum(0)
 
 
 def _forward(vit: "CTViT3D", video, params: List[torch.Tensor], save: bool):

@@ -449,29 +449,43 @@ def bert_embed_bwd(de, ids, token_type, word_shape, pos_shape, typ_shape, pad_id
     return dword, dpos, dtyp
 
 
-def mha_fwd(qkv, key_mask, B: int, L: int, heads: int, scale: float, p_drop: float = 0.0, seed=None, seed_off: int = 0):
-    """BertSelfAttention core (head dim 64) on the packed bf16 projections qkv [B*L, 3H]; key_mask uint8 [B, L] or None;
-    seed = int64 device tensor [1] (read by the kernel: graph replays see its current value).  Returns (ctx bf16 [B*L, H],
-    lse fp32 [B, heads, L])."""
+def mha_fwd(qkv, key_mask, B: int, L: int, heads: int, scale: float, p_drop: float = 0.0, seed=None, seed_off: int = 0,
+            null_k=None, null_v=None):
+    """Softmax attention core (head dim 64: BertSelfAttention; 32: CTViT3D's FlashAttention) on the packed bf16 projections
+    qkv [B*L, 3H]; key_mask uint8 [B, L] or None; null_k / null_v bf16 [heads, n_null, dh]: learned null pairs every query
+    also attends to; seed = int64 device tensor [1] (read by the kernel: graph replays see its current value).
+    Returns (ctx bf16 [B*L, H], lse fp32 [B, heads, L])."""
     _chk(qkv, torch.bfloat16, "qkv")
     H = qkv.shape[1] // 3
     assert qkv.shape == (B * L, 3 * H) and H % heads == 0
     assert key_mask is None or (key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.shape == (B, L))
     assert p_drop == 0.0 or (seed is not None and seed.dtype == torch.int64 and seed.is_cuda)
+    n_null = 0
+    if null_k is not None:
+        _chk(null_k, torch.bfloat16, "null_k"); _chk(null_v, torch.bfloat16, "null_v")
+        n_null = null_k.shape[1]
+        assert null_k.shape == (heads, n_null, H // heads) and null_v.shape == null_k.shape
     out = torch.empty(B * L, H, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(B, heads, L, dtype=torch.float32, device=qkv.device)
-    check(_lib.load().ctk_mha_fwd(_p(qkv), _p(key_mask), _p(out), _p(lse), B, L, heads, H // heads, scale, p_drop,
-                                  _p(seed), seed_off, _stream()), "ctk_mha_fwd")
+    check(_lib.load().ctk_mha_fwd(_p(qkv), _p(key_mask), _p(null_k), _p(null_v), n_null, _p(out), _p(lse), B, L, heads,
+                                  H // heads, scale, p_drop, _p(seed), seed_off, _stream()), "ctk_mha_fwd")
     return out, lse
 
 
 def mha_bwd(qkv, key_mask, out, dout, lse, B: int, L: int, heads: int, scale: float, p_drop: float = 0.0, seed=None,
-            seed_off: int = 0):
-    """dqkv bf16 [B*L, 3H] = (dq | dk | dv) of mha_fwd"""
+            seed_off: int = 0, null_k=None, null_v=None):
+    """dqkv bf16 [B*L, 3H] = (dq | dk | dv) of mha_fwd; with null pairs returns (dqkv, dnull_k, dnull_v) with the null
+    gradients fp32 [B, heads, n_null, dh] (one slab per sequence: sum over dim 0)."""
     _chk(dout, torch.bfloat16, "dout")
     H = qkv.shape[1] // 3
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
-    check(_lib.load().ctk_mha_bwd(_p(qkv), _p(key_mask), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, L, heads,
-                                  H // heads, scale, p_drop, _p(seed), seed_off, _stream()), "ctk_mha_bwd")
-    return dqkv
+    n_null, dnk, dnv = 0, None, None
+    if null_k is not None:
+        n_null = null_k.shape[1]
+        dnk = torch.empty(B, heads, n_null, H // heads, dtype=torch.float32, device=qkv.device)
+        dnv = torch.empty_like(dnk)
+    check(_lib.load().ctk_mha_bwd(_p(qkv), _p(key_mask), _p(null_k), _p(null_v), n_null, _p(out), _p(dout), _p(lse), _p(delta),
+                                  _p(dqkv), _p(dnk), _p(dnv), B, L, heads, H // heads, scale, p_drop, _p(seed), seed_off,
+                                  _stream()), "ctk_mha_bwd")
+    return dqkv if null_k is None else (dqkv, dnk, dnv)
