@@ -197,14 +197,23 @@ def run_ours(args):
     bert = clip.text_transformer
     model = clip
     if world > 1:
-        # find_unused_parameters=True as the reference trainer sets it (CTCLIPTrainer.py:318: pooler, *_extra projections
-        # and the cross-attention norms never get a gradient).  static_graph=True tells DDP that this set is the same
-        # every step, which removes its per-step all-reduce + device->host read of the used-parameter bitmap: that read
-        # is a host sync at the end of every backward pass and left the GPU idle for the ~2.6 ms of host time of
-        # optimizer.step() (profiles/r2_ddp_timeline_n2.txt).  --no-ddp-static-graph keeps the dynamic check.
-        model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], find_unused_parameters=True,
-                                                          gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb,
-                                                          static_graph=not args.no_ddp_static_graph)
+        # The reference trainer wraps with find_unused_parameters=True (CTCLIPTrainer.py:318) because the pooler, the
+        # *_extra projections, the first-frame / pixel heads and the cross-attention norms never get a gradient.  With
+        # that flag DDP all-reduces a used-parameter bitmap after every backward pass and reads it back on the host: a
+        # sync that leaves the GPU idle for the host time of optimizer.step() (profiles/r2_ddp_timeline_n2.txt).
+        #   --ddp ignore-unused (default): those parameters (CTCLIP.unused_parameter_names(), a fixed set) are handed to
+        #       DDP as ignored, and DDP runs with find_unused_parameters=False: no bitmap, no sync, buckets all-reduced
+        #       as soon as they fill.
+        #   --ddp find-unused: the reference's setting, unchanged.
+        #   --ddp static-graph: find_unused_parameters=True + static_graph=True (no sync either, but DDP then launches
+        #       every all-reduce at the end of the backward pass).
+        DDP = torch.nn.parallel.DistributedDataParallel
+        kw = dict(device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb)
+        if args.ddp == "ignore-unused":
+            DDP._set_params_and_buffers_to_ignore_for_model(clip, clip.unused_parameter_names())
+            model = DDP(clip, find_unused_parameters=False, **kw)
+        else:
+            model = DDP(clip, find_unused_parameters=True, static_graph=args.ddp == "static-graph", **kw)
     params = [p for p in clip.parameters() if p.requires_grad]
     if args.optimizer == "fused":        # clip_grad_norm_(0.5) + Adam in two libctk launches (vit_exp_b200/optim.py)
         from vit_exp_b200.optim import FusedClipAdam
@@ -281,7 +290,15 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     n0 = lib.ctk_launch_count() + ops.GRAPH_LAUNCHES
+    # CTK_BENCH_PROFILER_RANGE=1: cudaProfilerStart/Stop around the device-timed loop, so that
+    # `ncu --profile-from-start off ...` lists exactly the launches of the timed region (tools/ncu_round2.sh)
+    prof_range = os.environ.get("CTK_BENCH_PROFILER_RANGE") == "1"
+    if prof_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ms_dev, _ = timed(lambda k: [step(i % 2) for i in range(k)], args.steps)
+    if prof_range:
+        torch.cuda.profiler.stop()
     launches = (lib.ctk_launch_count() + ops.GRAPH_LAUNCHES - n0)      # direct launches + launches replayed from CUDA graphs
     clocks = sampler.stop() if rank == 0 else None
 
@@ -331,11 +348,22 @@ def run_ours(args):
     stored = [(v[:, 0] * 2 - 1).half().pin_memory() for v in host_vid]          # (B, D, H, W) stored arrays
     dev_stored = [torch.empty(B, *VOL, dtype=torch.float16, device=dev) for _ in range(NSLOT)]
 
+    prep_stream = torch.cuda.Stream()
+
     def feed_stored(slot, src):
+        # called under copy_stream.  ONE copy of the whole stored batch (at 4-8 GPUs the host delivers ~25 % less per GPU
+        # when the same bytes arrive as eight per-volume copies), then the preparation kernels on their own stream behind
+        # an event: on the copy stream they would wait for SMs behind the train step's persistent kernels and hold up
+        # the next transfer with them.
         dev_ids[slot].copy_(host_ids[src], non_blocking=True)
-        for b in range(B):
-            dev_stored[slot][b].copy_(stored[src][b], non_blocking=True)
-            ops.volume_prep(dev_stored[slot][b], dev_vid[slot][b])
+        dev_stored[slot].copy_(stored[src], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        with torch.cuda.stream(prep_stream):
+            prep_stream.wait_event(ev)
+            for b in range(B):
+                ops.volume_prep(dev_stored[slot][b], dev_vid[slot][b])
+        copy_stream.wait_stream(prep_stream)            # "batch staged" = copy and preparation done
 
     pipeline(0, feed_stored, prime_only=True)
     pipeline(2, feed_stored)                                # first use of the prep kernel / slots
@@ -395,8 +423,8 @@ def run_ours(args):
                                "480x480x240) + random-init BERT-base text tower + all-gathered InfoNCE + clip 0.5 + Adam",
                    "per_gpu_batch": B, "global_batch": B * world, "text_len": TEXT_LEN, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (1.77 GB of volumes per step); two alternating batches",
-                   "e2e_pipeline": "host batch (pinned, stored float16 volumes) -> per-volume H2D + ctk_volume_prep on a side "
-                                   "stream into one of 3 device slots while the previous step computes; loss read back "
+                   "e2e_pipeline": "host batch (pinned, stored float16 volumes) -> H2D (copy stream) + ctk_volume_prep per volume "
+                                   "(second side stream) into one of 3 device slots while the previous step computes; loss read back "
                                    "every step; software-pipelined by one batch: the timed region holds K steps and the K "
                                    "transfers of batches 1..K (batch 0 is staged before the clock starts)",
                    "text_tower": (("BertModel parameters through libctk (vit_exp_b200/text_tower.py)"
@@ -406,8 +434,7 @@ def run_ours(args):
                                 "config['defer_loss_read']: async D2H copy, read every step after the step is enqueued",
                    "launch": "encoder and text tower forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
                              else "eager launches",
-                   "ddp": None if world == 1 else f"find_unused_parameters=True, gradient_as_bucket_view=True, bucket_cap_mb="
-                                                  f"{args.bucket_mb}, static_graph={not args.no_ddp_static_graph}"},
+                   "ddp": None if world == 1 else f"{args.ddp}, gradient_as_bucket_view=True, bucket_cap_mb={args.bucket_mb}"},
         "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s",
                 "h2d_bytes_per_step": int(host_vid[0].numel() * 2 + host_ids[0].numel() * 8), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
@@ -595,8 +622,8 @@ def main():
     ap.add_argument("--no-torch-eager", action="store_true",
                     help="skip the informational torch_eager_gpu leg (oracle port + HF BertModel as plain PyTorch eager ops on this GPU)")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (MB)")
-    ap.add_argument("--no-ddp-static-graph", action="store_true",
-                    help="DDP re-discovers the unused parameters every step (a host sync at the end of each backward pass)")
+    ap.add_argument("--ddp", default="ignore-unused", choices=["ignore-unused", "find-unused", "static-graph"],
+                    help="how DDP deals with the parameters that never get a gradient (see run_ours)")
     ap.add_argument("--sync-loss-read", action="store_true",
                     help="CTCLIP returns cl_loss via loss.item() inside forward (reference behaviour: a host sync between "
                          "forward and backward); default: config['defer_loss_read'], the same value read back at the end of the step")

@@ -115,3 +115,28 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_unused_parameter_names_are_exactly_the_gradient_free_ones():
+    """CTCLIP.unused_parameter_names() (what bench.py hands to DDP as ignored parameters) = SURVEY appendix C: every name
+    exists, covers the first-frame / pixel heads, cross-attention norms, empty null_kv, BERT pooler and *_extra
+    projections, and nothing the backward pass produces a gradient for."""
+    from transformers import BertConfig, BertModel
+    from vit_exp_b200.ct_clip import CTCLIP
+    from vit_exp_b200.transformer_maskgit import CTViT
+    vit = CTViT(dim=64, codebook_size=32, image_size=(8, 8), patch_size=(4, 4), temporal_patch_size=2, spatial_depth=1,
+                temporal_depth=1, dim_head=32, heads=2)
+    bert = BertModel(BertConfig(vocab_size=50, hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256))
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=128, dim_image=64, dim_latent=16, config={})
+    names = clip.unused_parameter_names()
+    all_names = dict(clip.named_parameters())
+    assert len(set(names)) == len(names) and all(n in all_names for n in names)
+    for frag in ("to_patch_emb_first_frame.", "to_pixels.", "to_pixels_first_frame.", "context_norm.gamma", "null_kv", "pooler.dense.",
+                 "to_text_latent_extra.weight", "to_visual_latent_extra.weight"):
+        assert any(frag in n for n in names), frag
+    used = {id(p) for p in vit._flat_params()}
+    for n in names:
+        assert id(all_names[n]) not in used
+    for n in all_names:       # everything else is on the gradient path: encoder flat params, BERT minus pooler, the head
+        if n not in names:
+            assert n.startswith(("visual_transformer.", "text_transformer.")) or n in ("to_text_latent.weight", "to_visual_latent.weight", "temperature")

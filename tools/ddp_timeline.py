@@ -22,9 +22,14 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 B = 8
 clip = bench.build_model(dev, config={"defer_loss_read": True}).train()
-model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], find_unused_parameters=True,
-                                                  gradient_as_bucket_view=True, bucket_cap_mb=int(os.environ.get("BUCKET_MB", "25")),
-                                                  static_graph=os.environ.get("STATIC_GRAPH", "1") == "1")
+DDP = torch.nn.parallel.DistributedDataParallel
+mode = os.environ.get("DDP_MODE", "ignore-unused")
+kw = dict(device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=int(os.environ.get("BUCKET_MB", "25")))
+if mode == "ignore-unused":
+    DDP._set_params_and_buffers_to_ignore_for_model(clip, clip.unused_parameter_names())
+    model = DDP(clip, find_unused_parameters=False, **kw)
+else:
+    model = DDP(clip, find_unused_parameters=True, static_graph=mode == "static-graph", **kw)
 params = [p for p in clip.parameters() if p.requires_grad]
 opt = FusedClipAdam(params, lr=1.25e-6, betas=(0.9, 0.99), max_grad_norm=0.5)
 acc = TorchDistAccelerator()

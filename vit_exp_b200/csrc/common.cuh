@@ -1,6 +1,7 @@
 // Shared device/host helpers for the ctk (CT-CLIP kernels) library: error plumbing,
 // mbarrier / TMA / tcgen05 PTX wrappers for sm_100a, small math utilities.
 #pragma once
+#include <stdlib.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -81,6 +82,21 @@ static inline int ctk_num_sms() {
         n[slot] = v > 0 ? v : 148;
     }
     return n[slot];
+}
+// SMs the persistent kernels may fill.  CTK_GEMM_RESERVE_SMS=n leaves n SMs (rounded to CTA pairs) to co-running work:
+// the tcgen05 GEMM partitions its tiles statically over its CTAs, so a CTA that cannot start because NCCL's kernels
+// hold its SM delays the whole launch by that CTA's full share (multi-GPU runs: gradient all-reduces overlap the
+// encoder's backward).
+static inline int ctk_gemm_sms() {
+    static int reserve = -1;
+    if (reserve < 0) {
+        const char* e = getenv("CTK_GEMM_RESERVE_SMS");
+        reserve = e ? atoi(e) : 0;
+        if (reserve < 0 || reserve > 64) reserve = 0;
+    }
+    int n = ctk_num_sms() - reserve;
+    n &= ~1;
+    return n < 2 ? 2 : n;
 }
 // opt a kernel into `bytes` of dynamic shared memory, once per device
 #define CTK_SET_MAX_SMEM(kern, bytes)                                                                          \

@@ -788,7 +788,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc0,
     CTK_SET_MAX_SMEM(kern, SMEM_BYTES);
     const int rows = PAIR ? 2 * BM : BM;
     const long long work = (long long)((M + rows - 1) / rows) * ((N + BN - 1) / BN) * splits;
-    const int sms = ctk_num_sms();
+    const int sms = ctk_gemm_sms();
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     if (PAIR) {
@@ -862,7 +862,7 @@ extern "C" int ctk_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     } else if (splits <= 0) {
         const int rows_item = (M > BM) ? 2 * BM : BM;     // CTA pairs own 256 rows
         splits = pick_splits((long long)((M + rows_item - 1) / rows_item) * ((N + BN - 1) / BN), kb_total,
-                             M > BM ? ctk_num_sms() / 2 : ctk_num_sms());
+                             M > BM ? ctk_gemm_sms() / 2 : ctk_gemm_sms());
     }
     if (splits > kb_total) splits = kb_total;
     {   // every split must own at least one k-block

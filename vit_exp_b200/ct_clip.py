@@ -224,6 +224,22 @@ class CTCLIP(nn.Module):
                       flush=True)
         return self.text_transformer(text.input_ids, attention_mask=text.attention_mask)[0]
 
+    def unused_parameter_names(self):
+        """Names (relative to this module) of the parameters that never receive a gradient on the contrastive path -
+        the reason the reference wraps the model with `find_unused_parameters=True` (CTCLIPTrainer.py:318; SURVEY
+        appendix C): the first-frame / pixel heads and cross-attention norms of the image encoder, the text encoder's
+        pooler, the `*_latent_extra` projections.  A caller may hand them to
+        `DistributedDataParallel._set_params_and_buffers_to_ignore_for_model` and run DDP with
+        `find_unused_parameters=False`, which removes DDP's per-step used-parameter bitmap all-reduce and host read."""
+        vt = self.visual_transformer
+        names = []
+        if hasattr(vt, "_flat_params"):
+            used = {id(p) for p in vt._flat_params()}
+            names += [f"visual_transformer.{n}" for n, p in vt.named_parameters() if id(p) not in used]
+        names += [f"text_transformer.{n}" for n, _ in self.text_transformer.named_parameters() if n.startswith("pooler.")]
+        names += ["to_text_latent_extra.weight", "to_visual_latent_extra.weight"]
+        return names
+
     def _text_on_ctk(self) -> bool:
         bert = self.text_transformer
         return self.ctk_text_tower and text_tower.unsupported_reason(bert, getattr(bert, "training", False)) is None

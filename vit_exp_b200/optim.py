@@ -22,7 +22,7 @@ class FusedClipAdam(torch.optim.Optimizer):
       `.grad` is None are skipped, as torch does.
     * `step()` returns the total gradient norm before clipping as a 0-d device tensor (what
       clip_grad_norm_ returns); nothing is synchronised with the host.
-    * the step count lives in `state[p]["step"]` (a 0-d fp32 CPU tensor, as torch.optim.Adam keeps it), so
+    * the step count lives in `state[p]["step"]` (torch.optim.Adam's key; a plain int here), so
       state_dict() / load_state_dict() round-trip the bias correction and the state is interchangeable with
       torch.optim.Adam's; parameters that joined later (first gradient at a later step) get their own launch.
     * `write_clipped_grads=True` also writes the scaled gradients back to `.grad` (clip_grad_norm_ does;
@@ -55,11 +55,13 @@ class FusedClipAdam(torch.optim.Optimizer):
             assert p.is_contiguous() and g.is_contiguous()
             st = self.state[p]
             if not st:
-                st["step"] = torch.zeros((), dtype=torch.float32)
+                st["step"] = 0
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            st["step"] += 1
-            by_step.setdefault(int(st["step"]), []).append(
+            # a plain number (torch.optim.Adam accepts one when it loads a state dict; a state loaded from torch's Adam
+            # arrives as a 0-d tensor and is converted here): a tensor increment per parameter cost 1.5 ms of host time
+            step = st["step"] = int(st["step"]) + 1
+            by_step.setdefault(step, []).append(
                 (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()))
         return by_step
 
