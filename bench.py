@@ -429,7 +429,7 @@ def run_ours(args):
                                    "transfers of batches 1..K (batch 0 is staged before the clock starts)",
                    "text_tower": (("BertModel parameters through libctk (vit_exp_b200/text_tower.py)"
                                    if args.text_tower == "ctk" else "stock PyTorch BertModel under bf16 autocast")
-                                  + f", dropout {args.text_dropout} (CXR-BERT ships 0.1; the CPU arm uses 0)"),
+                                  + f", hidden / attention dropout {args.text_dropout} (CXR-BERT ships 0.1; the CPU arm runs without)"),
                    "loss_read": "loss.item() inside forward" if args.sync_loss_read else
                                 "config['defer_loss_read']: async D2H copy, read every step after the step is enqueued",
                    "launch": "encoder and text tower forward/backward replayed from CUDA graphs" if clip.visual_transformer.cuda_graphs
@@ -629,8 +629,9 @@ def main():
                          "forward and backward); default: config['defer_loss_read'], the same value read back at the end of the step")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: libctk clip+Adam (2 launches); torch: clip_grad_norm_ + torch.optim.Adam(fused=True)")
-    ap.add_argument("--text-dropout", type=float, default=0.0,
-                    help="hidden / attention dropout of the random-init BERT-base text tower (CXR-BERT's config has 0.1)")
+    ap.add_argument("--text-dropout", type=float, default=0.1,
+                    help="hidden / attention dropout of the random-init BERT-base text tower: 0.1 as CXR-BERT's config ships "
+                         "and the reference trains with (the tower is in train mode); 0 switches it off")
     ap.add_argument("--text-tower", default="ctk", choices=["hf", "ctk"],
                     help="ctk: the BertModel's forward/backward run through libctk (vit_exp_b200/text_tower.py, CUDA-graph "
                          "replay); hf: the module runs as passed (stock PyTorch under bf16 autocast)")

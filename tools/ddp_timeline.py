@@ -75,6 +75,50 @@ if rank == 0:
         n = e["name"]
         if "nccl" in n.lower() or "multi_adam" in n or "multi_sqnorm" in n or "patch_norm" in n or "clip_grad_tiles" in n:
             print(f"  t={(e['ts'] - t0) / 1e3:8.3f} ms dur={e['dur'] / 1e3:7.3f} ms stream {e['args'].get('stream')}  {n[:80]}")
+    # per stream: busy segments (activities closer than 0.3 ms merged) with their three most frequent kernels
+    import collections
+    for sid, lst in sorted(streams.items(), key=lambda kv: -sum(x["dur"] for x in kv[1])):
+        print(f"segments of stream {sid} (first 45 ms):")
+        seg = None
+        segs = []
+        for e in lst:
+            if seg is not None and e["ts"] - seg["end"] < 300:
+                seg["end"] = max(seg["end"], e["ts"] + e["dur"])
+                seg["names"][e["name"][:46]] += 1
+            else:
+                seg = {"start": e["ts"], "end": e["ts"] + e["dur"], "names": collections.Counter({e["name"][:46]: 1})}
+                segs.append(seg)
+        for g in segs:
+            if (g["start"] - t0) / 1e3 > 45:
+                break
+            top = ", ".join(f"{n} x{c}" for n, c in g["names"].most_common(3))
+            print(f"  {(g['start'] - t0) / 1e3:7.2f} - {(g['end'] - t0) / 1e3:7.2f} ms  {sum(g['names'].values()):4d} act  {top}")
+    print("1 ms bins of the SECOND profiled step: DtoD copies (gradient -> bucket) | NCCL all-reduces | text-tower backward kernels (mha_bwd) | encoder GEMMs")
+    starts = [e["ts"] for e in ev if "patch_norm" in e["name"]]
+    t1 = starts[1] if len(starts) > 1 else t0
+    bins = collections.defaultdict(lambda: [0, 0, 0, 0])
+    for e in ev:
+        if e["ts"] < t1:
+            continue
+        b = int((e["ts"] - t1) / 1e3)
+        if b >= 46:
+            break
+        n = e["name"]
+        if "DtoD" in n:
+            bins[b][0] += 1
+        elif "AllReduce" in n:
+            bins[b][1] += 1
+        elif "mha_bwd" in n:
+            bins[b][2] += 1
+        elif "gemm_kernel" in n:
+            bins[b][3] += 1
+    for b in range(46):
+        print(f"  {b:3d} ms: {bins[b][0]:4d} | {bins[b][1]:3d} | {bins[b][2]:3d} | {bins[b][3]:3d}")
+    try:
+        info = model._get_ddp_logging_data()
+        print("ddp buckets:", info.get("rebuilt_bucket_sizes") or info.get("bucket_sizes"), "| has_rebuilt_buckets", info.get("has_rebuilt_buckets"))
+    except Exception as e:
+        print("no ddp logging data:", e)
     # idle gaps: no activity on any stream
     end, prev = ev[0]["ts"], ev[0]
     print("all-stream idle gaps > 0.2 ms:")

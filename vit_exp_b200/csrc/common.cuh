@@ -167,6 +167,40 @@ __device__ __forceinline__ void normal_cdf_pdf(float g, float& cdf, float& pdf) 
     pdf = 0.39894228040143268f * e;
 }
 
+// ---- packed fp32 (two lanes per instruction: fma.rn.f32x2 issues one FFMA2 for two FMAs) ----------
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 f2_set(float v) { return make_float2(v, v); }
+// normal_cdf_pdf for two values at once: the polynomial and the scalings run as packed fp32 instructions, the two
+// ex2 / rcp stay scalar SFU operations.  Same formula, same accuracy.
+__device__ __forceinline__ void normal_cdf_pdf2(float2 g, float2& cdf, float2& pdf) {
+    const float2 ax = f2_mul(make_float2(fabsf(g.x), fabsf(g.y)), f2_set(0.70710678118654752f));
+    const float2 arg = f2_mul(f2_mul(ax, ax), f2_set(-1.4426950408889634f));
+    const float2 den = f2_fma(f2_set(0.3275911f), ax, f2_set(1.0f));
+    float2 e, t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+    float2 poly = f2_fma(f2_set(1.061405429f), t, f2_set(-1.453152027f));
+    poly = f2_fma(poly, t, f2_set(1.421413741f));
+    poly = f2_fma(poly, t, f2_set(-0.284496736f));
+    poly = f2_fma(poly, t, f2_set(0.254829592f));
+    const float2 ht = f2_mul(f2_mul(poly, t), f2_mul(e, f2_set(0.5f)));         // 0.5 * (1 - erf(|x|))
+    cdf.x = g.x >= 0.f ? 1.0f - ht.x : ht.x;
+    cdf.y = g.y >= 0.f ? 1.0f - ht.y : ht.y;
+    pdf = f2_mul(e, f2_set(0.39894228040143268f));
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }

@@ -257,10 +257,13 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
             slot_write_bf16(sg.base, lane, val);
             slot_write_bf16(sg.base + SLOT_BYTES, lane, gate);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float cdf, pdf;
-                normal_cdf_pdf(gate[i], cdf, pdf);
-                val[i] = gate[i] * cdf * val[i];                 // gelu(gate) * value
+            for (int i = 0; i < 32; i += 2) {                    // packed fp32: two hidden units per instruction
+                const float2 g2 = make_float2(gate[i], gate[i + 1]);
+                float2 cdf, pdf;
+                normal_cdf_pdf2(g2, cdf, pdf);
+                const float2 h2 = f2_mul(f2_mul(g2, cdf), make_float2(val[i], val[i + 1]));   // gelu(gate) * value
+                val[i] = h2.x;
+                val[i + 1] = h2.y;
             }
             slot_write_bf16(sg.base + 2 * SLOT_BYTES, lane, val);
             sg.fence();
@@ -297,13 +300,15 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
                 slot_read_bf16(sv, lane, val);
                 slot_read_bf16(sgt, lane, gate);
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    float cdf, pdf;
-                    normal_cdf_pdf(gate[q], cdf, pdf);
-                    const float dv = dh[q] * gate[q] * cdf;                          // dh * gelu(gate)
-                    const float dg = dh[q] * val[q] * fmaf(gate[q], pdf, cdf);       // dh * value * gelu'(gate)
-                    val[q] = dv;
-                    gate[q] = dg;
+                for (int q = 0; q < 32; q += 2) {               // packed fp32: two hidden units per instruction
+                    const float2 g2 = make_float2(gate[q], gate[q + 1]), v2 = make_float2(val[q], val[q + 1]);
+                    const float2 d2 = make_float2(dh[q], dh[q + 1]);
+                    float2 cdf, pdf;
+                    normal_cdf_pdf2(g2, cdf, pdf);
+                    const float2 dv = f2_mul(f2_mul(d2, g2), cdf);                   // dh * gelu(gate)
+                    const float2 dg = f2_mul(f2_mul(d2, v2), f2_fma(g2, pdf, cdf));  // dh * value * gelu'(gate)
+                    val[q] = dv.x; val[q + 1] = dv.y;
+                    gate[q] = dg.x; gate[q + 1] = dg.y;
                 }
                 slot_write_bf16(sv, lane, val);
                 slot_write_bf16(sgt, lane, gate);
@@ -333,10 +338,13 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
                 uint8_t* su = sg.base + (2 * h2) * SLOT_BYTES;
                 slot_write_bf16(su, lane, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float cdf, pdf;
-                    normal_cdf_pdf(v[i], cdf, pdf);
-                    v[i] *= cdf;
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 u2 = make_float2(v[i], v[i + 1]);
+                    float2 cdf, pdf;
+                    normal_cdf_pdf2(u2, cdf, pdf);
+                    const float2 g2 = f2_mul(u2, cdf);
+                    v[i] = g2.x;
+                    v[i + 1] = g2.y;
                 }
                 slot_write_bf16(su + SLOT_BYTES, lane, v);
                 sg.fence();
@@ -368,10 +376,13 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& p, const CUtensorM
                 uint8_t* slot = sg.base + (par * 2) * SLOT_BYTES;
                 slot_read_bf16(slot, lane, u);
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    float cdf, pdf;
-                    normal_cdf_pdf(u[q], cdf, pdf);
-                    dg[q] *= fmaf(u[q], pdf, cdf);           // gelu'(u) = Phi(u) + u phi(u)
+                for (int q = 0; q < 32; q += 2) {
+                    const float2 u2 = make_float2(u[q], u[q + 1]);
+                    float2 cdf, pdf;
+                    normal_cdf_pdf2(u2, cdf, pdf);
+                    const float2 r2 = f2_mul(make_float2(dg[q], dg[q + 1]), f2_fma(u2, pdf, cdf));   // gelu'(u) = Phi(u) + u phi(u)
+                    dg[q] = r2.x;
+                    dg[q + 1] = r2.y;
                 }
                 slot_write_bf16(slot, lane, dg);
                 sg.fence();

@@ -195,6 +195,7 @@ class CTCLIP(nn.Module):
         self._text_tower_note = None
         self._side_stream = None
         self._enc_stream = None
+        self._txt_stream = None
         if self.fix_text_encoder:
             for p in self.text_transformer.parameters():
                 p.requires_grad = False
@@ -247,15 +248,16 @@ class CTCLIP(nn.Module):
     def _encode_both(self, text, image):
         """Both towers of one step, on two streams (results are identical to running them one after the other).
 
-        libctk text tower (the default for a HF BertModel): both towers are CUDA-graph replays.  The IMAGE ENCODER goes
-        to a side stream and the text tower stays on the caller's stream, its autograd node created last:
+        libctk text tower (the default for a HF BertModel): both towers are CUDA-graph replays, each on its own side
+        stream - the text tower's with high priority - and the tower's autograd node is created last:
           * forward and backward of the two towers overlap (tensor-bound GEMMs of one next to the HBM-bound LayerNorm /
             PEG kernels of the other);
-          * under DDP the text tower's gradients - 80 % of the bytes to all-reduce - are complete ~4 ms into the backward
-            pass, and their AccumulateGrad copies run on the caller's stream right behind the tower's backward graph, so
-            their buckets travel while the encoder's backward computes.  (The other way round - tower on the side
-            stream - those copies queued on the caller's stream behind the encoder's 22 ms backward graph and every
-            all-reduce ended up exposed at the end of the step: profiles/r2_ddp_timeline_n2.txt.)
+          * under DDP the text tower's gradients - 80 % of the bytes to all-reduce - are complete a few ms into the
+            backward pass; their AccumulateGrad copies run on the caller's stream, which is idle during the backward
+            pass, so their buckets travel while the encoder's backward computes.  (Tower on a side stream and the encoder
+            on the caller's stream, round 1's arrangement: those copies queued behind the encoder's 22 ms backward graph.
+            Tower on the caller's stream without priority: its backward was starved by the encoder's persistent kernels
+            and finished with it.  Either way every all-reduce was exposed at the end of the step.)
         CTK_TOWER_STREAMS=serial runs both on the caller's stream.
 
         Text encoder run as passed (stock PyTorch, hundreds of small launches): on a high-priority side stream next to
@@ -270,13 +272,22 @@ class CTCLIP(nn.Module):
             cur = torch.cuda.current_stream()
             if self._enc_stream is None:
                 self._enc_stream = torch.cuda.Stream(device=image.device)
-            enc = self._enc_stream
+                # high priority: whenever an SM frees up the tower's kernels are scheduled ahead of the encoder's
+                # persistent ones.  Without it the tower's 3.5 ms backward is stretched over the encoder's whole 24 ms
+                # backward pass and its gradient buckets leave as late as the encoder's (profiles/r2_ddp_timeline_n2.txt)
+                prio = -1 if os.environ.get("CTK_TEXT_STREAM_PRIORITY", "1") != "0" else 0
+                self._txt_stream = torch.cuda.Stream(device=image.device, priority=prio)
+            enc, txt = self._enc_stream, self._txt_stream
             enc.wait_stream(cur)
+            txt.wait_stream(cur)
             with torch.cuda.stream(enc):
                 enc_image = self.visual_transformer(image, return_encoded_tokens=True)
-            enc_text = self._encode_text(text)
+            with torch.cuda.stream(txt):
+                enc_text = self._encode_text(text)          # autograd node created last: its backward is launched first
             cur.wait_stream(enc)
+            cur.wait_stream(txt)
             enc_image.record_stream(cur)
+            enc_text.record_stream(cur)
             return enc_text, enc_image
         cur = torch.cuda.current_stream()
         if self._side_stream is None:

@@ -307,6 +307,20 @@ def _graphs_enabled() -> bool:
     return os.environ.get("CTK_TEXT_GRAPHS", "1") != "0"
 
 
+_CAPTURE_STREAM: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+def _capture_stream(dev: torch.device):
+    """Graph kernel nodes keep the priority of the stream they were CAPTURED on.  The tower runs next to the image
+    encoder's persistent kernels and must win the SMs that free up (ct_clip.py: _encode_both), so its graphs are
+    captured on a high-priority stream (CTK_TEXT_STREAM_PRIORITY=0: default priority)."""
+    st = _CAPTURE_STREAM.get(dev)
+    if st is None:
+        prio = -1 if os.environ.get("CTK_TEXT_STREAM_PRIORITY", "1") != "0" else 0
+        st = _CAPTURE_STREAM[dev] = torch.cuda.Stream(device=dev, priority=prio)
+    return st
+
+
 def _graph_forward(bert, s: _Shape, plist, input_ids, attention_mask, token_type_ids):
     """Replay (capturing on first use) the forward graph for these inputs.  Returns None when this call must run on
     eager launches, else dict(out, eg, token)."""
@@ -335,7 +349,8 @@ def _graph_forward(bert, s: _Shape, plist, input_ids, attention_mask, token_type
                       tt=None if token_type_ids is None else token_type_ids.clone())
             if s.p_attn > 0:
                 _next_seed(dev)                    # create the device counter outside the capture
-            g, outs, n = _capture(lambda: _forward(s, plist, st["ids"], st["tt"], st["mask"], True), eg.pool)
+            g, outs, n = _capture(lambda: _forward(s, plist, st["ids"], st["tt"], st["mask"], True), eg.pool,
+                                  _capture_stream(dev))
             eg.fwd = dict(graph=g, outs=outs, launches=n, st=st)
         except Exception as e:                                                  # pragma: no cover
             import warnings
@@ -365,7 +380,8 @@ def _graph_backward(eg: _TowerGraph, token: _Token, s: _Shape, plist, dout):
         _, saved, emb_saved = f["outs"]
         st = f["st"]
         # _backward drops its references to the saved activations layer by layer: hand it a copy of the list
-        g, grads, n = _capture(lambda: _backward(s, plist, st["ids"], st["tt"], list(saved), emb_saved, dstat), eg.pool)
+        g, grads, n = _capture(lambda: _backward(s, plist, st["ids"], st["tt"], list(saved), emb_saved, dstat), eg.pool,
+                               _capture_stream(dstat.device))
         eg.bwd = dict(graph=g, grads=grads, launches=n, dout=dstat)
     b = eg.bwd
     b["dout"].copy_(dout.reshape(s.B, s.L, s.H))

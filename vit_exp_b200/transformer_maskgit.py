@@ -423,15 +423,17 @@ def _graph_key(video, training, params, embed):
     return (tuple(video.shape), bool(training), tuple(p.data_ptr() for p in params), embed.data_ptr())
 
 
-def _capture(fn, pool):
-    """capture fn() into a CUDA graph (nothing executes during capture); returns (graph, outputs, launches)"""
+def _capture(fn, pool, stream=None):
+    """capture fn() into a CUDA graph (nothing executes during capture); returns (graph, outputs, launches).
+    `stream`: capture stream - kernel nodes inherit ITS priority, not that of the stream the graph is later launched on."""
     from . import _lib
     lib = _lib.load()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     n0 = lib.ctk_launch_count()
+    kw = {} if stream is None else {"stream": stream}
     # thread_local: NCCL's watchdog / other streams' threads keep issuing CUDA calls while we capture
-    with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+    with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local", **kw):
         out = fn()
     return g, out, int(lib.ctk_launch_count() - n0)
 
