@@ -74,10 +74,14 @@ def emit(line):
 
 def gemm_traffic_sample():
     """Per-launch DRAM bytes of the tcgen05 GEMM family from the committed `ncu --set full` captures
-    (profiles/r1_ncu_gemm_b8_*.csv: 16 launches of one B=8 train step, forward and backward ranges)."""
+    (profiles/r2_ncu_gemm_{fwd,bwd}.csv: GEMM launches of the device-timed region of one B=8 train step; the round-1
+    captures if those are missing)."""
     import csv
     tot, n = 0.0, 0
-    for name in ("r1_ncu_gemm_b8_fwd.csv", "r1_ncu_gemm_b8_bwd.csv"):
+    names = ("r2_ncu_gemm_fwd.csv", "r2_ncu_gemm_bwd.csv")
+    if not all(os.path.exists(os.path.join(ROOT, "profiles", x)) for x in names):
+        names = ("r1_ncu_gemm_b8_fwd.csv", "r1_ncu_gemm_b8_bwd.csv")
+    for name in names:
         path = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(path):
             continue
@@ -383,18 +387,23 @@ def run_ours(args):
     # ---- roofline: instrument every tcgen05 GEMM launch of one more step --------------------------
     # (eager launches, and the two towers run one after the other on one stream: with the text tower on its side stream
     # the events around a GEMM would also count the time its CTAs wait for SMs held by the other tower's kernels)
-    # The timed loops are over: drop the CUDA graphs (their private pools hold one full set of saved activations, 1.7 GB
-    # per volume) before the eager step allocates its own.
-    import gc
-    clip.visual_transformer._graphs.clear()
-    getattr(bert, "__dict__", {}).pop("_ctk_graphs", None)
-    gc.collect()
-    torch.cuda.empty_cache()
-    clip.overlap_text_encoder = False
+    # The events around a launch must not also measure the host: the host needs ~45 ms to enqueue an eager step, about as
+    # long as the GPU needs to run it, so the GPU is first given two ordinary (graph-replayed, 7 ms of host time) steps
+    # to chew on and the instrumented step is enqueued behind them.  (A device-side sleep instead lets the clocks drop.)
+    big = B > 16
+    if big:
+        # large per-GPU batches: drop the CUDA graphs first (their private pools hold one full set of saved activations,
+        # 1.7 GB per volume) before the eager step allocates its own
+        import gc
+        clip.visual_transformer._graphs.clear()
+        getattr(bert, "__dict__", {}).pop("_ctk_graphs", None)
+        gc.collect()
+        torch.cuda.empty_cache()
+    else:
+        step(0)
+        step(1)
+    clip.overlap_text_encoder = False          # towers one after the other on one stream: no second stream competing for SMs
     ops.GEMM_PROFILE = []
-    # park the GPU for ~0.1 s first: the host needs ~40 ms to enqueue an eager step, and an event pair around a launch
-    # the GPU is already waiting for would also measure that wait
-    torch.cuda._sleep(int(0.12 * 1.9e9))
     step(0)
     torch.cuda.synchronize()
     prof = ops.GEMM_PROFILE
@@ -452,7 +461,7 @@ def run_ours(args):
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
                      "traffic_note": f"mean dram__bytes_read+write per launch over {traffic_n} GEMM launches of one B=8 step "
-                                     "(ncu --set full, profiles/r1_ncu_gemm_b8_*.csv)",
+                                     "(ncu --set full, profiles/r2_ncu_gemm_*.csv)",
                      "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": len(prof),
                      "gemm_share_of_step": gemm_ms / (ms_dev / args.steps),
                      "algorithmic_gflop_per_volume": gf_step, "ms_by_epilogue": by_epi},

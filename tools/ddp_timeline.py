@@ -47,15 +47,57 @@ def step():
     return float(ld["cl_loss"])
 
 
-for _ in range(5):
-    step()
+E2E = os.environ.get("E2E", "")           # "stored" / "fp32": bench.py's host-input pipeline instead of a resident batch
+if E2E:
+    from vit_exp_b200 import ops
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_vid = [torch.rand(B, 1, 240, 480, 480, generator=g).pin_memory() for _ in range(2)]
+    stored = [(v[:, 0] * 2 - 1).half().pin_memory() for v in host_vid]
+    NSLOT = 3
+    dev_vid = [torch.empty(B, 1, 240, 480, 480, device=dev) for _ in range(NSLOT)]
+    dev_st = [torch.empty(B, 240, 480, 480, dtype=torch.float16, device=dev) for _ in range(NSLOT)]
+    copy_stream, prep_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    done = [None] * NSLOT
+
+    def fill(slot, src):
+        with torch.cuda.stream(copy_stream):
+            if done[slot] is not None:
+                copy_stream.wait_event(done[slot])
+            if E2E == "fp32":
+                dev_vid[slot].copy_(host_vid[src], non_blocking=True)
+                return
+            dev_st[slot].copy_(stored[src], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            with torch.cuda.stream(prep_stream):
+                prep_stream.wait_event(ev)
+                for b in range(B):
+                    ops.volume_prep(dev_st[slot][b], dev_vid[slot][b])
+            copy_stream.wait_stream(prep_stream)
+
+    def run(k, first):
+        global vid
+        for i in range(first, first + k):
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            fill((i + 1) % NSLOT, (i + 1) % 2)
+            vid = dev_vid[i % NSLOT]
+            step()
+            ev = torch.cuda.Event()
+            ev.record()
+            done[i % NSLOT] = ev
+    fill(0, 0)
+    run(6, 0)
+else:
+    def run(k, first):
+        for _ in range(k):
+            step()
+    run(5, 0)
 torch.cuda.synchronize()
 dist.barrier()
 from torch.profiler import ProfilerActivity, profile
 
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    for _ in range(3):
-        step()
+    run(3, 6)
     torch.cuda.synchronize()
 if rank == 0:
     path = os.path.join(tempfile.gettempdir(), "ddp_trace.json")
@@ -70,6 +112,11 @@ if rank == 0:
         streams.setdefault(e["args"].get("stream"), []).append(e)
     for sid, lst in sorted(streams.items(), key=lambda kv: -sum(x["dur"] for x in kv[1])):
         print(f"  stream {sid}: {len(lst):5d} activities, busy {sum(x['dur'] for x in lst) / 1e3:8.2f} ms, e.g. {lst[len(lst) // 2]['name'][:70]}")
+    print("H2D copies > 1 MB:")
+    for e in ev:
+        if e["cat"] == "gpu_memcpy" and "HtoD" in e["name"] and e["args"].get("bytes", 0) > 1 << 20:
+            gb = e["args"]["bytes"] / 1e9
+            print(f"  at {(e['ts'] - t0) / 1e3:8.2f} ms  dur {e['dur'] / 1e3:7.2f} ms  {gb:.3f} GB  {gb / (e['dur'] / 1e6):6.1f} GB/s")
     print("NCCL kernels and step markers:")
     for e in ev:
         n = e["name"]

@@ -35,6 +35,7 @@ NSLOT = 3
 dev_vid = [torch.empty(B, 1, *bench.VOL, device=dev) for _ in range(NSLOT)]
 dev_st = [torch.empty(B, *bench.VOL, dtype=torch.float16, device=dev) for _ in range(NSLOT)]
 copy_stream = torch.cuda.Stream()
+prep_stream = torch.cuda.Stream()
 for s in range(NSLOT):
     dev_vid[s].copy_(host_vid[s % 2])
 
@@ -51,10 +52,15 @@ def step(image):
 def feed(slot, src):
     if args.mode == "fp32":
         dev_vid[slot].copy_(host_vid[src], non_blocking=True)
-    elif args.mode == "stored":
-        for b in range(B):
-            dev_st[slot][b].copy_(stored[src][b], non_blocking=True)
-            ops.volume_prep(dev_st[slot][b], dev_vid[slot][b])
+    elif args.mode == "stored":                      # bench.py's feed: one copy, preparation kernels on their own stream
+        dev_st[slot].copy_(stored[src], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        with torch.cuda.stream(prep_stream):
+            prep_stream.wait_event(ev)
+            for b in range(B):
+                ops.volume_prep(dev_st[slot][b], dev_vid[slot][b])
+        copy_stream.wait_stream(prep_stream)
 
 
 def pipeline(k):
