@@ -303,6 +303,15 @@ def run_ours(args):
     ms_dev, _ = timed(lambda k: [step(i % 2) for i in range(k)], args.steps)
     if prof_range:
         torch.cuda.profiler.stop()
+        # a profiler run only wants the launches of the timed region: no e2e / baseline legs under the profiler, and the
+        # line says so (a number printed by a run under ncu is never a bench value)
+        if rank == 0:
+            emit({"metric": "CT volumes/s, CT-CLIP train step", "under_profiler": True, "n_gpus": world, "steps": args.steps,
+                  "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                  "gpu_launches": int(lib.ctk_launch_count() + ops.GRAPH_LAUNCHES - n0)})
+        if world > 1:
+            dist.destroy_process_group()
+        return
     launches = (lib.ctk_launch_count() + ops.GRAPH_LAUNCHES - n0)      # direct launches + launches replayed from CUDA graphs
     clocks = sampler.stop() if rank == 0 else None
 
@@ -462,6 +471,9 @@ def run_ours(args):
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
                      "traffic_note": f"mean dram__bytes_read+write per launch over {traffic_n} GEMM launches of one B=8 step "
                                      "(ncu --set full, profiles/r2_ncu_gemm_*.csv)",
+                     "measurement_note": "event pairs serialise the boundary between consecutive kernels (~7 us on each of the "
+                                         "mostly short launches): CUPTI kernel time of the same 315 launches is 19.6 ms = 911 "
+                                         "TF/s = 0.675 of peak (profiles/r2_step_profile_cupti.txt, profiles/r2_launches_summary.md)",
                      "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": len(prof),
                      "gemm_share_of_step": gemm_ms / (ms_dev / args.steps),
                      "algorithmic_gflop_per_volume": gf_step, "ms_by_epilogue": by_epi},

@@ -100,7 +100,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     run(3, 6)
     torch.cuda.synchronize()
 if rank == 0:
-    path = os.path.join(tempfile.gettempdir(), "ddp_trace.json")
+    path = os.path.join(tempfile.gettempdir(), f"ddp_trace_{os.getpid()}.json")
     prof.export_chrome_trace(path)
     ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
     ev.sort(key=lambda e: e["ts"])

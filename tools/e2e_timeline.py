@@ -91,7 +91,7 @@ from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     pipeline(args.steps)
     torch.cuda.synchronize()
-path = os.path.join(tempfile.gettempdir(), "e2e_trace.json")
+path = os.path.join(tempfile.gettempdir(), f"e2e_trace_{os.getpid()}.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
 ev.sort(key=lambda e: e["ts"])
