@@ -47,7 +47,9 @@ unsigned long long ctk_launch_count(void);
  * Replaces every nn.Linear on the path: attention.py:52-57 (FeedForward), :123-129 (to_q,
  * to_kv, to_out), ctvit.py:173 (patch projection), and the matmuls autograd derives from them.
  * *_mn_major = 0: operand is [rows, K] with K contiguous; 1: operand is [K, rows] (rows
- * contiguous) - the layout of activations in a weight-gradient product.
+ * contiguous) - the layout of activations in a weight-gradient product.  Instantiated: (0, 0) every epilogue;
+ * (1, 1) BF16 / F32 / RESID_F32 / GEGLU / GEGLU_BWD / QKV / ATOMIC_F32 / ARGMAX; (a = 0, b = 1) - the input-gradient
+ * product dX = dY W with the weight W [K = out, N = in] as stored - BF16 / RESID_F32 / GEGLU_BWD / GELU_BWD.
  * ------------------------------------------------------------------------------------------ */
 typedef enum {
     CTK_EPI_BF16 = 0,      /* C bf16 = alpha * (acc + bias)                                        */
@@ -110,7 +112,8 @@ int ctk_cast_bf16(const float* src, void* dst, long long rows, long long cols, l
 int ctk_transpose_cast_bf16(const float* src, void* dst, long long rows, long long cols,
                             long long ld_dst, void* stream);
 /* same, but ONLY the columns [0, rows) of every dst row are written: dst may be a column slice of a wider matrix
- * (text tower: [Wq^T | Wk^T | Wv^T] packed side by side for the input gradient of the fused q|k|v projection). */
+ * (e.g. [Wq^T | Wk^T | Wv^T] packed side by side).  The shipped modules no longer need transposed weight copies - their
+ * input-gradient products read the [out, in] operand MN-major (b_mn_major = 1 below) - the entry stays for callers that do. */
 int ctk_transpose_cast_bf16_slice(const float* src, void* dst, long long rows, long long cols,
                                   long long ld_dst, void* stream);
 /* FeedForward W1 (2*inner, dim) fp32 -> interleaved bf16 (2*inner_pad, dim): for every block of

@@ -39,7 +39,7 @@ def test_scorer_vs_oracle(cuda_dev):
 
 
 def test_eval_graph_replay_matches_eager(cuda_dev):
-    """opt-in CUDA-graph replay of the no-grad eval forward (CTViT.eval_graphs): bit-identical to eager launches, across
+    """CUDA-graph replay of the no-grad eval forward (CTViT.eval_graphs, on by default): bit-identical to eager launches, across
     different input volumes and after a parameter update (the graph reads the fp32 masters each replay)."""
     from vit_exp_b200.transformer_maskgit import CTViT
     torch.manual_seed(0)
