@@ -320,3 +320,34 @@ def ctclip_loss(enc_text, enc_image, p: Params, b_local: Optional[int] = None):
 def forward_infer_logits(text_lat, image_lat, log_temp):
     """ct_clip.py:842-855: einsum('b d, b d -> b') * exp(temperature) with text b broadcast on image b=1."""
     return (text_lat * image_lat).sum(dim=-1) * log_temp.exp()
+
+
+# ------------------------------------------------------------------------------------------
+# legacy pooling of the original CT-CLIP checkpoints: CTCLIP.forward_old
+# ------------------------------------------------------------------------------------------
+def image_embeds_legacy(enc_image):
+    """ct_clip.py:1549,1566: mean over axis 1 of the encoded tokens (B, t, h, w, C), then flatten (h w C)."""
+    return enc_image.mean(dim=1).reshape(enc_image.shape[0], -1)
+
+
+def forward_old_latents(enc_text, enc_image, p: Params, text_valid_mask):
+    """ct_clip.py:1583-1626: CLS row / legacy image embedding, rows selected by `text_valid_mask` (B, 1) BEFORE the
+    projections (:1593-1594), to_text_latent / to_visual_latent (in_features = h*w*C), l2norm."""
+    keep = text_valid_mask.squeeze(1).bool()
+    text_embeds = enc_text[:, 0, :][keep, :]
+    image_embeds = image_embeds_legacy(enc_image)[keep, :]
+    return l2norm(text_embeds @ p["to_text_latent.weight"].T), l2norm(image_embeds @ p["to_visual_latent.weight"].T)
+
+
+def forward_old_similarity(enc_text, enc_image, p: Params, text_valid_mask):
+    """ct_clip.py:1655-1657 (return_loss=False): einsum('b d, b d -> b') * exp(temperature) over the valid rows."""
+    tl, il = forward_old_latents(enc_text, enc_image, p, text_valid_mask)
+    return (tl * il).sum(dim=-1) * p["temperature"].exp()
+
+
+def forward_old_loss(enc_text, enc_image, p: Params, text_valid_mask):
+    """ct_clip.py:1661-1768 single process, no multiview / MLM / SSL terms (weights 0 -> cl_loss_weight 1,
+    :1757-1761) and seg_loss 0: the same symmetric loss as the new forward over the VALID rows, divided by their
+    count (`bs_single_gpu = text_latents.shape[0]` is taken after the selection, :1661)."""
+    tl, il = forward_old_latents(enc_text, enc_image, p, text_valid_mask)
+    return clip_loss_reference_form(tl, il, p["temperature"], tl.shape[0]), tl, il

@@ -42,8 +42,25 @@ __global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict_
     }
 }
 
+// Short axis, wide rows - the legacy pooling of CTCLIP.forward_old (ct_clip.py:1549: mean over the n = 24 frames of
+// rows of h*w*C = 294 912 floats): one thread per float4 column, frames summed in index order.  Coalesced, no atomics,
+// dim/1024 x B CTAs (mean_pool_kernel above would put B CTAs on it).
+__global__ void __launch_bounds__(256)
+mean_frames_kernel(const float* __restrict__ x, float* __restrict__ pooled, int n, long long dim4) {
+    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= dim4) return;
+    const int b = blockIdx.y;
+    const float4* p = reinterpret_cast<const float4*>(x) + (long long)b * n * dim4 + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < n; ++t, p += dim4) {
+        const float4 v = __ldg(p);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float inv = 1.0f / (float)n;
+    reinterpret_cast<float4*>(pooled)[(long long)b * dim4 + c] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
 // ---------------------------------------------------------------- latent projection + l2norm
-// one CTA (256 threads) per sample
 // raw[b, j] = <W[j, :], x[b, :]>.  One warp per output row j holds W[j, :] in registers (read once, coalesced) and
 // sweeps the B input rows staged in shared memory; grid = dl / 8 CTAs (a B-CTA grid left 140 SMs idle and made every
 // CTA stream the whole weight matrix).  din <= 1024.
@@ -76,6 +93,87 @@ latent_raw_kernel(const float* __restrict__ x, long long x_stride, const float* 
             acc = warp_sum(acc);
             if (lane == 0 && j < dl) raw[(long long)(b0 + b) * dl + j] = acc;
         }
+    }
+}
+// din > 1024: the to_visual_latent of the original CT-CLIP checkpoints, Linear(294 912 -> 512) on the legacy pooling
+// (ct_clip.py:1614; scripts/run_zero_shot_latent.py:26-31) - 604 MB of fp32 weights against <= 8 input rows, bound by
+// the one pass over W.  CTA = 8 warps = LATW_ROWS output rows x 2 halves of a LATW_KC-float slice of K; per slice the
+// weight quads are requested first (8 x 16 B per lane in flight), then the input rows' slice is staged in shared
+// memory and swept.  Each output is summed in a fixed order (no split-K atomics): bitwise repeatable.
+constexpr int LATW_KC = 2048;
+constexpr int LATW_ROWS = 4;
+constexpr int LATW_Q = LATW_KC / 4 / 2 / 32;          // float4 per lane per slice = 8
+constexpr int LATW_XV = LAT_MAX_B * (LATW_KC / 4) / 256;                     // staged float4 per thread per slice = 16
+constexpr size_t LATW_SMEM = sizeof(float4) * LAT_MAX_B * (LATW_KC / 4);     // 64 KB
+__global__ void __launch_bounds__(256)
+latent_raw_wide_kernel(const float* __restrict__ x, long long x_stride, const float* __restrict__ W,
+                       float* __restrict__ raw, int B, int din, int dl) {
+    extern __shared__ float4 xs[];                    // [LAT_MAX_B][LATW_KC / 4]
+    __shared__ float part[LATW_ROWS][2][LAT_MAX_B];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = warp >> 1, half = warp & 1;
+    const int j = blockIdx.x * LATW_ROWS + r;
+    constexpr int QS = LATW_KC / 4;                   // quads per slice
+    for (int b0 = 0; b0 < B; b0 += LAT_MAX_B) {
+        const int nb = min(LAT_MAX_B, B - b0);
+        float acc[LAT_MAX_B];
+#pragma unroll
+        for (int bb = 0; bb < LAT_MAX_B; ++bb) acc[bb] = 0.f;
+        // One slice of K in registers: this warp's weight quads and this thread's share of the input rows' slice
+        // (all-zero past the end of K).  The requests for slice k+1 are issued before slice k is swept.
+        float4 w[LATW_Q], xv[LATW_XV];
+        auto request = [&](int k0, float4 (&wq)[LATW_Q]) {
+            const int nq = min(LATW_KC, din - k0) >> 2;           // valid quads of the slice (din % 4 == 0); <= 0 past the end
+            const float4* wrow = reinterpret_cast<const float4*>(W + (long long)(j < dl ? j : 0) * din + k0);
+#pragma unroll
+            for (int u = 0; u < LATW_Q; ++u) {
+                const int q = half * (QS / 2) + u * 32 + lane;
+                wq[u] = (j < dl && q < nq) ? __ldg(wrow + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < LATW_XV; ++i) {
+                const int t = i * 256 + threadIdx.x, bb = t / QS, q = t % QS;
+                xv[i] = (bb < nb && q < nq)
+                            ? *reinterpret_cast<const float4*>(x + (long long)(b0 + bb) * x_stride + k0 + 4 * q)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        request(0, w);
+        for (int k0 = 0; k0 < din; k0 += LATW_KC) {
+            __syncthreads();                                       // previous slice fully consumed
+#pragma unroll
+            for (int i = 0; i < LATW_XV; ++i) xs[i * 256 + threadIdx.x] = xv[i];
+            __syncthreads();
+            float4 wn[LATW_Q];
+            request(k0 + LATW_KC, wn);
+#pragma unroll
+            for (int bb = 0; bb < LAT_MAX_B; ++bb) {
+                if (bb < nb) {
+                    float a = acc[bb];
+#pragma unroll
+                    for (int u = 0; u < LATW_Q; ++u) {
+                        const float4 xr = xs[bb * QS + half * (QS / 2) + u * 32 + lane];
+                        a = fmaf(w[u].x, xr.x, a); a = fmaf(w[u].y, xr.y, a);
+                        a = fmaf(w[u].z, xr.z, a); a = fmaf(w[u].w, xr.w, a);
+                    }
+                    acc[bb] = a;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < LATW_Q; ++u) w[u] = wn[u];
+        }
+#pragma unroll
+        for (int bb = 0; bb < LAT_MAX_B; ++bb) {
+            const float v = warp_sum(acc[bb]);
+            if (lane == 0) part[r][half][bb] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < LATW_ROWS * LAT_MAX_B) {
+            const int r2 = threadIdx.x / LAT_MAX_B, bb = threadIdx.x % LAT_MAX_B;
+            const int j2 = blockIdx.x * LATW_ROWS + r2;
+            if (j2 < dl && bb < nb) raw[(long long)(b0 + bb) * dl + j2] = part[r2][0][bb] + part[r2][1][bb];
+        }
+        __syncthreads();
     }
 }
 // latent[b, :] = raw[b, :] / max(|raw[b, :]|, 1e-12) in place; rnorm[b] = the reciprocal (F.normalize, ct_clip.py:70-71)
@@ -130,11 +228,13 @@ latent_bwd_dx_kernel(const float* __restrict__ dlat, const float* __restrict__ l
     if (q == 0 && i < din) dx[(long long)b * dx_stride + i] = (part[0][ic] + part[1][ic]) + (part[2][ic] + part[3][ic]);
 }
 
-// dW[j, i] = sum_b draw[b, j] x[b, i]; one CTA per 8 output rows j
+// dW[j, i] = sum_b draw[b, j] x[b, i]; one CTA per 8 output rows j and `cols` columns i (grid.y; one slab when
+// din <= LAT_DW_COLS, 72 of them for the 294 912-wide projection of forward_old)
+constexpr int LAT_DW_COLS = 4096;
 __global__ void latent_bwd_dw_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
                                      const float* __restrict__ rnorm, const float* __restrict__ x,
                                      long long x_stride, float* __restrict__ dW, int B, int din,
-                                     int dl) {
+                                     int dl, int cols) {
     extern __shared__ float sm[];
     float* coef = sm;                 // [B]
     float* draw = sm + B;             // [8][B]
@@ -156,7 +256,8 @@ __global__ void latent_bwd_dw_kernel(const float* __restrict__ dlat, const float
                                   : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < din; i += blockDim.x) {
+    const int i_end = min(din, (int)(blockIdx.y + 1) * cols);
+    for (int i = blockIdx.y * cols + threadIdx.x; i < i_end; i += blockDim.x) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int b = 0; b < B; ++b) {
             const float xv = x[(long long)b * x_stride + i];
@@ -359,6 +460,12 @@ extern "C" int ctk_mean_pool_fwd(const float* x, float* pooled, int B, long long
                 "mean_pool: bad args");
     CTK_REQUIRE(CTK_ALIGNED(x, 16), CTK_ERR_ALIGN, "mean_pool: x must be 16-byte aligned");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    if (n <= 256 && dim >= 2048 && CTK_ALIGNED(pooled, 16)) {      // short axis, wide rows: CTCLIP.forward_old's pooling
+        const long long dim4 = dim / 4;
+        mean_frames_kernel<<<dim3((unsigned)((dim4 + 255) / 256), B), 256, 0, s>>>(x, pooled, (int)n, dim4);
+        CTK_LAUNCH_CHECK();
+        return CTK_OK;
+    }
     CTK_CUDA(cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)B * dim, s));
     const long long tpb = 128;
     dim3 grid((unsigned)((n + tpb - 1) / tpb), B);
@@ -374,9 +481,15 @@ extern "C" int ctk_latent_fwd(const float* x, long long x_stride, const float* W
     CTK_REQUIRE(x && W && latent && rnorm && B > 0 && din > 0 && dl > 0, CTK_ERR_SHAPE,
                 "latent_fwd: bad args");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    CTK_REQUIRE(din <= 1024, CTK_ERR_SHAPE, "latent_fwd: din %d > 1024", din);
-    const size_t sm = sizeof(float) * (size_t)din * (size_t)(B < LAT_MAX_B ? B : LAT_MAX_B);
-    latent_raw_kernel<<<(dl + 7) / 8, 256, sm, s>>>(x, x_stride, W, latent, B, din, dl);
+    if (din <= 1024) {
+        const size_t sm = sizeof(float) * (size_t)din * (size_t)(B < LAT_MAX_B ? B : LAT_MAX_B);
+        latent_raw_kernel<<<(dl + 7) / 8, 256, sm, s>>>(x, x_stride, W, latent, B, din, dl);
+    } else {
+        CTK_REQUIRE(din % 4 == 0 && x_stride % 4 == 0 && CTK_ALIGNED(x, 16) && CTK_ALIGNED(W, 16), CTK_ERR_ALIGN,
+                    "latent_fwd: din %d > 1024 needs din and the row stride to be multiples of 4 and 16-byte aligned x, W", din);
+        CTK_SET_MAX_SMEM(latent_raw_wide_kernel, LATW_SMEM);
+        latent_raw_wide_kernel<<<(dl + LATW_ROWS - 1) / LATW_ROWS, 256, LATW_SMEM, s>>>(x, x_stride, W, latent, B, din, dl);
+    }
     CTK_LAUNCH_CHECK();
     latent_norm_kernel<<<B, 256, 0, s>>>(latent, rnorm, dl);
     CTK_LAUNCH_CHECK();
@@ -400,8 +513,9 @@ extern "C" int ctk_latent_bwd(const float* dlatent, const float* latent, const f
     if (dW) {
         const size_t sm = sizeof(float) * (size_t)(9 * B);
         CTK_REQUIRE(sm <= 48 * 1024, CTK_ERR_SHAPE, "latent_bwd: batch too large");
-        latent_bwd_dw_kernel<<<(dl + 7) / 8, 256, sm, s>>>(dlatent, latent, rnorm, x, x_stride, dW,
-                                                           B, din, dl);
+        const int cols = din <= LAT_DW_COLS ? din : LAT_DW_COLS;
+        latent_bwd_dw_kernel<<<dim3((dl + 7) / 8, (din + cols - 1) / cols), 256, sm, s>>>(dlatent, latent, rnorm, x,
+                                                                                          x_stride, dW, B, din, dl, cols);
         CTK_LAUNCH_CHECK();
     }
     return CTK_OK;

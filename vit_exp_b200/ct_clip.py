@@ -56,19 +56,26 @@ class AllGather(torch.autograd.Function):
 
 class _ClipHead(torch.autograd.Function):
     """Fused contrastive head. Inputs: CLS rows of the text encoder output, encoded image tokens
-    (B, t, h, w, d), the two projection weights and the log-temperature."""
+    (B, t, h, w, d), the two projection weights and the log-temperature.
+
+    `frames_pool` selects the pooling of `CTCLIP.forward_old` (ct_clip.py:1549,1566: mean over the t axis only, the
+    (h w d) rest flattened into the projection's input) instead of the mean over all tokens (ct_clip.py:1297);
+    `valid` (int64 indices, or None) keeps those rows of both towers before the projections (ct_clip.py:1593-1594)."""
 
     @staticmethod
-    def forward(ctx, text_cls, tokens, w_text, w_vis, temperature, accelerator):
+    def forward(ctx, text_cls, tokens, w_text, w_vis, temperature, accelerator, frames_pool=False, valid=None):
         B = text_cls.shape[0]
-        dim = tokens.shape[-1]
-        n_tok = tokens.numel() // (B * dim)
+        n_pool = tokens.shape[1] if frames_pool else tokens.numel() // (B * tokens.shape[-1])
+        width = tokens.numel() // (B * n_pool)
         text_cls = text_cls.float()
         if text_cls.stride(-1) != 1:
             text_cls = text_cls.contiguous()
-        pooled = ops.mean_pool(tokens.reshape(B, n_tok, dim).contiguous())     # ct_clip.py:1297 (pool first)
+        pooled = ops.mean_pool(tokens.reshape(B, n_pool, width).contiguous())  # ct_clip.py:1297 (pool first) / :1549
+        if valid is not None:
+            text_cls, pooled = text_cls.index_select(0, valid), pooled.index_select(0, valid)
         il, rn_i = ops.latent_fwd(pooled, w_vis)                               # ct_clip.py:1290,1316
         tl, rn_t = ops.latent_fwd(text_cls, w_text)                            # ct_clip.py:1313-1316
+        b_local = tl.shape[0]
         world, rank = accelerator.num_processes, accelerator.process_index
         if world > 1:
             packed = torch.cat([tl, il], dim=1)                                 # one gather instead of two
@@ -78,25 +85,33 @@ class _ClipHead(torch.autograd.Function):
         else:
             T, I = tl, il
         lt = temperature.detach().reshape(1).float()
-        out, d_local = ops.clip_loss_fwd_bwd(T, I, lt, b_local=B, row0=rank * B)
-        ctx.save_for_backward(text_cls, pooled, w_text, w_vis, tl, il, rn_t, rn_i, out, d_local)
+        out, d_local = ops.clip_loss_fwd_bwd(T, I, lt, b_local=b_local, row0=rank * b_local)
+        ctx.save_for_backward(text_cls, pooled, w_text, w_vis, tl, il, rn_t, rn_i, out, d_local, valid)
         ctx.tok_shape = tuple(tokens.shape)
-        ctx.n_tok = n_tok
+        ctx.n_pool = n_pool
+        ctx.frames_pool = frames_pool
+        ctx.batch = B
         ctx.mark_non_differentiable(tl, il)
         return out[0].clone(), tl, il
 
     @staticmethod
     def backward(ctx, gloss, _gtl, _gil):
-        text_cls, pooled, w_text, w_vis, tl, il, rn_t, rn_i, out, d_local = ctx.saved_tensors
+        text_cls, pooled, w_text, w_vis, tl, il, rn_t, rn_i, out, d_local, valid = ctx.saved_tensors
         d_local = d_local * gloss
         dwt, dcls = ops.latent_bwd(d_local[0].contiguous(), tl, rn_t, text_cls, w_text)
         dwv, dpool = ops.latent_bwd(d_local[1].contiguous(), il, rn_i, pooled, w_vis)
-        B, dim = dpool.shape
-        # mean-pool backward: every token receives dpooled / n; left as a stride-0 expand so the
+        if valid is not None:                     # rows that were not selected receive no gradient
+            dcls = dcls.new_zeros(ctx.batch, dcls.shape[1]).index_copy_(0, valid, dcls)
+            dpool = dpool.new_zeros(ctx.batch, dpool.shape[1]).index_copy_(0, valid, dpool)
+        B = ctx.batch
+        # mean-pool backward: every pooled-over position receives dpooled / n; left as a stride-0 expand so the
         # encoder backward can consume it without materialising B*n*dim floats
-        dtok = (dpool / ctx.n_tok).view(B, *([1] * (len(ctx.tok_shape) - 2)), dim).expand(ctx.tok_shape)
+        if ctx.frames_pool:
+            dtok = (dpool / ctx.n_pool).view(B, 1, *ctx.tok_shape[2:]).expand(ctx.tok_shape)
+        else:
+            dtok = (dpool / ctx.n_pool).view(B, *([1] * (len(ctx.tok_shape) - 2)), dpool.shape[1]).expand(ctx.tok_shape)
         dtemp = (out[1] * gloss).reshape(())
-        return dcls, dtok, dwt, dwv, dtemp, None
+        return dcls, dtok, dwt, dwv, dtemp, None, None, None
 
 
 class DeferredFloat:
@@ -333,9 +348,22 @@ class CTCLIP(nn.Module):
             return loss, {"cl_loss": DeferredFloat(loss)}
         return loss, {"cl_loss": loss.item()}      # the reference also syncs here (ct_clip.py:1384)
 
+    def _frames_pool(self, enc_image) -> bool:
+        """True when `to_visual_latent` was built for the pooling of the original CT-CLIP checkpoints
+        (`dim_image = h*w*C = 294912`, scripts/run_zero_shot_latent.py:26-31; ct_clip.py:1549,1566) rather than for
+        the token mean (`dim_image = C`, ct_clip.py:1286-1297)."""
+        din = self.to_visual_latent.in_features
+        if din == enc_image.shape[-1]:
+            return False
+        per_frame = enc_image[0, 0].numel()
+        assert din == per_frame, (f"to_visual_latent expects {din} inputs; the encoder yields tokens of width "
+                                  f"{enc_image.shape[-1]} (token mean) or {per_frame} per frame (forward_old pooling)")
+        return True
+
     @torch.no_grad()
     def latents(self, text=None, image=None, buffer_text_embed=None, buffer_image_embed=None):
-        """l2-normalised (text_latents, image_latents); either side may be None."""
+        """l2-normalised (text_latents, image_latents); either side may be None.  The image pooling follows the
+        width of `to_visual_latent` (see `_frames_pool`), so checkpoints of either generation load and score."""
         tl = il = None
         if text is not None or buffer_text_embed is not None:
             emb = buffer_text_embed if buffer_text_embed is not None else \
@@ -345,10 +373,69 @@ class CTCLIP(nn.Module):
         if image is not None or buffer_image_embed is not None:
             enc = buffer_image_embed if buffer_image_embed is not None else \
                 self.visual_transformer(image, return_encoded_tokens=True)
-            B, dim = enc.shape[0], enc.shape[-1]
-            pooled = ops.mean_pool(enc.reshape(B, -1, dim).contiguous().float())
-            il, _ = ops.latent_fwd(pooled, self.to_visual_latent.weight)
+            il, _ = ops.latent_fwd(self._pool_tokens(enc), self.to_visual_latent.weight)
         return tl, il
+
+    def _pool_tokens(self, enc):
+        B, dim = enc.shape[0], enc.shape[-1]
+        if self._frames_pool(enc):
+            return ops.mean_pool(enc.reshape(B, enc.shape[1], -1).contiguous().float())      # ct_clip.py:1549,1566
+        return ops.mean_pool(enc.reshape(B, -1, dim).contiguous().float())                   # ct_clip.py:1286-1297
+
+    def forward_old(self, text, image, device=None, return_loss=False, return_loss_dict=False, return_encodings=False,
+                    return_latents=False, use_seg=False, seg_mask=None, seg_valid_mask=None, text_valid_mask=None,
+                    seg_weight=1.0, accelerator=None, freeze_image_encoder=False, freeze_text_encoder=False,
+                    text_to_image=True, aug_text=None, aug_image=None):
+        """ct_clip.py:1392-1778, the forward of the original CT-CLIP checkpoints: image embedding = mean over the t
+        axis of the encoded tokens, flattened (h w C) (`dim_image = 294912` for the full-size encoder, :1549,1566),
+        rows of both towers selected by `text_valid_mask` (B, 1) before the projections (:1593-1594).
+
+          return_encodings -> (enc_text, image embedding)                               (:1572-1573)
+          return_latents   -> (text_latents, image_latents, encoded tokens)             (:1638-1642)
+          neither, no loss -> exp(temperature) * <text_latent_b, image_latent_b>        (:1655-1657)
+          return_loss      -> the symmetric contrastive loss over the valid rows, divided by their count
+                              (:1661-1768; with return_loss_dict also {'cl_loss', 'loss_total'})
+
+        Outside this path, as in `forward`: segmentation (`use_seg`), multiview augmentations, MLM / visual SSL.  The
+        reference's loss branch reads `seg_loss` even when `use_seg` is off (:1766, a NameError there); here that term
+        is 0.  With at most one valid report the reference returns the segmentation loss alone (:1600-1608): an error
+        here.  The three inference modes run without autograd."""
+        assert not use_seg and seg_mask is None, "segmentation heads are outside the contrastive hot path"
+        assert aug_text is None and aug_image is None, "multiview augmentations are outside the contrastive hot path"
+        assert text_valid_mask is not None, "text_valid_mask (B, 1) is required (ct_clip.py:1593)"
+        keep = text_valid_mask.reshape(text_valid_mask.shape[0], -1)[:, 0].bool()
+        keep_host = keep if keep.device.type == "cpu" else keep.cpu()       # the reference's boolean indexing syncs too
+        valid = None if bool(keep_host.all()) else torch.nonzero(keep_host).squeeze(1).to(image.device)
+        if not return_loss:
+            with torch.no_grad():                           # towers as in `latents` / `forward_infer`
+                enc_text = self.text_transformer(text.input_ids, attention_mask=text.attention_mask)[0]
+                enc_image = self.visual_transformer(image, return_encoded_tokens=True)
+                assert self._frames_pool(enc_image), "forward_old needs dim_image = h*w*C (ct_clip.py:1566,1614)"
+                embeds = ops.mean_pool(enc_image.reshape(enc_image.shape[0], enc_image.shape[1], -1).contiguous().float())
+                if return_encodings:
+                    return enc_text, embeds
+                cls = enc_text[:, 0, :].float()
+                if valid is not None:
+                    cls, embeds = cls.index_select(0, valid), embeds.index_select(0, valid)
+                tl, _ = ops.latent_fwd(cls, self.to_text_latent.weight)
+                il, _ = ops.latent_fwd(embeds, self.to_visual_latent.weight)
+                if return_latents:
+                    return tl, il, enc_image
+                lt = self.temperature.detach().reshape(1).float()
+                return torch.cat([ops.pair_logits(tl[i:i + 1], il[i], lt) for i in range(tl.shape[0])])
+        assert accelerator is not None, "accelerator is not provided"
+        n_valid = keep_host.numel() if valid is None else valid.numel()
+        if n_valid <= 1:
+            raise ValueError("forward_old: the contrastive loss needs more than one valid report; the reference falls "
+                             "back to the segmentation loss here (ct_clip.py:1600-1608), which is outside this path")
+        enc_text, enc_image = self._encode_both(text, image)
+        assert self._frames_pool(enc_image), "forward_old needs dim_image = h*w*C (ct_clip.py:1566,1614)"
+        loss, _, _ = _ClipHead.apply(enc_text[:, 0, :], enc_image, self.to_text_latent.weight,
+                                     self.to_visual_latent.weight, self.temperature, accelerator, True, valid)
+        if not return_loss_dict:
+            return loss
+        value = DeferredFloat(loss) if self.config.get("defer_loss_read", False) else loss.item()
+        return loss, {"cl_loss": value, "loss_total": value}
 
     def forward_infer(self, text, image, buffer_text_embed=None, buffer_image_embed=None):
         """ct_clip.py:792-855: exp(temperature) * <text latent_p, image latent> for each prompt p
