@@ -75,7 +75,8 @@ def emit(line):
 def gemm_traffic_sample():
     """Per-launch DRAM bytes of the tcgen05 GEMM family from the committed `ncu --set full` captures
     (profiles/r2_ncu_gemm_{fwd,bwd}.csv: GEMM launches of the device-timed region of one B=8 train step; the round-1
-    captures if those are missing)."""
+    captures if those are missing - round 2's `--set full` run was lost to the copy-back size limit, profiles/README.md).
+    Returns (mean bytes per launch, launches, the files used)."""
     import csv
     tot, n = 0.0, 0
     names = ("r2_ncu_gemm_fwd.csv", "r2_ncu_gemm_bwd.csv")
@@ -94,7 +95,7 @@ def gemm_traffic_sample():
                 continue
             tot += float(r[ir]) * scale.get(unit[ir], 1.0) + float(r[iw]) * scale.get(unit[iw], 1.0)
             n += 1
-    return (tot / n, n) if n else (None, 0)
+    return (tot / n, n, names) if n else (None, 0, ())
 
 
 def measured_peaks():
@@ -425,7 +426,7 @@ def run_ours(args):
     peak_tf, peak_hbm, peak_src = measured_peaks()
     gf_step = GF_GEMM_STEP + (GF_TEXT_GEMM_STEP if args.text_tower == "ctk" else 0.0)
     achieved_tf = gf_step * B / gemm_ms                                        # GFLOP / ms == TFLOP/s
-    traffic, traffic_n = gemm_traffic_sample()
+    traffic, traffic_n, traffic_files = gemm_traffic_sample()
 
     if rank != 0:
         if world > 1:
@@ -470,7 +471,9 @@ def run_ours(args):
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
                      "traffic_note": f"mean dram__bytes_read+write per launch over {traffic_n} GEMM launches of one B=8 step "
-                                     "(ncu --set full, profiles/r2_ncu_gemm_*.csv)",
+                                     f"(ncu --set full: {', '.join('profiles/' + f for f in traffic_files) or 'no capture found'}; "
+                                     "the round-1 captures predate the packed-fp32 epilogues and the mixed-major "
+                                     "input-gradient products, which changed launch times but not operand bytes)",
                      "measurement_note": "event pairs serialise the boundary between consecutive kernels (~7 us on each of the "
                                          "mostly short launches): CUPTI kernel time of the same 315 launches is 19.6 ms = 911 "
                                          "TF/s = 0.675 of peak (profiles/r2_step_profile_cupti.txt, profiles/r2_launches_summary.md)",
