@@ -104,7 +104,7 @@ def test_forward_old_loss_and_gradients_match_reference(doubles, gold):
     clip.train()
     loss, ld = clip.forward_old(text, g["video"], None, return_loss=True, return_loss_dict=True,
                                 text_valid_mask=g["valid_some"], accelerator=CC.TorchDistAccelerator())
-    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    assert abs(loss.item() - g["loss"].item()) < 1e-5
     assert ld["cl_loss"] == ld["loss_total"] and abs(ld["cl_loss"] - g["cl_loss"]) < 1e-5
     loss.backward()
     assert _rel(clip.to_text_latent.weight.grad, g["grad_to_text_latent"]) < 1e-4
@@ -168,3 +168,72 @@ def test_forward_old_with_bf16_operands(monkeypatch, gold):
     clip, vit, bert, text = _clip_from(gold)
     agree = forward_old_checks.run(clip, vit, bert, text, gold["video"], gold, CC.TorchDistAccelerator(), None)
     assert agree >= 0.9
+
+
+# ------------------------------------------------------------------------------------------
+# two ranks (gloo): each rank masks out a different report; the gathered loss and the local gradients against the
+# single-process oracle on the concatenated valid rows
+# ------------------------------------------------------------------------------------------
+def _two_rank_inputs():
+    g = torch.Generator().manual_seed(77)
+    world, B, t, h, w, dim, dt, dl = 2, 3, 4, 2, 3, 8, 12, 6
+    return dict(world=world, B=B,
+                tokens=torch.randn(world, B, t, h, w, dim, generator=g), cls=torch.randn(world, B, dt, generator=g),
+                wt=torch.randn(dl, dt, generator=g) * 0.3, wv=torch.randn(dl, h * w * dim, generator=g) * 0.15,
+                temp=torch.tensor(0.4), valid=[torch.tensor([0, 2]), torch.tensor([1, 2])])
+
+
+def _two_rank_worker(rank, world, port, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import emulated_ops
+    from vit_exp_b200 import ct_clip
+    ct_clip.ops = emulated_ops
+    d = _two_rank_inputs()
+    leaves = [v.clone().requires_grad_() for v in (d["cls"][rank], d["tokens"][rank], d["wt"], d["wv"], d["temp"])]
+    loss, tl, il = ct_clip._ClipHead.apply(*leaves, ct_clip.TorchDistAccelerator(), True, d["valid"][rank])
+    loss.backward()
+    torch.save(dict(loss=loss.detach(), tl=tl, il=il, grads=[v.grad for v in leaves]), f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_forward_old_head_two_ranks(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "old")
+    mp.spawn(_two_rank_worker, args=(2, port, out), nprocs=2, join=True)
+    res = [torch.load(f"{out}.{r}", weights_only=False) for r in range(2)]
+    d = _two_rank_inputs()
+    # single process: every rank's inputs (and its own replica of the shared weights) as leaves of ONE global loss
+    leaves = [[v.clone().requires_grad_() for v in (d["cls"][r], d["tokens"][r], d["wt"], d["wv"], d["temp"])] for r in range(2)]
+    T, I = [], []
+    for r in range(2):
+        cls, tok, wt, wv, _ = leaves[r]
+        mask = torch.zeros(d["B"], 1)
+        mask[d["valid"][r]] = 1
+        tl, il = O.forward_old_latents(cls[:, None, :], tok, {"to_text_latent.weight": wt, "to_visual_latent.weight": wv}, mask)
+        assert _rel(res[r]["tl"], tl) < 1e-5 and _rel(res[r]["il"], il) < 1e-5
+        T.append(tl)
+        I.append(il)
+    n_valid = len(d["valid"][0])
+    for r in range(2):                       # every rank differentiates the replicated global loss through ITS temperature
+        for v in leaves[0] + leaves[1]:
+            v.grad = None
+        loss = O.clip_loss_reference_form(torch.cat(T), torch.cat(I), leaves[r][4], n_valid)     # / bs_single_gpu (:1661,1747)
+        loss.backward(retain_graph=True)
+        assert abs(res[r]["loss"].item() - loss.item()) < 1e-6
+        for name, got, ref in zip(("cls", "tokens", "w_text", "w_vis", "temperature"), res[r]["grads"], leaves[r]):
+            assert _rel(got, ref.grad) < 1e-4, (r, name)
+        masked = [i for i in range(d["B"]) if i not in d["valid"][r].tolist()]
+        assert res[r]["grads"][1][masked].abs().max() == 0
