@@ -231,10 +231,15 @@ int ctk_vq_ema_update(const float* xn_f32, const long long* ind, float* cluster_
  * Contrastive head (ct_clip.py:1280-1388, distributed.py:9-20).
  * ------------------------------------------------------------------------------------------ */
 /* pooled fp32 [B, dim] = mean over n tokens of x fp32 [B, n, dim]  (ct_clip.py:1297, applied
- * before the bias-free projection, which commutes with the mean). */
+ * before the bias-free projection, which commutes with the mean).  Also the pooling of CTCLIP.forward_old
+ * (ct_clip.py:1549,1566: mean over the frame axis, n = t = 24, dim = h*w*C = 294 912 - the flatten is the layout);
+ * dim % 4 == 0, x 16-byte aligned. */
 int ctk_mean_pool_fwd(const float* x, float* pooled, int B, long long n, int dim, void* stream);
 /* latent fp32 [B, dl] = l2norm(x[B, din] . W[dl, din]^T)  (ct_clip.py:1290,1313-1316, eps 1e-12);
- * x rows are x_stride floats apart (CLS rows of the text encoder output). rnorm fp32 [B]. */
+ * x rows are x_stride floats apart (CLS rows of the text encoder output). rnorm fp32 [B].
+ * din > 1024 - to_visual_latent of the original checkpoints, Linear(294912, 512) on forward_old's pooling
+ * (ct_clip.py:1614) - additionally needs din % 4 == 0, x_stride % 4 == 0 and 16-byte aligned x, W; every output is
+ * summed in a fixed order (bitwise repeatable). */
 int ctk_latent_fwd(const float* x, long long x_stride, const float* W, float* latent, float* rnorm,
                    int B, int din, int dl, void* stream);
 /* dW fp32 [dl, din] and dx fp32 [B, din] (row pitch dx_stride) are overwritten; either may be NULL. */
